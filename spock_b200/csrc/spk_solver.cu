@@ -1,0 +1,974 @@
+// spk_solver.cu -- handle, operator orchestration, Chambolle-Pock / SuperMann loops and the C ABI
+// (include/spock_b200.h).  Reference citations are file:line under /root/reference/src.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/spock_b200.h"
+#include "spk_kernels.cuh"
+#include "spk_offline.h"
+
+#ifdef SPK_HOST_EMU
+thread_local spk_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local std::vector<unsigned char> spk_emu_smem;
+#endif
+
+// ------------------------------------------------------------------------------------------------ errors
+
+static thread_local std::string g_last_error;
+const char *spk_last_error(void) { return g_last_error.c_str(); }
+int spk_version(void) { return 100; }
+
+static int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define SPK_TRY(expr)            \
+  do {                           \
+    const int rc_ = (expr);      \
+    if (rc_ != SPK_OK) return rc_; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ runtime shims
+
+#ifndef SPK_HOST_EMU
+#define RT_CHECK(call)                                                                          \
+  do {                                                                                          \
+    const cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(SPK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+static int rt_malloc(void **p, size_t bytes) {
+  const cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail(SPK_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  return SPK_OK;
+}
+static void rt_free(void *p) { cudaFree(p); }
+static int rt_h2d(void *dst, const void *src, size_t bytes, spk_stream_t s) {
+  RT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+  RT_CHECK(cudaStreamSynchronize(s));
+  return SPK_OK;
+}
+static int rt_d2h(void *dst, const void *src, size_t bytes, spk_stream_t s) {
+  RT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  RT_CHECK(cudaStreamSynchronize(s));
+  return SPK_OK;
+}
+static int rt_d2d(void *dst, const void *src, size_t bytes, spk_stream_t s) {
+  RT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+  return SPK_OK;
+}
+static int rt_memset(void *dst, int val, size_t bytes, spk_stream_t s) {
+  RT_CHECK(cudaMemsetAsync(dst, val, bytes, s));
+  return SPK_OK;
+}
+static int rt_sync(spk_stream_t s) {
+  RT_CHECK(cudaStreamSynchronize(s));
+  return SPK_OK;
+}
+static int rt_launch_check() {
+  RT_CHECK(cudaGetLastError());
+  return SPK_OK;
+}
+#else
+static int rt_malloc(void **p, size_t bytes) {
+  *p = calloc(bytes ? bytes : 16, 1);
+  return *p ? SPK_OK : fail(SPK_ERR_ALLOC, "calloc failed");
+}
+static void rt_free(void *p) { free(p); }
+static int rt_h2d(void *dst, const void *src, size_t bytes, spk_stream_t) { memcpy(dst, src, bytes); return SPK_OK; }
+static int rt_d2h(void *dst, const void *src, size_t bytes, spk_stream_t) { memcpy(dst, src, bytes); return SPK_OK; }
+static int rt_d2d(void *dst, const void *src, size_t bytes, spk_stream_t) { memmove(dst, src, bytes); return SPK_OK; }
+static int rt_memset(void *dst, int val, size_t bytes, spk_stream_t) { memset(dst, val, bytes); return SPK_OK; }
+static int rt_sync(spk_stream_t) { return SPK_OK; }
+static int rt_launch_check() { return SPK_OK; }
+#endif
+
+static double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+
+enum { PC_S1_BWD = 0, PC_S1_FWD, PC_LLT, PC_PROX_H, PC_S2, PC_VEC, PC_FUSED_BWD, PC_FUSED_FWD, PC_COUNT };
+#define AA_M 3  // ANDERSON_BUFFER_SIZE (anderson.jl:6, spock.jl:108)
+
+struct ProfSection {
+  int cls;
+#ifndef SPK_HOST_EMU
+  cudaEvent_t e0, e1;
+#else
+  double t0, t1;
+#endif
+};
+
+struct spk_handle {
+  SpkDims D;
+  SpkPtrs P;
+  int alg = SPK_CP;
+  double L_norm = 10.0;
+  int device = 0;
+  spk_stream_t stream = 0;
+  std::vector<void *> allocs;
+  int64_t bytes = 0;
+  int64_t launches = 0;
+  SpkFactorTable table;      // per-stage factors (host copy, also serves spk_get_factors)
+  std::vector<double> ls_host;
+  // iterate vectors: every "zv" buffer holds [z (nz) | v (nv)] contiguously
+  double *zv = nullptr, *zvbar = nullptr, *zv_old = nullptr, *dzv = nullptr, *xi12 = nullptr, *zw = nullptr,
+         *xi = nullptr, *ric_q = nullptr, *ric_d = nullptr, *x0 = nullptr;
+  // SuperMann / Anderson (model.jl:137-226)
+  double *rzv = nullptr, *rzv_old = nullptr, *drzv = nullptr, *dir = nullptr, *wu = nullptr, *wubar = nullptr,
+         *rwu = nullptr, *ws_rho = nullptr, *ws_L = nullptr;
+  double *MP[AA_M] = {nullptr, nullptr, nullptr}, *MR[AA_M] = {nullptr, nullptr, nullptr},
+         *AQ[AA_M] = {nullptr, nullptr, nullptr};
+  double aaR[AA_M * AA_M];  // column-major upper triangular (spock.jl:200)
+  double res_0[2];
+  double last_xi1 = NAN, last_xi2 = NAN;
+  // reductions
+  double *d_partial = nullptr, *d_scal = nullptr;
+  double h_scal[32];
+  int red_blocks = 0;
+  // profiling
+  bool prof_on = false;
+  double prof_ms[PC_COUNT];
+  int64_t prof_launches[PC_COUNT];
+  std::vector<ProfSection> prof_open;
+#ifndef SPK_HOST_EMU
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+#endif
+  double *z() { return zv; }
+  double *v() { return zv + D.nz; }
+};
+
+static int dev_alloc(spk_handle *h, double **p, long count, bool zero = true) {
+  void *q = nullptr;
+  const size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(double);
+  SPK_TRY(rt_malloc(&q, bytes));
+  h->allocs.push_back(q);
+  h->bytes += (int64_t)bytes;
+  *p = (double *)q;
+  if (zero) SPK_TRY(rt_memset(q, 0, bytes, h->stream));
+  return SPK_OK;
+}
+
+static int upload(spk_handle *h, double **p, const double *src, long count) {
+  SPK_TRY(dev_alloc(h, p, count, false));
+  return rt_h2d(*p, src, (size_t)count * sizeof(double), h->stream);
+}
+
+// ------------------------------------------------------------------------------------------------ profiling sections
+
+struct ProfScope {
+  spk_handle *h;
+  bool on;
+  ProfSection s;
+  ProfScope(spk_handle *h_, int cls) : h(h_), on(h_->prof_on) {
+    if (!on) return;
+    s.cls = cls;
+#ifndef SPK_HOST_EMU
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    s.e0 = get();
+    s.e1 = get();
+    cudaEventRecord(s.e0, h->stream);
+#else
+    s.t0 = wall_ms();
+#endif
+  }
+  ~ProfScope() {
+    if (!on) return;
+#ifndef SPK_HOST_EMU
+    cudaEventRecord(s.e1, h->stream);
+#else
+    s.t1 = wall_ms();
+#endif
+    h->prof_open.push_back(s);
+  }
+};
+
+static void prof_harvest(spk_handle *h) {
+#ifndef SPK_HOST_EMU
+  if (!h->prof_open.empty()) cudaStreamSynchronize(h->stream);
+#endif
+  for (auto &s : h->prof_open) {
+#ifndef SPK_HOST_EMU
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.e0, s.e1);
+    h->prof_ms[s.cls] += ms;
+    h->ev_pool.push_back(s.e0);
+    h->ev_pool.push_back(s.e1);
+#else
+    h->prof_ms[s.cls] += s.t1 - s.t0;
+#endif
+  }
+  h->prof_open.clear();
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+
+static inline int pow2_lanes(int rows) {
+#ifdef SPK_HOST_EMU
+  (void)rows;
+  return 1;
+#else
+  int l = 1;
+  while (l < rows && l < 32) l <<= 1;
+  return l;
+#endif
+}
+static inline int elem_block() { return SPK_EMU ? 1 : 256; }
+static inline unsigned grid_for(long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+#define SPK_LANES_SWITCH(L, ...)                                   \
+  switch (L) {                                                     \
+    case 1: { constexpr int LANES = 1; __VA_ARGS__; } break;        \
+    case 2: { constexpr int LANES = 2; __VA_ARGS__; } break;        \
+    case 4: { constexpr int LANES = 4; __VA_ARGS__; } break;        \
+    case 8: { constexpr int LANES = 8; __VA_ARGS__; } break;        \
+    case 16: { constexpr int LANES = 16; __VA_ARGS__; } break;      \
+    default: { constexpr int LANES = 32; __VA_ARGS__; } break;      \
+  }
+
+#define COUNT_LAUNCH(h, cls) \
+  do { (h)->launches++; if ((h)->prof_on) (h)->prof_launches[cls]++; } while (0)
+
+// out = alpha * L' v + beta * in   (spock_mul! with trans = true, implicit_l.jl:451-481)
+static int op_Lt(spk_handle *h, const double *v, double alpha, double beta, const double *in, double *out) {
+  ProfScope ps(h, PC_LLT);
+  const int b = elem_block();
+  SPK_LAUNCH(spk_k_Lt, grid_for(h->D.nz, b), b, 0, h->stream, h->D, h->P, v, alpha, beta, in, out);
+  COUNT_LAUNCH(h, PC_LLT);
+  return rt_launch_check();
+}
+// out = alpha * L z + beta * in
+static int op_L(spk_handle *h, const double *z, double alpha, double beta, const double *in, double *out) {
+  ProfScope ps(h, PC_LLT);
+  const int b = elem_block();
+  SPK_LAUNCH(spk_k_L, grid_for(h->D.nv, b), b, 0, h->stream, h->D, h->P, z, alpha, beta, in, out);
+  COUNT_LAUNCH(h, PC_LLT);
+  return rt_launch_check();
+}
+
+static int op_axpby(spk_handle *h, long n, double a, const double *x, double b, const double *y, double *out) {
+  ProfScope ps(h, PC_VEC);
+  const int blk = elem_block();
+  long g = (n + blk - 1) / blk;
+  if (g > 148L * 32) g = 148L * 32;
+  if (g < 1) g = 1;
+  SPK_LAUNCH(spk_k_axpby, (unsigned)g, blk, 0, h->stream, n, a, x, b, y, out);
+  COUNT_LAUNCH(h, PC_VEC);
+  return rt_launch_check();
+}
+
+// mode 0: d_scal[slot] (+)= sum x.*y ; mode 1: d_scal[slot] = max|x|
+static int op_reduce(spk_handle *h, long n, int mode, const double *x, const double *y, int slot, int accumulate) {
+  ProfScope ps(h, PC_VEC);
+  const int blk = SPK_EMU ? 1 : 256;
+  long g = (n + blk - 1) / blk;
+  if (g > h->red_blocks) g = h->red_blocks;
+  if (g < 1) g = 1;
+  SPK_LAUNCH(spk_k_reduce_partial, (unsigned)g, blk, blk * sizeof(double), h->stream, n, mode, x, y, h->d_partial);
+  SPK_LAUNCH(spk_k_reduce_final, 1, blk, blk * sizeof(double), h->stream, (int)g, mode, h->d_partial, h->d_scal, slot,
+             accumulate);
+  COUNT_LAUNCH(h, PC_VEC);
+  COUNT_LAUNCH(h, PC_VEC);
+  return rt_launch_check();
+}
+static int fetch_scalars(spk_handle *h, int count) {
+  return rt_d2h(h->h_scal, h->d_scal, sizeof(double) * count, h->stream);
+}
+
+// projection_S1! (implicit_l.jl:559-686) in place on arg = (x | u)
+static int op_proj_S1(spk_handle *h, double *arg) {
+  const SpkDims &D = h->D;
+  const int lanes = pow2_lanes(std::max(D.nx, D.nu));
+  int block = SPK_EMU ? 1 : 128;
+  const size_t per_group_b = (size_t)(D.d * D.nx + 3 * D.nu) * sizeof(double);
+  const size_t per_group_f = (size_t)(D.nx + D.nu) * sizeof(double);
+  while (block > lanes && (block / lanes) * per_group_b > 40000) block >>= 1;
+  const int gpb = block / lanes;
+  for (int t = D.N - 2; t >= 0; --t) {
+    ProfScope ps(h, PC_S1_BWD);
+    const long count = spk_level_count(D.d, t);
+    const unsigned grid = (unsigned)((count + gpb - 1) / gpb);
+    SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_s1_bwd<LANES>, grid, block, gpb * per_group_b, h->stream, D, h->P, t,
+                                       (int)(t == D.N - 2), arg, h->ric_q, h->ric_d));
+    COUNT_LAUNCH(h, PC_S1_BWD);
+  }
+  for (int t = 0; t <= D.N - 2; ++t) {
+    ProfScope ps(h, PC_S1_FWD);
+    const long count = spk_level_count(D.d, t);
+    const unsigned grid = (unsigned)((count + gpb - 1) / gpb);
+    SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_s1_fwd<LANES>, grid, block, gpb * per_group_f, h->stream, D, h->P, t, arg,
+                                       h->ric_d));
+    COUNT_LAUNCH(h, PC_S1_FWD);
+  }
+  return rt_launch_check();
+}
+
+// projection_S2! (implicit_l.jl:688-727) in place on the full z-sized vector
+static int op_proj_S2(spk_handle *h, double *arg) {
+  ProfScope ps(h, PC_S2);
+  const int b = SPK_EMU ? 1 : 128;
+  SPK_LAUNCH(spk_k_s2, grid_for(h->D.nnl, b), b, 0, h->stream, h->D, h->P, arg);
+  COUNT_LAUNCH(h, PC_S2);
+  return rt_launch_check();
+}
+
+// prox_f! (implicit_l.jl:729-748) in place
+static int op_prox_f(spk_handle *h, double *arg, double gamma) {
+  {
+    ProfScope ps(h, PC_VEC);
+    SPK_LAUNCH(spk_k_add_scalar, 1, 1, 0, h->stream, arg, h->D.zo[2], -gamma);  // :741
+    COUNT_LAUNCH(h, PC_VEC);
+  }
+  SPK_TRY(op_proj_S1(h, arg));
+  return op_proj_S2(h, arg);
+}
+
+// prox_h_conj! (implicit_l.jl:911-951); in == out allowed
+static int op_prox_hconj(spk_handle *h, const double *in, double sigma, double *out) {
+  ProfScope ps(h, PC_PROX_H);
+  const SpkDims &D = h->D;
+  const int b = elem_block();
+  SPK_LAUNCH(spk_k_prox_own, grid_for(D.nnl, b), b, 0, h->stream, D, sigma, in, out);
+  const long nbox = D.nnl * (long)(D.nx + D.nu) + D.nl * (long)D.nx;
+  SPK_LAUNCH(spk_k_prox_box, grid_for(nbox, b), b, 0, h->stream, D, sigma, in, out);
+  const int lanes = pow2_lanes(D.nx + D.nu);
+  const int block = SPK_EMU ? 1 : 128;
+  const int gpb = block / lanes;
+  SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_prox_soc_child<LANES>, grid_for(D.n - 1, gpb), block, 0, h->stream, D, sigma,
+                                     in, out));
+  const int lanes_l = pow2_lanes(D.nx);
+  const int gpb_l = block / lanes_l;
+  SPK_LANES_SWITCH(lanes_l, SPK_LAUNCH(spk_k_prox_soc_leaf<LANES>, grid_for(D.nl, gpb_l), block, 0, h->stream, D, sigma,
+                                       in, out));
+  for (int k = 0; k < 4; ++k) COUNT_LAUNCH(h, PC_PROX_H);
+  return rt_launch_check();
+}
+
+// T: (z,v) -> (zbar,vbar)   update_zbar!/update_vbar! (cp.jl:5-32 == sp.jl:5-32 == sp.jl:133-153)
+static int op_T(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma) {
+  const long nz = h->D.nz;
+  const double *z = zv_in, *v = zv_in + nz;
+  double *zbar = zv_out, *vbar = zv_out + nz;
+  SPK_TRY(op_Lt(h, v, -gamma, 1.0, z, zbar));                 // zbar = -gamma L'v + z
+  SPK_TRY(op_prox_f(h, zbar, gamma));
+  SPK_TRY(op_axpby(h, nz, 2.0, zbar, -1.0, z, h->zw));        // z_workspace = 2 zbar - z
+  SPK_TRY(op_L(h, h->zw, sigma, 1.0, v, vbar));               // vbar = sigma L(zw) + v
+  return op_prox_hconj(h, vbar, sigma, vbar);
+}
+
+// spock_dot (implicit_l.jl:485-516): d_scal[slot] = <a, P b>, P(b) = (b_z - gamma L'b_v, b_v - sigma L b_z)
+static int op_pdot(spk_handle *h, const double *a_zv, const double *b_zv, double gamma, double sigma, int slot) {
+  const long nz = h->D.nz, nv = h->D.nv;
+  SPK_TRY(op_Lt(h, b_zv + nz, -gamma, 1.0, b_zv, h->ws_L));
+  SPK_TRY(op_L(h, b_zv, -sigma, 1.0, b_zv + nz, h->ws_L + nz));
+  return op_reduce(h, nz + nv, 0, a_zv, h->ws_L, slot, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ loops
+
+struct LoopState {
+  double gamma, sigma, tol;
+  int verbose_log;
+  double r_safe = INFINITY;
+  int iter = 0, broyden_k = 0, k1 = 0, k2 = 0, fb = 0;
+};
+
+// should_terminate! (cp.jl:54-123 / sp.jl:270-344).  Leaves xi1, xi2 (and xi in LOG mode) in d_scal[0..2].
+static int launch_termination(spk_handle *h, const LoopState &S) {
+  const long nz = h->D.nz, nv = h->D.nv;
+  SPK_TRY(op_axpby(h, nz + nv, 1.0, h->zv, -1.0, h->zv_old, h->dzv));                 // delta = (z,v) - (z,v)_old
+  SPK_TRY(op_Lt(h, h->dzv + nz, 1.0, -1.0 / S.gamma, h->dzv, h->xi12));               // xi_1 = L'dv - dz/gamma
+  SPK_TRY(op_L(h, h->dzv, 1.0, -1.0 / S.sigma, h->dzv + nz, h->xi12 + nz));           // xi_2 = L dz - dv/sigma
+  SPK_TRY(op_reduce(h, nz, 1, h->xi12, nullptr, 0, 0));
+  SPK_TRY(op_reduce(h, nv, 1, h->xi12 + nz, nullptr, 1, 0));
+  if (S.verbose_log && h->alg == SPK_CP) {  // cp.jl:82-86
+    SPK_TRY(op_Lt(h, h->xi12 + nz, 1.0, 1.0, h->xi12, h->xi));
+    SPK_TRY(op_reduce(h, nz, 1, h->xi, nullptr, 2, 0));
+  }
+  return SPK_OK;
+}
+// host side of should_terminate!; expects h_scal[0..2] fetched
+static bool decide_termination(spk_handle *h, const LoopState &S, double *xi, double *xi1, double *xi2) {
+  *xi1 = h->h_scal[0];
+  *xi2 = h->h_scal[1];
+  *xi = NAN;
+  bool res = false;
+  if (S.verbose_log) {
+    *xi = (h->alg == SPK_CP) ? h->h_scal[2] : std::max(*xi1, *xi2);  // sp.jl:304
+    res = *xi <= S.tol;
+  } else {
+    const double t1 = std::max(S.tol * h->res_0[0], S.tol), t2 = std::max(S.tol * h->res_0[1], S.tol);
+    res = (*xi1 <= t1) && (*xi2 <= t2);
+  }
+  if (h->res_0[0] == -INFINITY) h->res_0[0] = *xi1;
+  if (h->res_0[1] == -INFINITY) h->res_0[1] = *xi2;
+  h->last_xi1 = *xi1;
+  h->last_xi2 = *xi2;
+  return res;
+}
+
+// one pass of run_cp! (cp.jl:205-228) up to and including the launches of should_terminate!
+static int cp_pass_launch(spk_handle *h, const LoopState &S) {
+  const long nzv = h->D.nz + h->D.nv;
+  SPK_TRY(rt_d2d(h->zv_old, h->zv, sizeof(double) * nzv, h->stream));  // :207-208
+  SPK_TRY(op_T(h, h->zv, h->zvbar, S.gamma, S.sigma));                 // :210-211
+  std::swap(h->zv, h->zvbar);                                          // :213-214 with lambda = 1
+  return launch_termination(h, S);
+}
+
+// anderson! (anderson.jl:1-123) with rotating column buffers instead of physical shifts
+static int anderson(spk_handle *h, int iter) {
+  const long nr = h->D.nz + h->D.nv;
+  double *R = h->aaR;
+  auto rot = [](double **a) { double *last = a[AA_M - 1]; for (int j = AA_M - 1; j >= 1; --j) a[j] = a[j - 1]; a[0] = last; };
+  rot(h->MP); rot(h->MR); rot(h->AQ);                                             // :13-24, :52-56
+  SPK_TRY(rt_d2d(h->MR[0], h->drzv, sizeof(double) * nr, h->stream));             // :26-33
+  SPK_TRY(op_axpby(h, nr, 1.0, h->dzv, -1.0, h->MR[0], h->MP[0]));
+  for (int j = AA_M - 1; j >= 1; --j)                                             // :46-50
+    for (int i = AA_M - 1; i >= 1; --i)
+      if (i <= j) R[i + j * AA_M] = R[(i - 1) + (j - 1) * AA_M];
+  SPK_TRY(rt_d2d(h->AQ[0], h->MR[0], sizeof(double) * nr, h->stream));            // :63-65
+  if (iter > 1) {
+    const int jmax = std::min(iter, AA_M);
+    for (int j = 2; j <= jmax; ++j) {                                             // :78-91
+      SPK_TRY(op_reduce(h, nr, 0, h->AQ[j - 1], h->AQ[0], 8, 0));
+      SPK_TRY(op_reduce(h, nr, 0, h->AQ[j - 1], h->AQ[j - 1], 9, 0));
+      SPK_TRY(fetch_scalars(h, 10));
+      const double r = h->h_scal[8] / std::sqrt(h->h_scal[9]);
+      R[0 + (j - 1) * AA_M] = r;
+      SPK_TRY(op_axpby(h, nr, 1.0, h->AQ[0], -r, h->AQ[j - 1], h->AQ[0]));
+    }
+  }
+  SPK_TRY(op_reduce(h, nr, 0, h->AQ[0], h->AQ[0], 8, 0));                         // :68-76 / :93-98
+  SPK_TRY(fetch_scalars(h, 9));
+  const double r = std::sqrt(h->h_scal[8]);
+  SPK_TRY(op_axpby(h, nr, 1.0 / r, h->AQ[0], 0.0, nullptr, h->AQ[0]));
+  R[0] = r;
+  for (int j = 0; j < AA_M; ++j) SPK_TRY(op_reduce(h, nr, 0, h->AQ[j], h->rzv, 8 + j, 0));  // :111 gamma = Q' r
+  SPK_TRY(fetch_scalars(h, 8 + AA_M));
+  double g[AA_M];
+  for (int j = 0; j < AA_M; ++j) g[j] = h->h_scal[8 + j];
+  for (int j = AA_M - 1; j >= 0; --j) {                                           // :113 ldiv!(UpperTriangular)
+    g[j] = g[j] / R[j + j * AA_M];
+    for (int i = 0; i < j; ++i) g[i] -= R[i + j * AA_M] * g[j];
+  }
+  // d = -r - MP*gamma (:116-122)
+  SPK_TRY(op_axpby(h, nr, -1.0, h->rzv, -g[0], h->MP[0], h->dir));
+  for (int j = 1; j < AA_M; ++j) SPK_TRY(op_axpby(h, nr, 1.0, h->dir, -g[j], h->MP[j], h->dir));
+  return SPK_OK;
+}
+
+// one pass of run_sp! (sp.jl:388-463); *bc = backtrack_count.  Ends with the launches of should_terminate!.
+static int sp_pass_launch(spk_handle *h, LoopState &S, int *bc) {
+  const long nz = h->D.nz, nv = h->D.nv, nr = nz + nv;
+  const double c1 = 0.99, q = 0.99, sigma_k2 = 0.1, lambda_sp = 1.0;  // sp.jl:366-372
+  SPK_TRY(op_T(h, h->zv, h->zvbar, S.gamma, S.sigma));                                 // :389-390
+  SPK_TRY(op_axpby(h, nr, 1.0, h->zv, -1.0, h->zvbar, h->rzv));                        // update_residual! :34-51
+  SPK_TRY(op_pdot(h, h->rzv, h->rzv, S.gamma, S.sigma, 4));
+  SPK_TRY(op_axpby(h, nr, 1.0, h->rzv, -1.0, h->rzv_old, h->drzv));                    // update_delta_r! :257-268
+  SPK_TRY(rt_d2d(h->zv_old, h->zv, sizeof(double) * nr, h->stream));                   // update_sy! :232-255
+  SPK_TRY(rt_d2d(h->rzv_old, h->rzv, sizeof(double) * nr, h->stream));
+  S.broyden_k += 1;                                                                    // spock.jl:212-224
+  SPK_TRY(anderson(h, S.broyden_k));  // its last fetch also brought slot 4 (launched earlier on the stream)
+  const double rnorm = std::sqrt(h->h_scal[4]);
+  // tau is always 1: perform_linesearch!'s result is discarded (sp.jl:439), so the up-to-9 "backtracks" recompute
+  // the same candidate.  It is evaluated once; a failed K1/K2 test reports backtrack_count = 9 like the reference.
+  const double tau = 1.0;
+  SPK_TRY(op_axpby(h, nr, 1.0, h->zv, tau, h->dir, h->wu));                            // generate_candidate_update! :118-131
+  SPK_TRY(op_T(h, h->wu, h->wubar, S.gamma, S.sigma));                                 // update_candidate_residual! :133-164
+  SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
+  SPK_TRY(op_pdot(h, h->rwu, h->rwu, S.gamma, S.sigma, 5));
+  SPK_TRY(fetch_scalars(h, 6));
+  const double rtilde_norm = std::sqrt(h->h_scal[5]);
+  int backtrack_count = 0;
+  if (rnorm <= S.r_safe && rtilde_norm <= c1 * rnorm) {                                // K1 :166-191
+    std::swap(h->zv, h->wu);
+    S.r_safe = rtilde_norm + std::pow(q, (double)S.iter);
+    S.k1++;
+  } else {
+    SPK_TRY(op_axpby(h, nr, 1.0, h->rwu, -tau, h->dir, h->ws_rho));                    // :419-424
+    SPK_TRY(op_pdot(h, h->rwu, h->ws_rho, S.gamma, S.sigma, 6));
+    SPK_TRY(fetch_scalars(h, 7));
+    double rho = h->h_scal[6];
+    if (rho >= sigma_k2 * rnorm * rtilde_norm) {                                       // K2 :193-222
+      rho /= rtilde_norm * rtilde_norm;
+      SPK_TRY(op_axpby(h, nr, 1.0, h->zv, -(lambda_sp * rho), h->rwu, h->zv));
+      S.k2++;
+    } else {                                                                           // fallback :443-446
+      backtrack_count = 9;
+      std::swap(h->zv, h->zvbar);
+      S.fb++;
+    }
+  }
+  *bc = backtrack_count;
+  return launch_termination(h, S);
+}
+
+static void default_steps(const spk_handle *h, double &gamma, double &sigma) {
+  if (!(sigma > 0) || !(gamma > 0)) {  // cp.jl:198-201
+    sigma = 0.99 / std::sqrt(h->L_norm);
+    gamma = sigma;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+
+static int check_problem(const spk_problem *p) {
+  if (!p) return fail(SPK_ERR_INVALID, "problem is NULL");
+  if (p->d <= 1) return fail(SPK_ERR_INVALID, "Branching factor d must be larger than 1, but is " + std::to_string(p->d) + ".");
+  if (p->N < 2 || p->N > SPK_MAX_LEVELS) return fail(SPK_ERR_INVALID, "N must be in 2.." + std::to_string(SPK_MAX_LEVELS));
+  if (p->nx < 1 || p->nu < 1 || p->ny < 1) return fail(SPK_ERR_INVALID, "nx, nu, ny must be positive");
+  if (p->ny + 2 * p->d > SPK_MAX_LS) return fail(SPK_ERR_INVALID, "ny + 2d exceeds " + std::to_string(SPK_MAX_LS));
+  if (p->n_cones < 1 || p->n_cones > SPK_MAX_CONES) return fail(SPK_ERR_INVALID, "1.." + std::to_string(SPK_MAX_CONES) + " sub-cones supported");
+  if (p->algorithm != SPK_CP && p->algorithm != SPK_SP)
+    return fail(SPK_ERR_INVALID, "This combination of solver options is not supported.");  // model.jl:295
+  if (!p->A || !p->B || !p->sqrtQ || !p->sqrtR || !p->sqrtQN || !p->E || !p->F || !p->b || !p->cone_type || !p->cone_dim)
+    return fail(SPK_ERR_INVALID, "NULL array in spk_problem");
+  int sum = 0;
+  for (int c = 0; c < p->n_cones; ++c) {
+    if (p->cone_type[c] < 0 || p->cone_type[c] > 4 || p->cone_dim[c] < 1) return fail(SPK_ERR_INVALID, "bad sub-cone");
+    sum += p->cone_dim[c];
+  }
+  if (sum != p->ny) return fail(SPK_ERR_INVALID, "sub-cone dimensions must add up to ny");
+  if (p->factor_mode != SPK_FACTORS_PER_NODE && p->factor_mode != SPK_FACTORS_PER_STAGE)
+    return fail(SPK_ERR_INVALID, "unknown factor_mode");
+  if (p->world_size > 1) return fail(SPK_ERR_INVALID, "multi-GPU sharding is not available in this build");
+  double dn = 1.0;
+  for (int k = 0; k < p->N; ++k) dn *= p->d;
+  if (dn > 4.0e9) return fail(SPK_ERR_INVALID, "tree too large");
+  return SPK_OK;
+}
+
+int spk_tree_maps(int32_t N, int32_t d, int64_t *child_first, int64_t *anc, int32_t *w, int64_t *min_index) {
+  if (d <= 1) return fail(SPK_ERR_INVALID, "Branching factor d must be larger than 1, but is " + std::to_string(d) + ".");
+  if (N < 1) return fail(SPK_ERR_INVALID, "N must be positive");
+  int64_t dN = 1;
+  for (int k = 0; k < N; ++k) dN *= d;
+  const int64_t n = (dN - 1) / (d - 1), nnl = (dN / d - 1) / (d - 1);
+  if (child_first)
+    for (int64_t i0 = 0; i0 < nnl; ++i0) child_first[i0] = (int64_t)d * i0 + 2;          // scenario_tree.jl:82-88
+  if (anc)
+    for (int64_t j0 = 0; j0 < n; ++j0) anc[j0] = j0 == 0 ? 0 : (j0 - 1) / d + 1;         // :90-95
+  if (w)
+    for (int64_t j0 = 0; j0 < n; ++j0) w[j0] = j0 == 0 ? 0 : (int32_t)((j0 + 1) % d) + 1; // :77
+  if (min_index)
+    for (int t = 0; t < N; ++t) min_index[t] = spk_level_first0(d, t) + 1;               // :107
+  return SPK_OK;
+}
+
+int spk_destroy(spk_handle *h) {
+  if (!h) return SPK_OK;
+  rt_sync(h->stream);
+  for (void *p : h->allocs) rt_free(p);
+#ifndef SPK_HOST_EMU
+  for (auto &s : h->prof_open) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->ev_a) cudaEventDestroy(h->ev_a);
+  if (h->ev_b) cudaEventDestroy(h->ev_b);
+  if (h->stream) cudaStreamDestroy(h->stream);
+#endif
+  delete h;
+  return SPK_OK;
+}
+
+static int create_impl(const spk_problem *p, spk_handle *h) {
+  SpkDims &D = h->D;
+  memset(&D, 0, sizeof(D));
+  D.N = p->N; D.d = p->d; D.nx = p->nx; D.nu = p->nu; D.ny = p->ny; D.nls = p->ny + 2 * p->d;
+  long dN = 1;
+  for (int k = 0; k < p->N; ++k) dN *= p->d;
+  D.n = (dN - 1) / (p->d - 1);
+  D.nl = dN / p->d;
+  D.nnl = (dN / p->d - 1) / (p->d - 1);
+  const long n = D.n, nnl = D.nnl, nl = D.nl;
+  const int nx = D.nx, nu = D.nu, ny = D.ny, d = D.d;
+  D.zo[0] = 0; D.zo[1] = n * nx; D.zo[2] = D.zo[1] + nnl * nu; D.zo[3] = D.zo[2] + n; D.zo[4] = D.zo[3] + (n - 1);
+  D.nz = D.zo[4] + nnl * ny;                                                     // implicit_l.jl:5-15
+  D.vo[0] = 0; D.vo[1] = nnl * ny; D.vo[2] = D.vo[1] + nnl; D.vo[3] = D.vo[2] + (long)nx * (n - 1);
+  D.vo[4] = D.vo[3] + (long)nu * (n - 1); D.vo[5] = D.vo[4] + (n - 1); D.vo[6] = D.vo[5] + (n - 1);
+  D.vo[7] = D.vo[6] + nnl * (nx + nu); D.vo[8] = D.vo[7] + nl * nx; D.vo[9] = D.vo[8] + nl; D.vo[10] = D.vo[9] + nl;
+  D.nv = D.vo[10] + nl * nx;                                                     // cpock.jl:51-60
+  D.n_cones = p->n_cones;
+  for (int c = 0; c < p->n_cones; ++c) { D.cone_type[c] = p->cone_type[c]; D.cone_dim[c] = p->cone_dim[c]; }
+  D.x_min = p->x_min; D.x_max = p->x_max; D.u_min = p->u_min; D.u_max = p->u_max;
+  D.cost_dense = p->cost_dense ? 1 : 0;
+  if (p->n_sqrtQ != 1 && p->n_sqrtQ != n - 1) return fail(SPK_ERR_INVALID, "n_sqrtQ must be 1 or n-1");
+  if (p->n_sqrtQN != 1 && p->n_sqrtQN != nl) return fail(SPK_ERR_INVALID, "n_sqrtQN must be 1 or n_leaf");
+  D.n_sqrtQ = p->n_sqrtQ; D.n_sqrtQN = p->n_sqrtQN;
+  D.per_node = (p->factor_mode == SPK_FACTORS_PER_NODE) ? 1 : 0;
+  h->alg = p->algorithm;
+  h->L_norm = p->L_norm > 0 ? p->L_norm : (p->algorithm == SPK_SP ? 3.28 : 10.0);  // spock.jl:64 / cpock.jl:63
+
+  std::string err;
+  if (!spk_offline_factors(p->N, d, nx, nu, p->A, p->B, h->table, err)) return fail(SPK_ERR_INVALID, err);
+  if (!spk_kernel_projector(ny, d, p->E, p->F, h->ls_host, err)) return fail(SPK_ERR_INVALID, err);
+  D.abk_stride = h->table.abk_stride; D.k_stride = h->table.k_stride; D.r_stride = h->table.r_stride;
+
+  // ---- problem data
+  double *tmp;
+  SPK_TRY(upload(h, &tmp, p->A, (long)d * nx * nx)); h->P.A = tmp;
+  SPK_TRY(upload(h, &tmp, p->B, (long)d * nx * nu)); h->P.B = tmp;
+  std::vector<double> Bt((size_t)d * nx * nu);
+  for (int w = 0; w < d; ++w)
+    for (int r = 0; r < nx; ++r)
+      for (int k = 0; k < nu; ++k) Bt[(size_t)w * nx * nu + k + (size_t)r * nu] = p->B[(size_t)w * nx * nu + r + (size_t)k * nx];
+  SPK_TRY(upload(h, &tmp, Bt.data(), (long)Bt.size())); h->P.Bt = tmp;
+  const long qsz = D.cost_dense ? (long)nx * nx : nx, rsz = D.cost_dense ? (long)nu * nu : nu;
+  SPK_TRY(upload(h, &tmp, p->sqrtQ, p->n_sqrtQ * qsz)); h->P.sqrtQ = tmp;
+  SPK_TRY(upload(h, &tmp, p->sqrtR, p->n_sqrtQ * rsz)); h->P.sqrtR = tmp;
+  SPK_TRY(upload(h, &tmp, p->sqrtQN, p->n_sqrtQN * qsz)); h->P.sqrtQN = tmp;
+  SPK_TRY(upload(h, &tmp, p->b, ny)); h->P.b = tmp;
+  SPK_TRY(upload(h, &tmp, h->ls_host.data(), (long)h->ls_host.size())); h->P.ls = tmp;
+  SPK_TRY(dev_alloc(h, &h->x0, nx)); h->P.x0 = h->x0;
+
+  // ---- factors: per-stage table, replicated to per-node slots in PER_NODE mode
+  const SpkFactorTable &T = h->table;
+  double *tABK, *tABKt, *tK, *tKt, *tG, *tR;
+  SPK_TRY(upload(h, &tABK, T.ABK.data(), (long)T.ABK.size()));
+  SPK_TRY(upload(h, &tABKt, T.ABKt.data(), (long)T.ABKt.size()));
+  SPK_TRY(upload(h, &tK, T.K.data(), (long)T.K.size()));
+  SPK_TRY(upload(h, &tKt, T.Kt.data(), (long)T.Kt.size()));
+  SPK_TRY(upload(h, &tG, T.G.data(), (long)T.G.size()));
+  SPK_TRY(upload(h, &tR, T.Rinv.data(), (long)T.Rinv.size()));
+  if (!D.per_node) {
+    h->P.ABK = tABK; h->P.ABKt = tABKt; h->P.K = tK; h->P.Kt = tKt; h->P.G = tG; h->P.Rinv = tR;
+  } else {
+    double *nABK, *nABKt, *nK, *nKt, *nG, *nR;
+    SPK_TRY(dev_alloc(h, &nABK, (n - 1) * D.abk_stride, false));
+    SPK_TRY(dev_alloc(h, &nABKt, (n - 1) * D.abk_stride, false));
+    SPK_TRY(dev_alloc(h, &nK, nnl * D.k_stride, false));
+    SPK_TRY(dev_alloc(h, &nKt, nnl * D.k_stride, false));
+    SPK_TRY(dev_alloc(h, &nG, nnl * D.k_stride, false));
+    SPK_TRY(dev_alloc(h, &nR, nnl * D.r_stride, false));
+    const int b = elem_block();
+    const unsigned g = SPK_EMU ? 64 : 148 * 16;
+    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 0, D.abk_stride, n - 1, tABK, nABK);
+    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 0, D.abk_stride, n - 1, tABKt, nABKt);
+    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tK, nK);
+    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tKt, nKt);
+    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tG, nG);
+    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.r_stride, nnl, tR, nR);
+    h->launches += 6;
+    SPK_TRY(rt_launch_check());
+    h->P.ABK = nABK; h->P.ABKt = nABKt; h->P.K = nK; h->P.Kt = nKt; h->P.G = nG; h->P.Rinv = nR;
+  }
+
+  // ---- state (cpock.jl:83-103)
+  const long nr = D.nz + D.nv;
+  SPK_TRY(dev_alloc(h, &h->zv, nr));
+  SPK_TRY(dev_alloc(h, &h->zvbar, nr));
+  SPK_TRY(dev_alloc(h, &h->zv_old, nr));
+  SPK_TRY(dev_alloc(h, &h->dzv, nr));
+  SPK_TRY(dev_alloc(h, &h->xi12, nr));
+  SPK_TRY(dev_alloc(h, &h->zw, D.nz));
+  SPK_TRY(dev_alloc(h, &h->xi, D.nz));
+  SPK_TRY(dev_alloc(h, &h->ric_q, n * nx));
+  SPK_TRY(dev_alloc(h, &h->ric_d, std::max(nnl, 1L) * nu));
+  SPK_TRY(dev_alloc(h, &h->ws_L, nr));
+  h->red_blocks = SPK_EMU ? 8 : 148 * 8;
+  SPK_TRY(dev_alloc(h, &h->d_partial, h->red_blocks));
+  SPK_TRY(dev_alloc(h, &h->d_scal, 32));
+  h->res_0[0] = h->res_0[1] = -INFINITY;
+  if (h->alg == SPK_SP) {  // spock.jl:160-202
+    SPK_TRY(dev_alloc(h, &h->rzv, nr));
+    SPK_TRY(dev_alloc(h, &h->rzv_old, nr));
+    SPK_TRY(dev_alloc(h, &h->drzv, nr));
+    SPK_TRY(dev_alloc(h, &h->dir, nr));
+    SPK_TRY(dev_alloc(h, &h->wu, nr));
+    SPK_TRY(dev_alloc(h, &h->wubar, nr));
+    SPK_TRY(dev_alloc(h, &h->rwu, nr));
+    SPK_TRY(dev_alloc(h, &h->ws_rho, nr));
+    for (int j = 0; j < AA_M; ++j) {
+      SPK_TRY(dev_alloc(h, &h->MP[j], nr));
+      SPK_TRY(dev_alloc(h, &h->MR[j], nr));
+      SPK_TRY(dev_alloc(h, &h->AQ[j], nr));
+    }
+    for (int k = 0; k < AA_M * AA_M; ++k) h->aaR[k] = 0.0;
+    for (int k = 0; k < AA_M; ++k) h->aaR[k + k * AA_M] = 1.0;
+  }
+  // fill the "ones" initial values: z_old, v_old (cpock.jl:98-99), rz_old, rv_old (spock.jl:187-188)
+  {
+    std::vector<double> ones((size_t)std::min(nr, 1L << 20), 1.0);
+    for (long off = 0; off < nr; off += (long)ones.size()) {
+      const long cnt = std::min((long)ones.size(), nr - off);
+      SPK_TRY(rt_h2d(h->zv_old + off, ones.data(), sizeof(double) * cnt, h->stream));
+      if (h->alg == SPK_SP) SPK_TRY(rt_h2d(h->rzv_old + off, ones.data(), sizeof(double) * cnt, h->stream));
+    }
+  }
+  for (int c = 0; c < PC_COUNT; ++c) { h->prof_ms[c] = 0.0; h->prof_launches[c] = 0; }
+  return rt_sync(h->stream);
+}
+
+int spk_create(const spk_problem *p, spk_handle **out) {
+  if (!out) return fail(SPK_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  SPK_TRY(check_problem(p));
+  spk_handle *h = new spk_handle();
+#ifndef SPK_HOST_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    delete h;
+    return fail(SPK_ERR_CUDA, "no CUDA device available: libspock_b200 has no CPU fallback");
+  }
+  if (p->device >= 0) {
+    if (cudaSetDevice(p->device) != cudaSuccess) { delete h; return fail(SPK_ERR_CUDA, "cudaSetDevice failed"); }
+  }
+  cudaGetDevice(&h->device);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(SPK_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  cudaEventCreate(&h->ev_a);
+  cudaEventCreate(&h->ev_b);
+#endif
+  const int rc = create_impl(p, h);
+  if (rc != SPK_OK) {
+    const std::string keep = g_last_error;
+    spk_destroy(h);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = h;
+  return SPK_OK;
+}
+
+int spk_sizes(const spk_handle *h, int64_t s[5]) {
+  if (!h || !s) return fail(SPK_ERR_INVALID, "NULL argument");
+  s[0] = h->D.n; s[1] = h->D.nnl; s[2] = h->D.nl; s[3] = h->D.nz; s[4] = h->D.nv;
+  return SPK_OK;
+}
+int spk_offsets(const spk_handle *h, int64_t zo[5], int64_t vo[11]) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (zo) for (int k = 0; k < 5; ++k) zo[k] = h->D.zo[k];
+  if (vo) for (int k = 0; k < 11; ++k) vo[k] = h->D.vo[k];
+  return SPK_OK;
+}
+int spk_device_bytes(const spk_handle *h, int64_t *b) {
+  if (!h || !b) return fail(SPK_ERR_INVALID, "NULL argument");
+  *b = h->bytes;
+  return SPK_OK;
+}
+int spk_launch_count(const spk_handle *h, int64_t *l) {
+  if (!h || !l) return fail(SPK_ERR_INVALID, "NULL argument");
+  *l = h->launches;
+  return SPK_OK;
+}
+
+int spk_set_x0(spk_handle *h, const double *x0) {
+  if (!h || !x0) return fail(SPK_ERR_INVALID, "NULL argument");
+  return rt_h2d(h->x0, x0, sizeof(double) * h->D.nx, h->stream);
+}
+int spk_set_iterate(spk_handle *h, const double *z, const double *v) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (z) SPK_TRY(rt_h2d(h->z(), z, sizeof(double) * h->D.nz, h->stream));
+  if (v) SPK_TRY(rt_h2d(h->v(), v, sizeof(double) * h->D.nv, h->stream));
+  return SPK_OK;
+}
+int spk_get_iterate(spk_handle *h, double *z, double *v) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (z) SPK_TRY(rt_d2h(z, h->z(), sizeof(double) * h->D.nz, h->stream));
+  if (v) SPK_TRY(rt_d2h(v, h->v(), sizeof(double) * h->D.nv, h->stream));
+  return SPK_OK;
+}
+
+int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double scalar) {
+  if (!h || !in || !out) return fail(SPK_ERR_INVALID, "NULL argument");
+  const SpkDims &D = h->D;
+  const long nz = D.nz, nv = D.nv;
+  // scratch: wu-sized temporaries carved from dzv / xi12 (not live outside the loops)
+  double *tz = h->dzv, *tv = h->dzv + nz, *oz = h->xi12, *ov = h->xi12 + nz;
+  switch (op) {
+    case SPK_OP_L:
+      SPK_TRY(rt_h2d(tz, in, sizeof(double) * nz, h->stream));
+      SPK_TRY(op_L(h, tz, 1.0, 0.0, nullptr, ov));
+      return rt_d2h(out, ov, sizeof(double) * nv, h->stream);
+    case SPK_OP_LT:
+      SPK_TRY(rt_h2d(tv, in, sizeof(double) * nv, h->stream));
+      SPK_TRY(op_Lt(h, tv, 1.0, 0.0, nullptr, oz));
+      return rt_d2h(out, oz, sizeof(double) * nz, h->stream);
+    case SPK_OP_PROX_F:
+      SPK_TRY(rt_h2d(tz, in, sizeof(double) * nz, h->stream));
+      SPK_TRY(op_prox_f(h, tz, scalar));
+      return rt_d2h(out, tz, sizeof(double) * nz, h->stream);
+    case SPK_OP_PROX_HCONJ:
+      if (!(scalar > 0)) return fail(SPK_ERR_INVALID, "sigma must be positive");
+      SPK_TRY(rt_h2d(tv, in, sizeof(double) * nv, h->stream));
+      SPK_TRY(op_prox_hconj(h, tv, scalar, ov));
+      return rt_d2h(out, ov, sizeof(double) * nv, h->stream);
+    case SPK_OP_PROJ_S1:
+      SPK_TRY(rt_h2d(tz, in, sizeof(double) * D.zo[2], h->stream));
+      SPK_TRY(op_proj_S1(h, tz));
+      return rt_d2h(out, tz, sizeof(double) * D.zo[2], h->stream);
+    case SPK_OP_PROJ_S2:  // z2 = view(arg, s_inds[1]+1 : nz), implicit_l.jl:747
+      SPK_TRY(rt_h2d(tz + D.zo[2] + 1, in, sizeof(double) * (nz - D.zo[2] - 1), h->stream));
+      SPK_TRY(op_proj_S2(h, tz));
+      return rt_d2h(out, tz + D.zo[2] + 1, sizeof(double) * (nz - D.zo[2] - 1), h->stream);
+    default:
+      return fail(SPK_ERR_INVALID, "unknown operator");
+  }
+}
+
+int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b_z, const double *b_v, double gamma,
+            double sigma, double *out) {
+  if (!h || !a_z || !a_v || !b_z || !b_v || !out) return fail(SPK_ERR_INVALID, "NULL argument");
+  const long nz = h->D.nz, nv = h->D.nv;
+  SPK_TRY(rt_h2d(h->dzv, a_z, sizeof(double) * nz, h->stream));
+  SPK_TRY(rt_h2d(h->dzv + nz, a_v, sizeof(double) * nv, h->stream));
+  SPK_TRY(rt_h2d(h->xi12, b_z, sizeof(double) * nz, h->stream));
+  SPK_TRY(rt_h2d(h->xi12 + nz, b_v, sizeof(double) * nv, h->stream));
+  SPK_TRY(op_pdot(h, h->dzv, h->xi12, gamma, sigma, 4));
+  SPK_TRY(fetch_scalars(h, 5));
+  *out = h->h_scal[4];
+  return SPK_OK;
+}
+
+int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, double *K, double *Rinv, double *ls) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  const SpkDims &D = h->D;
+  if (i < 1 || i > D.n) return fail(SPK_ERR_INVALID, "node index out of range");
+  const long i0 = i - 1;
+  int t = 0;
+  while (t + 1 < D.N && i0 >= spk_level_first0(D.d, t + 1)) ++t;
+  const SpkFactorTable &T = h->table;
+  const size_t nx2 = (size_t)D.nx * D.nx;
+  if (Pm) std::copy(T.P.begin() + t * nx2, T.P.begin() + (t + 1) * nx2, Pm);
+  if (ABK && i0 >= 1) {
+    const int c = (int)((i0 - 1) % D.d);
+    const double *src = T.ABK.data() + ((size_t)(t - 1) * D.d + c) * T.abk_stride;
+    std::copy(src, src + nx2, ABK);
+  }
+  if (i0 < D.nnl) {
+    if (K) std::copy(T.K.begin() + t * T.k_stride, T.K.begin() + t * T.k_stride + (size_t)D.nu * D.nx, K);
+    if (Rinv) std::copy(T.Rinv.begin() + t * T.r_stride, T.Rinv.begin() + t * T.r_stride + (size_t)D.nu * D.nu, Rinv);
+  }
+  if (ls) std::copy(h->ls_host.begin(), h->ls_host.end(), ls);
+  return SPK_OK;
+}
+
+struct LoopTimer {
+  spk_handle *h;
+  double t0 = 0;
+  explicit LoopTimer(spk_handle *h_) : h(h_) {
+#ifndef SPK_HOST_EMU
+    cudaEventRecord(h->ev_a, h->stream);
+#else
+    t0 = wall_ms();
+#endif
+  }
+  float stop() {
+#ifndef SPK_HOST_EMU
+    cudaEventRecord(h->ev_b, h->stream);
+    cudaEventSynchronize(h->ev_b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    return ms;
+#else
+    return (float)(wall_ms() - t0);
+#endif
+  }
+};
+
+int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  LoopState S;
+  default_steps(h, gamma, sigma);
+  S.gamma = gamma; S.sigma = sigma; S.tol = 0.0; S.verbose_log = 0;
+  LoopTimer timer(h);
+  for (int k = 0; k < K; ++k) {
+    S.iter = k;
+    int bc = 0;
+    if (h->alg == SPK_SP) SPK_TRY(sp_pass_launch(h, S, &bc));
+    else SPK_TRY(cp_pass_launch(h, S));
+    if (h->prof_on && h->prof_open.size() > 8192) prof_harvest(h);
+  }
+  SPK_TRY(fetch_scalars(h, 3));
+  h->last_xi1 = h->h_scal[0];
+  h->last_xi2 = h->h_scal[1];
+  const float t = timer.stop();
+  if (ms) *ms = t;
+  return SPK_OK;
+}
+
+int spk_get_residuals(spk_handle *h, double out[2]) {
+  if (!h || !out) return fail(SPK_ERR_INVALID, "NULL argument");
+  out[0] = h->last_xi1;
+  out[1] = h->last_xi2;
+  return SPK_OK;
+}
+
+int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, double gamma, double sigma,
+              int32_t verbose_log, const double *z0, const double *v0, spk_result *result, double *log_xi,
+              double *log_xi1, double *log_xi2, int32_t *log_bc, int32_t log_cap) {
+  if (!h || !x0) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (z0 != nullptr || v0 != nullptr) {  // cpock.jl:180-183: logical-or guard, then both are copied
+    if (z0 == nullptr || v0 == nullptr) return fail(SPK_ERR_INVALID, "z0 and v0 must be given together");
+    SPK_TRY(spk_set_iterate(h, z0, v0));
+  }
+  SPK_TRY(spk_set_x0(h, x0));                      // :185
+  h->res_0[0] = h->res_0[1] = -INFINITY;           // :186
+  LoopState S;
+  default_steps(h, gamma, sigma);
+  S.gamma = gamma; S.sigma = sigma; S.tol = tol; S.verbose_log = verbose_log;
+  if (max_iter <= 0) max_iter = (h->alg == SPK_SP) ? 1000 : 5000;  // sp.jl:360 / cp.jl:190
+  int iter = 0, passes = 0, converged = 0;
+  double xi = NAN, xi1 = NAN, xi2 = NAN;
+  LoopTimer timer(h);
+  while (iter < max_iter) {
+    int bc = 0;
+    S.iter = iter;
+    if (h->alg == SPK_SP) SPK_TRY(sp_pass_launch(h, S, &bc));
+    else SPK_TRY(cp_pass_launch(h, S));
+    SPK_TRY(fetch_scalars(h, 3));
+    const bool stop = decide_termination(h, S, &xi, &xi1, &xi2);
+    if (passes < log_cap) {
+      if (log_xi) log_xi[passes] = xi;
+      if (log_xi1) log_xi1[passes] = xi1;
+      if (log_xi2) log_xi2[passes] = xi2;
+      if (log_bc) log_bc[passes] = bc;
+    }
+    passes++;
+    if (h->prof_on && h->prof_open.size() > 8192) prof_harvest(h);
+    if (stop) { converged = 1; break; }
+    iter += 1;
+  }
+  const float ms = timer.stop();
+  if (result) {
+    result->passes = passes; result->printed_iter = iter; result->converged = converged;
+    result->xi1 = xi1; result->xi2 = xi2; result->xi = xi;
+    result->k1_count = S.k1; result->k2_count = S.k2; result->fallback_count = S.fb;
+    result->solve_ms = ms;
+  }
+  return SPK_OK;
+}
+
+int spk_profile(spk_handle *h, int32_t enable, int32_t reset) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  prof_harvest(h);
+  h->prof_on = enable != 0;
+  if (reset) for (int c = 0; c < PC_COUNT; ++c) { h->prof_ms[c] = 0.0; h->prof_launches[c] = 0; }
+  return SPK_OK;
+}
+int spk_profile_get(spk_handle *h, int32_t cls, double *ms, int64_t *launches) {
+  if (!h || cls < 0 || cls >= PC_COUNT) return fail(SPK_ERR_INVALID, "bad profile class");
+  prof_harvest(h);
+  if (ms) *ms = h->prof_ms[cls];
+  if (launches) *launches = h->prof_launches[cls];
+  return SPK_OK;
+}
+
+int spk_comm_unique_id(uint8_t id[128]) {
+  (void)id;
+  return fail(SPK_ERR_COMM, "multi-GPU sharding is not available in this build");
+}

@@ -1,0 +1,67 @@
+// spk_types.h -- problem dimensions, device pointer tables and index arithmetic shared by all kernels.
+//
+// Indexing contract (bit-exact with the reference, src/scenario_tree.jl:61-109): nodes are numbered
+// breadth-first; kernels use 0-based node numbers i0 = i - 1:
+//   children(i0)   = d*i0 + 1 + c,  c = 0..d-1          (Julia: d(i-1)+2 .. d(i-1)+d+1)
+//   parent(j0)     = (j0 - 1) / d                        (Julia: (j-2) div d + 1)
+//   mode(j0)       = (j0 + 1) % d   (0-based)            (Julia: w = (j % d) + 1)
+//   first0(level t)= (d^t - 1)/(d - 1),  count = d^t     (Julia: min_index_per_timestep)
+// Vector layouts are the reference's (implicit_l.jl:5-44,106-158; cpock.jl:51-60), see include/spock_b200.h.
+#pragma once
+#include "spk_runtime.h"
+
+struct SpkDims {
+  int N, d, nx, nu, ny, nls, n_cones;
+  long n, nnl, nl, nz, nv;
+  long zo[5];   // x, u, s, tau, y
+  long vo[11];  // v1, v2, v3, v4, v5, v6, v7, v11, v12, v13, v14
+  int cone_type[SPK_MAX_CONES], cone_dim[SPK_MAX_CONES];
+  double x_min, x_max, u_min, u_max;
+  int cost_dense, n_sqrtQ, n_sqrtQN;
+  int per_node;            // factor mode: 1 = one factor slot per node, 0 = per (stage, mode)
+  long abk_stride;         // doubles per ABK slot (nx*nx rounded up to an even count: 16-byte aligned slots)
+  long k_stride, r_stride; // doubles per K/Kt/G slot and per Rinv slot
+};
+
+struct SpkPtrs {
+  const double *A, *B, *Bt;              // d modes: A nx*nx, B nx*nu, Bt = B' (nu*nx), column-major
+  const double *sqrtQ, *sqrtR, *sqrtQN;  // diagonals or dense matrices
+  const double *b, *ls;                  // risk vector b (ny), kernel projector (nls*nls)
+  const double *ABK, *ABKt;              // closed-loop matrices A_w + B_w K and their transposes
+  const double *K, *Kt, *Rinv, *G;       // feedback gain (nu*nx), its transpose, Rtilde^{-1}, sum ABK' P B
+  const double *x0;
+};
+
+SPK_HD long spk_level_first0(int d, int t) {
+  long p = 1;
+  for (int k = 0; k < t; ++k) p *= d;
+  return (p - 1) / (d - 1);
+}
+SPK_HD long spk_level_count(int d, int t) {
+  long p = 1;
+  for (int k = 0; k < t; ++k) p *= d;
+  return p;
+}
+
+// row k of (S x) for a sqrt-cost matrix S that is Diagonal (stored as its diagonal) or dense symmetric
+SPK_HD double spk_cost_row(const double *__restrict__ S, int dense, int dim, int k, const double *__restrict__ x) {
+  if (!dense) return S[k] * x[k];
+  double acc = 0.0;
+  for (int m = 0; m < dim; ++m) acc += S[k + (long)m * dim] * x[m];
+  return acc;
+}
+
+SPK_HD const double *spk_sqrtQ(const SpkDims &D, const SpkPtrs &P, long j0) {  // Julia sqrtQ[j-1]
+  const long id = (D.n_sqrtQ == 1) ? 0 : (j0 - 1);
+  return P.sqrtQ + id * (D.cost_dense ? (long)D.nx * D.nx : (long)D.nx);
+}
+SPK_HD const double *spk_sqrtR(const SpkDims &D, const SpkPtrs &P, long j0) {
+  const long id = (D.n_sqrtQ == 1) ? 0 : (j0 - 1);
+  return P.sqrtR + id * (D.cost_dense ? (long)D.nu * D.nu : (long)D.nu);
+}
+SPK_HD const double *spk_sqrtQN(const SpkDims &D, const SpkPtrs &P, long leaf) {
+  const long id = (D.n_sqrtQN == 1) ? 0 : leaf;
+  return P.sqrtQN + id * (D.cost_dense ? (long)D.nx * D.nx : (long)D.nx);
+}
+
+SPK_HD double spk_clip(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }  // constraints.jl:28-30

@@ -1,0 +1,158 @@
+"""GPU parity: the CUDA path through the C ABI (libspock_b200.so on a B200) against the CPU oracle on the same
+seeded inputs, against the reference's golden traces, and -- at sizes the oracle cannot reach quickly -- through
+size-independent properties.  fp64 tolerance from BASELINE.json north_star: 1e-9 relative after K passes."""
+import numpy as np
+import pytest
+
+from oracle.oracle import CP, SP, Oracle
+from spock_b200 import (LOG, SolverOptions, build_model, get_random_system_specs, get_server_heat_specs,
+                        get_test_fixture_specs, solve_model_)
+from spock_b200 import model as M
+from spock_b200.handle import Handle
+from spock_b200.problem import flatten_problem
+from tests.helpers import SMALL_PROBLEMS, check_k_steps, check_operators, flat_of, golden_cp, golden_sp, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("factor_mode", [0, 1])
+@pytest.mark.parametrize("name", list(SMALL_PROBLEMS))
+def test_operators(cuda_lib, name, factor_mode):
+    check_operators(cuda_lib, flat_of(name), factor_mode)
+
+
+@pytest.mark.parametrize("spec", [
+    ("heat", 9, 20, 2), ("heat", 6, 10, 3), ("heat", 5, 10, 4), ("random", 8, 2, 50, 20), ("random", 6, 3, 33, 7),
+])
+def test_operators_medium(cuda_lib, spec):
+    if spec[0] == "heat":
+        flat = flatten_problem(*get_server_heat_specs(spec[1], spec[2], spec[3]))
+    else:
+        flat = flatten_problem(*get_random_system_specs(spec[1], spec[2], spec[3], spec[4]))
+    check_operators(cuda_lib, flat, 0, seed=5)
+    check_operators(cuda_lib, flat, 1, seed=6)
+
+
+@pytest.mark.parametrize("name,alg,K", [
+    ("fixture_N3_d2", CP, 200), ("heat_N7_d2_nx5", CP, 500), ("heat_N4_d3_nx3", CP, 200),
+    ("l2ball_N4_d3_nx3", CP, 200), ("random_N3_d4_nx35_nu17", CP, 100),
+    ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
+])
+@pytest.mark.parametrize("factor_mode", [0, 1])
+def test_k_step_iterates(cuda_lib, name, alg, K, factor_mode):
+    check_k_steps(cuda_lib, flat_of(name), alg, K, factor_mode=factor_mode)
+
+
+def test_cp_golden_trace_full(cuda_lib):
+    """All 3159 CP iterations of examples/server_heat/residuals.jl: same stopping pass, xi within 1e-9."""
+    gold = golden_cp()
+    h = Handle(flat_of("heat_N7_d2_nx5"), CP, lib=cuda_lib)
+    res, log = h.solve(0.1 * np.ones(5), tol=1e-5, verbose_log=True)
+    assert res["passes"] == 3159 and res["converged"] == 1 and res["printed_iter"] == 3158
+    assert np.max(np.abs(log["xi"] - gold) / gold) < 1e-9
+    o = Oracle(flat_of("heat_N7_d2_nx5"), CP)
+    o.solve(0.1 * np.ones(5), tol=1e-5, verbose_log=True)
+    z, v = h.get_iterate()
+    assert relerr(z, o.z) < 1e-9 and relerr(v, o.v) < 1e-9
+
+
+def test_sp_golden_trace(cuda_lib):
+    xi, bc = golden_sp()
+    h = Handle(flat_of("heat_N7_d2_nx5"), SP, lib=cuda_lib)
+    res, log = h.solve(0.1 * np.ones(5), tol=1e-5, verbose_log=True)
+    assert np.max(np.abs(log["xi"][:30] - xi[:30]) / xi[:30]) < 1e-9
+    assert np.array_equal(log["backtrack_count"][:60], bc[:60])
+    assert res["converged"] == 1 and log["xi"][-1] <= 1e-5  # converged solution within the solver tolerance
+
+
+def test_silent_solve_matches_oracle(cuda_lib):
+    flat = flat_of("heat_N7_d2_nx5")
+    h, o = Handle(flat, CP, lib=cuda_lib), Oracle(flat, CP)
+    r1, _ = h.solve(0.1 * np.ones(5), tol=1e-3)
+    r2, _ = o.solve(0.1 * np.ones(5), tol=1e-3)
+    assert r1["passes"] == r2["passes"] and abs(r1["xi1"] - r2["xi1"]) < 1e-9 * r2["xi1"]
+    z, _ = h.get_iterate()
+    assert relerr(z, o.z) < 1e-9
+
+
+def test_reference_api_and_its_tests(cuda_lib):
+    """The reference's own test-suite (test/model_algorithms/prox.jl, test/model_dynamics/implicit_L.jl) through
+    the host mirror of build_model / solve_model!."""
+    scen_tree, cost, dynamics, rms, constraints = get_test_fixture_specs()
+    cp_model = build_model(scen_tree, cost, dynamics, rms, constraints, SolverOptions(M.CP, None))
+    solve_model_(cp_model, [0.1, 0.1], quiet=True)
+    z = cp_model.solver_state.z
+    si = cp_model.solver_state_internal
+    x, u, s, tau, y = (z[si.x_inds].reshape(7, 2), z[si.u_inds], z[si.s_inds], z[si.tau_inds],
+                       z[si.y_inds].reshape(3, 5))
+    A, B = dynamics.A, dynamics.B
+    for j in range(2, 8):  # implicit_L.jl:59-66
+        i, w = (j - 2) // 2 + 1, j % 2
+        assert np.allclose(x[j - 1], A[w] @ x[i - 1] + B[w][:, 0] * u[i - 1])
+    for i in range(1, 4):  # implicit_L.jl:70-78
+        ch = scen_tree.child_mapping[i]
+        assert np.allclose(rms[i - 1].E.T @ y[i - 1], [tau[c - 2] + s[c - 1] for c in ch])
+    rng = np.random.default_rng(0)
+    for _ in range(10):  # prox.jl:53-67
+        z1, z2 = rng.random(cp_model.solver_state.nz), rng.random(cp_model.solver_state.nz)
+        p1, p2 = z1.copy(), z2.copy()
+        M.prox_f_(cp_model, p1, 0.1)
+        M.prox_f_(cp_model, p2, 0.1)
+        assert (p1 - p2) @ (z1 - z2) >= np.linalg.norm(p1 - p2) ** 2 * (1 - 1e-12)
+    for _ in range(20):  # prox.jl:69-81
+        v1, v2 = rng.random(cp_model.solver_state.nv), rng.random(cp_model.solver_state.nv)
+        p1, p2 = v1.copy(), v2.copy()
+        M.prox_h_conj_(cp_model, p1, 0.1)
+        M.prox_h_conj_(cp_model, p2, 0.1)
+        assert (p1 - p2) @ (v1 - v2) >= np.linalg.norm(p1 - p2) ** 2 * (1 - 1e-12)
+    # LOG mode + SP through the same API
+    sp_model = build_model(*get_server_heat_specs(7, 5, 2), SolverOptions(M.SP, None))
+    solve_model_(sp_model, 0.1 * np.ones(5), tol=1e-5, verbose=LOG, quiet=True)
+    assert sp_model.last_result["converged"] == 1
+
+
+@pytest.mark.parametrize("factor_mode", [0, 1])
+def test_large_tree_properties(cuda_lib, factor_mode):
+    """Size-independent properties at a size the oracle does not visit here (N=14, nx=20: 16383 nodes):
+    adjointness, idempotence of the projections, dynamics feasibility of S1, firm non-expansiveness,
+    per-node == per-stage factors."""
+    flat = flatten_problem(*get_random_system_specs(14, 2, 20, 8))
+    h = Handle(flat, CP, factor_mode=factor_mode, lib=cuda_lib)
+    rng = np.random.default_rng(11)
+    z, v = rng.standard_normal(h.nz), rng.standard_normal(h.nv)
+    lhs, rhs = float(h.L(z) @ v), float(z @ h.Lt(v))
+    assert abs(lhs - rhs) < 1e-9 * abs(lhs)
+    x0 = rng.standard_normal(flat.nx)
+    h.set_x0(x0)
+    p = h.prox_f(z, 0.2)
+    nx, nu, n, nnl = flat.nx, flat.nu, flat.n, flat.n_non_leaf
+    x, u = p[: n * nx].reshape(n, nx), p[n * nx: n * nx + nnl * nu].reshape(nnl, nu)
+    A = [flat.A[k * nx * nx:(k + 1) * nx * nx].reshape(nx, nx).T for k in range(2)]
+    B = [flat.B[k * nx * nu:(k + 1) * nx * nu].reshape(nu, nx).T for k in range(2)]
+    j = np.arange(2, n + 1)
+    anc, w = (j - 2) // 2, j % 2
+    for mode in (0, 1):
+        sel = w == mode
+        pred = x[anc[sel]] @ A[mode].T + u[anc[sel]] @ B[mode].T
+        assert np.max(np.abs(pred - x[j[sel] - 1])) < 1e-10 * max(1.0, np.max(np.abs(x)))
+    assert np.allclose(x[0], x0)
+    xu = p[: h.z_off[2]]
+    assert relerr(h.projection_S1(xu), xu) < 1e-9
+    q = h.prox_h_conj(v, 0.3)
+    z2 = rng.standard_normal(h.nz)
+    p2 = h.prox_f(z2, 0.2)
+    assert (p - p2) @ (z - z2) >= np.linalg.norm(p - p2) ** 2 * (1 - 1e-10)
+    v2 = rng.standard_normal(h.nv)
+    q2 = h.prox_h_conj(v2, 0.3)
+    assert (q - q2) @ (v - v2) >= np.linalg.norm(q - q2) ** 2 * (1 - 1e-10)
+    # Moreau: v = prox_{sigma h*}(v) + sigma * Proj(v/sigma +- 1/2 shifts): the dual part is in the polar set, i.e.
+    # prox_h* is idempotent-free but 1-Lipschitz; check non-expansiveness
+    assert np.linalg.norm(q - q2) <= np.linalg.norm(v - v2) * (1 + 1e-12)
+    h.close()
+
+
+def test_large_tree_matches_oracle_k_steps(cuda_lib):
+    """N=11, nx=nu=10 (2047 nodes): 50 CP passes against the oracle in both factor modes."""
+    flat = flatten_problem(*get_server_heat_specs(11, 10, 2))
+    for fm in (0, 1):
+        check_k_steps(cuda_lib, flat, CP, 50, factor_mode=fm)

@@ -1,0 +1,80 @@
+"""CPU-only parity of the PRODUCT's kernels and solver orchestration against the oracle, using the host-emulation
+build (tests/hostemu: same sources compiled with -DSPK_HOST_EMU, one lane per group, serial).  This checks index
+arithmetic and the CP/SuperMann state machines without a GPU; the GPU parity proper is tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle.oracle import CP, SP, Oracle
+from spock_b200.handle import Handle
+from tests.helpers import SMALL_PROBLEMS, check_k_steps, check_operators, flat_of, golden_cp, golden_sp, relerr
+
+
+@pytest.mark.parametrize("factor_mode", [0, 1])
+@pytest.mark.parametrize("name", list(SMALL_PROBLEMS))
+def test_operators(emu_lib, name, factor_mode):
+    check_operators(emu_lib, flat_of(name), factor_mode)
+
+
+@pytest.mark.parametrize("name", ["fixture_N3_d2", "heat_N4_d3_nx3", "l2ball_N4_d3_nx3", "random_N5_d2_nx6_nu3"])
+def test_offline_factors(emu_lib, name):
+    flat = flat_of(name)
+    o, h = Oracle(flat, CP), Handle(flat, CP, lib=emu_lib)
+    from oracle.oracle import kernel_projector
+    for i in (1, 2, flat.n_non_leaf, flat.n_non_leaf + 1, flat.n):
+        P, ABK, K, Rinv, ls = h.factors(i)
+        Po, ABKo, Ko, Rc = o.factors(i)
+        assert relerr(P, Po) < 1e-12
+        if i > 1:
+            assert relerr(ABK, ABKo) < 1e-12
+        if i <= flat.n_non_leaf:
+            assert relerr(K, Ko) < 1e-12
+            assert relerr(Rinv, np.linalg.inv(Rc @ Rc.T)) < 1e-11
+    assert relerr(ls, kernel_projector(flat.E2d, flat.F2d)) < 1e-12
+
+
+@pytest.mark.parametrize("name,alg,K", [
+    ("fixture_N3_d2", CP, 200), ("heat_N7_d2_nx5", CP, 300), ("heat_N4_d3_nx3", CP, 200),
+    ("l2ball_N4_d3_nx3", CP, 200), ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
+])
+def test_k_step_iterates(emu_lib, name, alg, K):
+    check_k_steps(emu_lib, flat_of(name), alg, K, factor_mode=K % 2)
+
+
+def test_cp_golden_trace_prefix(emu_lib):
+    gold = golden_cp()
+    h = Handle(flat_of("heat_N7_d2_nx5"), CP, lib=emu_lib)
+    res, log = h.solve(0.1 * np.ones(5), tol=1e-5, verbose_log=True, max_iter=400)
+    assert res["passes"] == 400 and res["converged"] == 0
+    assert np.max(np.abs(log["xi"] - gold[:400]) / gold[:400]) < 1e-9
+
+
+def test_sp_golden_trace_prefix(emu_lib):
+    xi, bc = golden_sp()
+    h = Handle(flat_of("heat_N7_d2_nx5"), SP, lib=emu_lib)
+    res, log = h.solve(0.1 * np.ones(5), tol=1e-5, verbose_log=True, max_iter=60)
+    assert np.max(np.abs(log["xi"][:30] - xi[:30]) / xi[:30]) < 1e-9
+    assert np.array_equal(log["backtrack_count"][:60], bc[:60])
+
+
+def test_silent_termination_and_warm_start(emu_lib):
+    flat = flat_of("heat_N7_d2_nx5")
+    for alg in (CP, SP):
+        h, o = Handle(flat, alg, lib=emu_lib), Oracle(flat, alg)
+        x0 = 0.1 * np.ones(5)
+        r1, _ = h.solve(x0, tol=1e-3)
+        r2, _ = o.solve(x0, tol=1e-3)
+        if alg == CP:
+            assert r1["passes"] == r2["passes"] and r1["printed_iter"] == r2["printed_iter"]
+            assert abs(r1["xi1"] - r2["xi1"]) < 1e-9 * r2["xi1"]
+        assert r1["converged"] == 1
+        # second solve from the stored iterate (implicit warm start, cpock.jl:169-189) needs fewer passes
+        r3, _ = h.solve(1.02 * x0, tol=1e-3)
+        assert r3["converged"] == 1 and r3["passes"] < r1["passes"]
+        # explicit z0/v0
+        r4, _ = h.solve(x0, tol=1e-3, z0=np.zeros(h.nz), v0=np.zeros(h.nv))
+        if alg == CP:  # SP keeps its Anderson memory across solves like the reference
+            assert r4["passes"] == r1["passes"]
+        with pytest.raises(Exception):
+            h.solve(x0, z0=np.zeros(h.nz))
+        with pytest.raises(ValueError):
+            h.L(np.zeros(h.nz + 1))  # implicit_l.jl:184-186
