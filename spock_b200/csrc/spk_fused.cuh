@@ -1,0 +1,582 @@
+// spk_fused.cuh -- the fused hot path: one operator evaluation T(z,v) = (zbar, vbar)
+//
+//   zbar = prox_f(z - gamma L'v),  vbar = prox_{sigma h*}(v + sigma L(2 zbar - z))      (cp.jl:5-32, sp.jl:5-32)
+//
+// Unit of work = one FAMILY: a non-leaf node i, its d children and the dual blocks that only they touch.
+//   1. spk_k_bwd, one launch per level N-2 .. 0: forms (z - gamma L'v) for x_i, u_i on the fly (L_transpose! :320-449) and
+//      does the backward step of projection_S1! (:584-637)                                   -> q, d
+//   2. spk_k_fwd_s1, one launch per level 0 .. N-2: u_i, x_children (:667-681)                -> zbar (x, u)
+//   3. spk_k_s2t, one launch: (z - gamma L'v) on (y_i, s_children, tau_children) and projection_S2! (:688-727),
+//      prox_f!'s s_1 -= gamma (:741)                                                          -> zbar (s, tau, y)
+//   4. spk_k_dual, one launch over all families: L(2 zbar - z) (:177-318) and prox_h_conj! (:911-951) for v1_i, v2_i,
+//      v7_i, (v3..v6)_children and, for leaf children, (v11..v14); plus the residuals of should_terminate!
+//      (cp.jl:54-80) xi1 = ||L'dv - dz/gamma||_inf, xi2 = ||L dz - dv/sigma||_inf and <r, P r> (spock_dot :485-516),
+//      which are all family-local                                                             -> vbar, xi1, xi2, pnorm
+// z and v are read twice per pass, zbar and vbar written once, q and d written and read once.
+//
+// Kernels 1 and 2 stream the Riccati factors: one CTA per family at a time, the family's factor slots are contiguous in
+// HBM and are fetched with TMA bulk copies (cp.async.bulk -> UBLKCP) into shared memory, completing on an mbarrier,
+// while the threads gather the family's vector entries with ordinary coalesced loads; the mat-vecs run out of shared
+// memory with the inner dimension split over the CTA and only 3-6 CTA barriers per family, so that the time a CTA
+// spends NOT waiting for HBM is short (microbenchmarks/stream_bench.cu: single-shot bulk copies of 20-60 KB reach the
+// HBM roofline as long as the consumer is quick).  With per-stage factors the matrices are fetched once per CTA.
+// Kernel 4 is one warp per family without any CTA barrier.
+#pragma once
+#include "spk_kernels.cuh"
+
+#define SPK_FUSED_MAX_D 8
+
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier
+
+#if !SPK_EMU
+SPK_D uint32_t spk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SPK_D void spk_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spk_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+SPK_D void spk_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(spk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+SPK_D void spk_bulk_g2s(void *dst_smem, const void *src_global, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   spk_smem_u32(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(spk_smem_u32(bar))
+               : "memory");
+}
+SPK_D void spk_mbar_wait(uint64_t *bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SPK_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SPK_DONE_%=;\n"
+      "bra SPK_WAIT_%=;\n"
+      "SPK_DONE_%=:\n"
+      "}\n" ::"r"(spk_smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+#else
+SPK_D void spk_mbar_init(uint64_t *, uint32_t) {}
+SPK_D void spk_mbar_expect_tx(uint64_t *, uint32_t) {}
+SPK_D void spk_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+SPK_D void spk_mbar_wait(uint64_t *, uint32_t) {}
+#endif
+
+SPK_D double spk_warp_sum(double v) {
+#if !SPK_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+SPK_D double spk_warp_max(double v) {
+#if !SPK_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+#endif
+  return v;
+}
+// max of non-negative doubles: the IEEE bit pattern is monotone, so an integer atomicMax is exact and order-free
+SPK_D void spk_atomic_max_nonneg(double *addr, double val) {
+#if !SPK_EMU
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(val));
+#else
+  if (val > *addr) *addr = val;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ launch parameters
+
+struct SpkFusedArgs {
+  int t;                   // level of the parents handled by this launch (kernels 1, 2)
+  int children_are_leaves; // t == N-2
+  double gamma, sigma;
+  const double *z, *v;     // input iterate (reference layout)
+  double *zbar, *vbar;     // output iterate
+  double *q, *dd;          // sweep scratch: q (n*nx), d (nnl*nu)
+  double *xi;              // xi[0] = xi1, xi[1] = xi2 (atomic max; reset by the first backward launch of the pass)
+  double *pnorm;           // per-family partial of <r, P r> (nnl doubles), or NULL
+  int reset_xi;            // this launch zeroes xi[0..1] (block 0)
+};
+
+SPK_HD int spk_slices(int T, int rows) { return T / rows > 1 ? T / rows : 1; }
+
+// ------------------------------------------------------------------------------------------------ 1. backward S1
+
+SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
+  const long SA = spk_slices(T, D.nx), SB = spk_slices(T, D.nu);
+  return 2 + (long)D.d * D.abk_stride + 2 * D.k_stride + D.r_stride + (long)D.d * D.nx + 4L * D.nu + D.nx + SA * D.nx +
+         SB * D.nu + 4;
+}
+
+SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  SPK_SMEM_DECL(double, smem);
+  const int nx = D.nx, nu = D.nu, d = D.d, T = blockDim.x, tid = threadIdx.x, t = A.t;
+  const int SA = spk_slices(T, nx), SB = spk_slices(T, nu);
+  const long count = spk_level_count(d, t), first0 = spk_level_first0(d, t);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  double *mABKt = smem + 2, *mG = mABKt + (long)d * D.abk_stride, *mKt = mG + D.k_stride, *mRinv = mKt + D.k_stride;
+  double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *rhs = tx + nx, *dv = rhs + nu, *dmt = dv + nu,
+         *partA = dmt + nu, *partB = partA + (long)SA * nx;
+  const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double)),
+                 bytes_r = (uint32_t)(D.r_stride * sizeof(double));
+  if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
+    A.xi[0] = 0.0;
+    A.xi[1] = 0.0;
+  }
+  if (tid == 0) spk_mbar_init(bar, 1);
+  SPK_SYNCTHREADS();
+  uint32_t phase = 0;
+  bool loaded = false;
+  for (long p = blockIdx.x; p < count; p += gridDim.x) {
+    const long i0 = first0 + p;
+    const bool fetch = D.per_node || !loaded;
+    if (fetch && tid == 0) {  // TMA: the family's factor slots are contiguous
+      const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+      spk_mbar_expect_tx(bar, bytes_abk + 2 * bytes_k + bytes_r);
+      spk_bulk_g2s(mABKt, P.ABKt + aslot * D.abk_stride, bytes_abk, bar);
+      spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
+      spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
+      spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
+    }
+    // ---- P0: gather (z - gamma L'v) for u_i, x_i and the children's q while the matrices are in flight
+    const long cfirst = (long)d * i0 + 1;  // first child (0-based node), children are consecutive
+    for (int k = tid; k < nu; k += T) {    // L_transpose! :399-420
+      double val = A.v[D.vo[6] + i0 * (nx + nu) + nx + k];
+      for (int c = 0; c < d; ++c)
+        val += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, A.v + D.vo[3] + (cfirst + c - 1) * nu);
+      tu[k] = A.z[D.zo[1] + i0 * nu + k] - A.gamma * val;
+    }
+    for (int k = tid; k < nx; k += T) {  // :351-373
+      double val = A.v[D.vo[6] + i0 * (nx + nu) + k];
+      for (int c = 0; c < d; ++c)
+        val += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, A.v + D.vo[2] + (cfirst + c - 1) * nx);
+      tx[k] = A.z[i0 * nx + k] - A.gamma * val;
+    }
+    for (int idx = tid; idx < d * nx; idx += T) {
+      if (A.children_are_leaves) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
+        const int c = idx / nx, k = idx - c * nx;
+        const long l = cfirst + c - D.nnl;
+        double val = A.v[D.vo[10] + l * nx + k];
+        val += spk_cost_row(spk_sqrtQN(D, P, l), D.cost_dense, nx, k, A.v + D.vo[7] + l * nx);
+        qc[idx] = -(A.z[(cfirst + c) * nx + k] - A.gamma * val);
+      } else {
+        qc[idx] = A.q[cfirst * nx + idx];
+      }
+    }
+    SPK_SYNCTHREADS();
+    // ---- P1: partial sums of sum_c B_w' q_c (:590-596; B' is a small table that stays in L1) and of sum_c ABK_c' q_c
+    for (int o = tid; o < nu * SB; o += T) {
+      const int k = o % nu, sl = o / nu;
+      double acc = 0.0;
+      for (int c = 0; c < d; ++c) {
+        const double *Bt = P.Bt + (long)((cfirst + c + 1) % d) * nx * nu + k;
+        const double *qj = qc + c * nx;
+        for (int m = sl; m < nx; m += SB) acc += Bt[(long)m * nu] * qj[m];
+      }
+      partB[o] = acc;
+    }
+    if (fetch) {
+      spk_mbar_wait(bar, phase);
+      phase ^= 1;
+      loaded = true;
+    }
+    for (int o = tid; o < nx * SA; o += T) {
+      const int r = o % nx, sl = o / nx;
+      double acc = 0.0;
+      for (int c = 0; c < d; ++c) {
+        const double *At = mABKt + (long)c * D.abk_stride + r;
+        const double *qj = qc + c * nx;
+        for (int m = sl; m < nx; m += SA) acc += At[(long)m * nx] * qj[m];
+      }
+      partA[o] = acc;
+    }
+    SPK_SYNCTHREADS();
+    // ---- P2: right-hand side (:598-600)
+    for (int k = tid; k < nu; k += T) {
+      double s = 0.0;
+      for (int sl = 0; sl < SB; ++sl) s += partB[sl * nu + k];
+      rhs[k] = tu[k] - s;
+    }
+    SPK_SYNCTHREADS();
+    // ---- P3: d_i = Rtilde^{-1} rhs (:601)
+    for (int k = tid; k < nu; k += T) {
+      double acc = 0.0;
+      for (int l = 0; l < nu; ++l) acc += mRinv[k + (long)l * nu] * rhs[l];
+      dv[k] = acc;
+      dmt[k] = acc - tu[k];
+      A.dd[i0 * nu + k] = acc;
+    }
+    SPK_SYNCTHREADS();
+    // ---- P4: + G d + K'(d - ubar) (:610-632)
+    for (int o = tid; o < nx * SA; o += T) {
+      const int r = o % nx, sl = o / nx;
+      double acc = partA[o];
+      for (int k = sl; k < nu; k += SA) acc += mG[r + (long)k * nx] * dv[k] + mKt[r + (long)k * nx] * dmt[k];
+      partA[o] = acc;
+    }
+    SPK_SYNCTHREADS();
+    // ---- P5: q_i (:634-636)
+    for (int r = tid; r < nx; r += T) {
+      double acc = 0.0;
+      for (int sl = 0; sl < SA; ++sl) acc += partA[sl * nx + r];
+      A.q[i0 * nx + r] = acc - tx[r];
+    }
+    SPK_SYNCTHREADS();  // shared buffers are reused by the next family
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 2. forward S1
+
+SPK_HD long spk_fwd_smem_doubles(const SpkDims &D, int T) {
+  const long R = D.nu + (long)D.d * D.nx, S = spk_slices(T, (int)R);
+  return 2 + (long)D.d * D.abk_stride + D.k_stride + D.nx + D.nu + R * S + 4;
+}
+
+SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  SPK_SMEM_DECL(double, smem);
+  const int nx = D.nx, nu = D.nu, d = D.d, T = blockDim.x, tid = threadIdx.x, t = A.t;
+  const int R = nu + d * nx, S = spk_slices(T, R);
+  const long count = spk_level_count(d, t), first0 = spk_level_first0(d, t);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  double *mABK = smem + 2, *mK = mABK + (long)d * D.abk_stride, *xb = mK + D.k_stride, *ds = xb + nx, *part = ds + nu;
+  const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double));
+  if (tid == 0) spk_mbar_init(bar, 1);
+  SPK_SYNCTHREADS();
+  uint32_t phase = 0;
+  bool loaded = false;
+  for (long p = blockIdx.x; p < count; p += gridDim.x) {
+    const long i0 = first0 + p;
+    const long cfirst = (long)d * i0 + 1;
+    const bool fetch = D.per_node || !loaded;
+    if (fetch && tid == 0) {
+      const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+      spk_mbar_expect_tx(bar, bytes_abk + bytes_k);
+      spk_bulk_g2s(mABK, P.ABK + aslot * D.abk_stride, bytes_abk, bar);
+      spk_bulk_g2s(mK, P.K + kslot * D.k_stride, bytes_k, bar);
+    }
+    for (int k = tid; k < nx; k += T) {
+      const double xv = (t == 0) ? P.x0[k] : A.zbar[i0 * nx + k];  // :667
+      xb[k] = xv;
+      if (t == 0) A.zbar[k] = xv;
+    }
+    for (int k = tid; k < nu; k += T) ds[k] = A.dd[i0 * nu + k];
+    SPK_SYNCTHREADS();
+    if (fetch) {
+      spk_mbar_wait(bar, phase);
+      phase ^= 1;
+      loaded = true;
+    }
+    // rows 0..nu-1: K x_i (:670); rows nu + c*nx + rr: ABK_c x_i + B_w d_i (:675-679)
+    for (int o = tid; o < R * S; o += T) {
+      const int r = o % R, sl = o / R;
+      double acc = 0.0;
+      if (r < nu) {
+        const double *Kr = mK + r;
+        for (int m = sl; m < nx; m += S) acc += Kr[(long)m * nu] * xb[m];
+      } else {
+        const int c = (r - nu) / nx, rr = (r - nu) - c * nx;
+        const double *Ar = mABK + (long)c * D.abk_stride + rr;
+        for (int m = sl; m < nx; m += S) acc += Ar[(long)m * nx] * xb[m];
+        const double *Bw = P.B + (long)((cfirst + c + 1) % d) * nx * nu + rr;
+        for (int k = sl; k < nu; k += S) acc += Bw[(long)k * nx] * ds[k];
+      }
+      part[o] = acc;
+    }
+    SPK_SYNCTHREADS();
+    for (int r = tid; r < R; r += T) {
+      double acc = 0.0;
+      for (int sl = 0; sl < S; ++sl) acc += part[sl * R + r];
+      if (r < nu) A.zbar[D.zo[1] + i0 * nu + r] = acc + ds[r];  // :671-673
+      else A.zbar[cfirst * nx + (r - nu)] = acc;
+    }
+    SPK_SYNCTHREADS();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. S2 on (z - gamma L'v)
+
+// One thread per non-leaf node: gathers (z - gamma L'v) for (y_i, s_children, tau_children) (L_transpose! :423-448),
+// multiplies by the kernel projector (projection_S2! :688-727) and writes zbar; thread 0 also does prox_f!'s
+// s_1 -= gamma (:741), the only s entry outside every S2 group.
+SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= D.nnl) return;
+  const int ny = D.ny, d = D.d, nls = D.nls;
+  const double gamma = A.gamma;
+  const long cfirst = (long)d * i0 + 1;
+  double in[SPK_MAX_LS];
+  const double v2i = A.v[D.vo[1] + i0];
+  for (int k = 0; k < ny; ++k) in[k] = A.z[D.zo[4] + i0 * ny + k] - gamma * (A.v[i0 * ny + k] - P.b[k] * v2i);
+  for (int c = 0; c < d; ++c) {
+    const long j0 = cfirst + c;
+    const double lt = (j0 < D.nnl) ? A.v[D.vo[1] + j0] : 0.5 * A.v[D.vo[8] + (j0 - D.nnl)] + 0.5 * A.v[D.vo[9] + (j0 - D.nnl)];
+    in[ny + c] = A.z[D.zo[2] + j0] - gamma * lt;
+    in[ny + d + c] = A.z[D.zo[3] + j0 - 1] - gamma * (0.5 * A.v[D.vo[4] + j0 - 1] + 0.5 * A.v[D.vo[5] + j0 - 1]);
+  }
+  for (int k = 0; k < nls; ++k) {
+    double acc = 0.0;
+    for (int m = 0; m < nls; ++m) acc += P.ls[k + (long)m * nls] * in[m];
+    if (k < ny) A.zbar[D.zo[4] + i0 * ny + k] = acc;
+    else if (k < ny + d) A.zbar[D.zo[2] + cfirst + (k - ny)] = acc;
+    else A.zbar[D.zo[3] + cfirst + (k - ny - d) - 1] = acc;
+  }
+  if (i0 == 0) A.zbar[D.zo[2]] = A.z[D.zo[2]] - gamma * v2i - gamma;
+}
+
+// ------------------------------------------------------------------------------------------------ 4. dual blocks
+
+SPK_D void spk_soc_coeffs(double t, double nrm, int &mode, double &tp) {  // risk_measures.jl:57-70
+  if (nrm <= t) { mode = 0; tp = 0.0; }
+  else if (nrm <= -t) { mode = 1; tp = 0.0; }
+  else { mode = 2; tp = (t + nrm) / 2.0; }
+}
+SPK_D double spk_soc_apply(int mode, double tp, double nrm, double w) {
+  return mode == 0 ? w : (mode == 1 ? 0.0 : tp * w / nrm);
+}
+
+// per-warp shared scratch (doubles): wx, dx (nx each), wu, du (nu), wy, dy, dv1 (ny), dv7 (nx+nu), per child:
+// dv3 (nx), dv4 (nu), wxc, dxc, dv11, dv14 (nx each)
+SPK_HD long spk_dual_warp_doubles(const SpkDims &D) {
+  return 3L * D.nx + 3L * D.nu + 3L * D.ny + (long)D.d * (5L * D.nx + D.nu) + 8;
+}
+
+SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  SPK_SMEM_DECL(double, smem);
+  const int nx = D.nx, nu = D.nu, d = D.d, ny = D.ny, T = blockDim.x, tid = threadIdx.x;
+  const int WL = T < 32 ? T : 32;  // lanes per warp (1 in the host-emulation test build)
+  const int wpb = T / WL, warp = tid / WL, lane = tid % WL;
+  const double gamma = A.gamma, sigma = A.sigma, inv_sigma = 1.0 / sigma, inv_gamma = 1.0 / gamma;
+  double *W = smem + (long)warp * spk_dual_warp_doubles(D);
+  double *wx = W, *dx = wx + nx, *wu = dx + nx, *du = wu + nu, *wy = du + nu, *dy = wy + ny, *dv1 = dy + ny,
+         *dv7 = dv1 + ny, *dv3 = dv7 + nx + nu, *dv4 = dv3 + (long)d * nx, *wxc = dv4 + (long)d * nu,
+         *dxc = wxc + (long)d * nx, *dv11 = dxc + (long)d * nx, *dv14 = dv11 + (long)d * nx;
+  double my_xi1 = 0.0, my_xi2 = 0.0;
+  const long nfam_stride = (long)gridDim.x * wpb;
+  for (long i0 = (long)blockIdx.x * wpb + warp; i0 < D.nnl; i0 += nfam_stride) {
+    const long cfirst = (long)d * i0 + 1;
+    const bool leaves = cfirst >= D.nnl;
+    const long lfirst = cfirst - D.nnl;
+    double my_pn = 0.0;
+    // ---- w = 2 zbar - z and delta = zbar - z of the family's primal entries
+    for (int k = lane; k < nx; k += WL) {
+      const double nb = A.zbar[i0 * nx + k], old = A.z[i0 * nx + k];
+      wx[k] = 2.0 * nb - old;
+      dx[k] = nb - old;
+    }
+    for (int k = lane; k < nu; k += WL) {
+      const double nb = A.zbar[D.zo[1] + i0 * nu + k], old = A.z[D.zo[1] + i0 * nu + k];
+      wu[k] = 2.0 * nb - old;
+      du[k] = nb - old;
+    }
+    for (int k = lane; k < ny; k += WL) {
+      const double nb = A.zbar[D.zo[4] + i0 * ny + k], old = A.z[D.zo[4] + i0 * ny + k];
+      wy[k] = 2.0 * nb - old;
+      dy[k] = nb - old;
+    }
+    if (leaves)
+      for (int k = lane; k < d * nx; k += WL) {
+        const double nb = A.zbar[cfirst * nx + k], old = A.z[cfirst * nx + k];
+        wxc[k] = 2.0 * nb - old;
+        dxc[k] = nb - old;
+      }
+    const double sb_i = A.zbar[D.zo[2] + i0], so_i = A.z[D.zo[2] + i0];
+    const double ws_i = 2.0 * sb_i - so_i, ds_i = sb_i - so_i;
+    SPK_SYNCWARP();
+#define SPK_FIN(w_, vold_, Ld_, pr_, gidx_, dslot_)                     \
+  {                                                                     \
+    const double vnew_ = sigma * ((w_) - (pr_));                        \
+    A.vbar[gidx_] = vnew_;                                              \
+    const double dl_ = vnew_ - (vold_);                                 \
+    dslot_ = dl_;                                                       \
+    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
+    my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
+  }
+    // ---- own blocks: v1_i (dual-cone projection :833-845), v2_i (:849-851), v7_i box (:903-908)
+    double dv2 = 0.0;
+    {
+      int off = 0;
+      for (int c = 0; c < D.n_cones; ++c) {
+        const int dim = D.cone_dim[c], type = D.cone_type[c];
+        double snrm = 0.0, tp = 0.0;
+        int mode = 0;
+        if (type == 4) {  // SecondOrderCone (t, x)
+          double part = 0.0;
+          for (int k = 1 + lane; k < dim; k += WL) {
+            const double w = (A.v[i0 * ny + off + k] + sigma * wy[off + k]) / sigma;
+            part += w * w;
+          }
+          snrm = sqrt(spk_warp_sum(part));
+          spk_soc_coeffs((A.v[i0 * ny + off] + sigma * wy[off]) / sigma, snrm, mode, tp);
+        }
+        for (int k = lane; k < dim; k += WL) {
+          const double vold = A.v[i0 * ny + off + k];
+          const double w = (vold + sigma * wy[off + k]) / sigma;  // L! :207-210
+          double pr;
+          if (type == 0) pr = w;                         // Zeros -> dual Reals
+          else if (type == 1) pr = w < 0.0 ? 0.0 : w;     // Nonnegatives
+          else if (type == 2) pr = w > 0.0 ? 0.0 : w;     // Nonpositives
+          else if (type == 3) pr = 0.0;                  // Reals -> dual Zeros
+          else pr = (k == 0) ? (mode == 0 ? w : (mode == 1 ? 0.0 : tp)) : spk_soc_apply(mode, tp, snrm, w);
+          SPK_FIN(w, vold, dy[off + k], pr, i0 * ny + off + k, dv1[off + k]);
+        }
+        off += dim;
+      }
+      double bwy = 0.0, bdy = 0.0;  // every lane computes b'wy (ny is tiny) so that no broadcast is needed
+      for (int k = 0; k < ny; ++k) {
+        bwy += P.b[k] * wy[k];
+        bdy += P.b[k] * dy[k];
+      }
+      const double v2old = A.v[D.vo[1] + i0];
+      const double w2 = (v2old + sigma * (ws_i - bwy)) / sigma;  // L! :214-222
+      const double v2new = sigma * (w2 - (w2 >= 0 ? w2 : 0.0));
+      dv2 = v2new - v2old;
+      if (lane == 0) {
+        A.vbar[D.vo[1] + i0] = v2new;
+        const double l2 = ds_i - bdy;
+        my_xi2 = fmax(my_xi2, fabs(l2 - dv2 * inv_sigma));
+        my_pn += dv2 * (dv2 - sigma * l2);
+      }
+    }
+    for (int k = lane; k < nx + nu; k += WL) {
+      const long e = D.vo[6] + i0 * (nx + nu) + k;
+      const double vold = A.v[e];
+      const double w = (vold + sigma * (k < nx ? wx[k] : wu[k - nx])) / sigma;  // L! :275-282
+      const double pr = k < nx ? spk_clip(w, D.x_min, D.x_max) : spk_clip(w, D.u_min, D.u_max);
+      SPK_FIN(w, vold, (k < nx ? dx[k] : du[k - nx]), pr, e, dv7[k]);
+    }
+    // ---- children: SOC(nx+nu+2) on (t = v6; v3, v4, v5) (:854-900); leaf children: SOC(nx+2) on (v13; v11, v12), v14 box
+    double xi1_tau = 0.0;
+    for (int c = 0; c < d; ++c) {
+      const long j0 = cfirst + c, jm = j0 - 1;
+      const double *sQ = spk_sqrtQ(D, P, j0), *sR = spk_sqrtR(D, P, j0);
+      const double tb = A.zbar[D.zo[3] + jm], to = A.z[D.zo[3] + jm];
+      const double wtau = 2.0 * tb - to, dtau = tb - to;
+      double part = 0.0;
+      for (int k = lane; k < nx; k += WL) {  // L! :226-235
+        const double w = (A.v[D.vo[2] + jm * nx + k] + sigma * spk_cost_row(sQ, D.cost_dense, nx, k, wx)) / sigma;
+        dv3[c * nx + k] = w;
+        part += w * w;
+      }
+      for (int k = lane; k < nu; k += WL) {  // :239-248
+        const double w = (A.v[D.vo[3] + jm * nu + k] + sigma * spk_cost_row(sR, D.cost_dense, nu, k, wu)) / sigma;
+        dv4[c * nu + k] = w;
+        part += w * w;
+      }
+      const double v5old = A.v[D.vo[4] + jm], v6old = A.v[D.vo[5] + jm];
+      const double w5 = (v5old + sigma * (0.5 * wtau)) / sigma - 0.5, tt = (v6old + sigma * (0.5 * wtau)) / sigma + 0.5;
+      if (lane == 0) part += w5 * w5;
+      const double nrm = sqrt(spk_warp_sum(part));
+      int mode;
+      double tp;
+      spk_soc_coeffs(tt, nrm, mode, tp);
+      for (int k = lane; k < nx; k += WL) {
+        const double w = dv3[c * nx + k];
+        SPK_FIN(w, A.v[D.vo[2] + jm * nx + k], spk_cost_row(sQ, D.cost_dense, nx, k, dx), spk_soc_apply(mode, tp, nrm, w),
+                D.vo[2] + jm * nx + k, dv3[c * nx + k]);
+      }
+      for (int k = lane; k < nu; k += WL) {
+        const double w = dv4[c * nu + k];
+        SPK_FIN(w, A.v[D.vo[3] + jm * nu + k], spk_cost_row(sR, D.cost_dense, nu, k, du), spk_soc_apply(mode, tp, nrm, w),
+                D.vo[3] + jm * nu + k, dv4[c * nu + k]);
+      }
+      {  // v5, v6 and the tau entry of xi1 (L_transpose! :432-437); computed by every lane, counted by lane 0
+        const double v5new = sigma * (w5 - spk_soc_apply(mode, tp, nrm, w5));
+        const double v6new = sigma * (tt - (mode == 0 ? tt : (mode == 1 ? 0.0 : tp)));
+        const double d5 = v5new - v5old, d6 = v6new - v6old, ld = 0.5 * dtau;
+        if (lane == 0) {
+          A.vbar[D.vo[4] + jm] = v5new;
+          A.vbar[D.vo[5] + jm] = v6new;
+          my_xi2 = fmax(my_xi2, fmax(fabs(ld - d5 * inv_sigma), fabs(ld - d6 * inv_sigma)));
+          my_pn += d5 * (d5 - sigma * ld) + d6 * (d6 - sigma * ld);
+          const double lt = 0.5 * d5 + 0.5 * d6;
+          xi1_tau = fmax(xi1_tau, fabs(lt - dtau * inv_gamma));
+          my_pn += dtau * (dtau - gamma * lt);
+        }
+      }
+      if (leaves) {
+        const long l = lfirst + c;
+        const double *sQN = spk_sqrtQN(D, P, l);
+        const double *wxl = wxc + (long)c * nx, *dxl = dxc + (long)c * nx;
+        const double sb = A.zbar[D.zo[2] + j0], so = A.z[D.zo[2] + j0];
+        const double wsl = 2.0 * sb - so, dsl = sb - so;
+        double pl = 0.0;
+        for (int k = lane; k < nx; k += WL) {  // L! :288-294
+          const double w = (A.v[D.vo[7] + l * nx + k] + sigma * spk_cost_row(sQN, D.cost_dense, nx, k, wxl)) / sigma;
+          dv11[c * nx + k] = w;
+          pl += w * w;
+        }
+        const double v12old = A.v[D.vo[8] + l], v13old = A.v[D.vo[9] + l];
+        const double w12 = (v12old + sigma * (0.5 * wsl)) / sigma - 0.5, tl = (v13old + sigma * (0.5 * wsl)) / sigma + 0.5;
+        if (lane == 0) pl += w12 * w12;
+        const double nrl = sqrt(spk_warp_sum(pl));
+        int ml;
+        double tpl;
+        spk_soc_coeffs(tl, nrl, ml, tpl);
+        for (int k = lane; k < nx; k += WL) {
+          const double w = dv11[c * nx + k];
+          SPK_FIN(w, A.v[D.vo[7] + l * nx + k], spk_cost_row(sQN, D.cost_dense, nx, k, dxl), spk_soc_apply(ml, tpl, nrl, w),
+                  D.vo[7] + l * nx + k, dv11[c * nx + k]);
+          const double v14old = A.v[D.vo[10] + l * nx + k];  // v14 box :804-809, L! :311-317
+          const double wb = (v14old + sigma * wxl[k]) / sigma;
+          SPK_FIN(wb, v14old, dxl[k], spk_clip(wb, D.x_min, D.x_max), D.vo[10] + l * nx + k, dv14[c * nx + k]);
+        }
+        const double v12new = sigma * (w12 - spk_soc_apply(ml, tpl, nrl, w12));
+        const double v13new = sigma * (tl - (ml == 0 ? tl : (ml == 1 ? 0.0 : tpl)));
+        const double d12 = v12new - v12old, d13 = v13new - v13old, lds = 0.5 * dsl;
+        if (lane == 0) {
+          A.vbar[D.vo[8] + l] = v12new;
+          A.vbar[D.vo[9] + l] = v13new;
+          my_xi2 = fmax(my_xi2, fmax(fabs(lds - d12 * inv_sigma), fabs(lds - d13 * inv_sigma)));
+          my_pn += d12 * (d12 - sigma * lds) + d13 * (d13 - sigma * lds);
+          const double lt = 0.5 * d12 + 0.5 * d13;  // s_leaf :445-448
+          xi1_tau = fmax(xi1_tau, fabs(lt - dsl * inv_gamma));
+          my_pn += dsl * (dsl - gamma * lt);
+        }
+      }
+    }
+#undef SPK_FIN
+    my_xi1 = fmax(my_xi1, xi1_tau);
+    SPK_SYNCWARP();
+    // ---- xi1 = || L'dv - dz/gamma ||_inf and the z-part of <r, P r> for the z entries owned by this family
+#define SPK_Z(dz_, lt_)                                        \
+  {                                                            \
+    const double dzv_ = (dz_), ltv_ = (lt_);                   \
+    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
+    my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
+  }
+    for (int k = lane; k < nx; k += WL) {  // x_i :351-373
+      double lt = dv7[k];
+      for (int c = 0; c < d; ++c) lt += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, dv3 + c * nx);
+      SPK_Z(dx[k], lt);
+    }
+    for (int k = lane; k < nu; k += WL) {  // u_i :399-420
+      double lt = dv7[nx + k];
+      for (int c = 0; c < d; ++c) lt += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, dv4 + c * nu);
+      SPK_Z(du[k], lt);
+    }
+    for (int k = lane; k < ny; k += WL) SPK_Z(dy[k], dv1[k] - P.b[k] * dv2);  // y_i :423-429
+    if (lane == 0) SPK_Z(ds_i, dv2);                                          // s_i :440-442
+    if (leaves)
+      for (int idx = lane; idx < d * nx; idx += WL) {  // x_leaf :376-396
+        const int c = idx / nx, k = idx - c * nx;
+        const double lt = dv14[idx] + spk_cost_row(spk_sqrtQN(D, P, lfirst + c), D.cost_dense, nx, k, dv11 + c * nx);
+        SPK_Z(dxc[idx], lt);
+      }
+#undef SPK_Z
+    if (A.pnorm) {  // deterministic: fixed butterfly over the lanes
+      const double ws = spk_warp_sum(my_pn);
+      if (lane == 0) A.pnorm[i0] = ws;
+    }
+    SPK_SYNCWARP();  // the warp's scratch is reused by its next family
+  }
+  const double m1 = spk_warp_max(my_xi1), m2 = spk_warp_max(my_xi2);
+  if (lane == 0) {
+    spk_atomic_max_nonneg(A.xi + 0, m1);
+    spk_atomic_max_nonneg(A.xi + 1, m2);
+  }
+}

@@ -419,7 +419,7 @@ SPK_KERNEL void spk_k_add_scalar(double *x, long idx, double a) {
 
 // Deterministic two-stage reductions: stage 1 writes one partial per block (fixed grid, fixed tree),
 // stage 2 (one block) folds the partials in a fixed order.
-// mode 0: sum x[i]*y[i]; mode 1: max |x[i]|
+// mode 0: sum x[i]*y[i]; mode 1: max |x[i]|; mode 2: sum x[i]
 SPK_KERNEL void spk_k_reduce_partial(long n, int mode, const double *__restrict__ x, const double *__restrict__ y,
                                      double *__restrict__ partial) {
   SPK_SMEM_DECL(double, sm);
@@ -427,6 +427,7 @@ SPK_KERNEL void spk_k_reduce_partial(long n, int mode, const double *__restrict_
   double acc = 0.0;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (mode == 0) acc += x[i] * y[i];
+    else if (mode == 2) acc += x[i];
     else { const double a = fabs(x[i]); acc = a > acc ? a : acc; }
   }
   sm[threadIdx.x] = acc;
@@ -434,7 +435,7 @@ SPK_KERNEL void spk_k_reduce_partial(long n, int mode, const double *__restrict_
   for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       const double o = sm[threadIdx.x + s];
-      sm[threadIdx.x] = (mode == 0) ? sm[threadIdx.x] + o : (o > sm[threadIdx.x] ? o : sm[threadIdx.x]);
+      sm[threadIdx.x] = (mode != 1) ? sm[threadIdx.x] + o : (o > sm[threadIdx.x] ? o : sm[threadIdx.x]);
     }
     SPK_SYNCTHREADS();
   }
@@ -447,18 +448,18 @@ SPK_KERNEL void spk_k_reduce_final(int np, int mode, const double *__restrict__ 
   double acc = 0.0;
   for (int i = threadIdx.x; i < np; i += blockDim.x) {
     const double o = partial[i];
-    acc = (mode == 0) ? acc + o : (o > acc ? o : acc);
+    acc = (mode != 1) ? acc + o : (o > acc ? o : acc);
   }
   sm[threadIdx.x] = acc;
   SPK_SYNCTHREADS();
   for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       const double o = sm[threadIdx.x + s];
-      sm[threadIdx.x] = (mode == 0) ? sm[threadIdx.x] + o : (o > sm[threadIdx.x] ? o : sm[threadIdx.x]);
+      sm[threadIdx.x] = (mode != 1) ? sm[threadIdx.x] + o : (o > sm[threadIdx.x] ? o : sm[threadIdx.x]);
     }
     SPK_SYNCTHREADS();
   }
-  if (threadIdx.x == 0) out[slot] = (accumulate && mode == 0) ? out[slot] + sm[0] : sm[0];
+  if (threadIdx.x == 0) out[slot] = (accumulate && mode != 1) ? out[slot] + sm[0] : sm[0];
 }
 
 // replicate table slots into per-node slots: dst[s*stride + e] = src[id(s)*stride + e]

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/spock_b200.h"
+#include "spk_fused.cuh"
 #include "spk_kernels.cuh"
 #include "spk_offline.h"
 
@@ -128,6 +129,11 @@ struct spk_handle {
   double aaR[AA_M * AA_M];  // column-major upper triangular (spock.jl:200)
   double res_0[2];
   double last_xi1 = NAN, last_xi2 = NAN;
+  // fused path (spk_fused.cuh)
+  bool fused_ok = false;
+  int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1, num_sms = 148;
+  size_t fused_smem_bwd = 0, fused_smem_fwd = 0, fused_smem_dual = 0;
+  double *d_pnorm = nullptr;
   // reductions
   double *d_partial = nullptr, *d_scal = nullptr;
   double h_scal[32];
@@ -368,6 +374,93 @@ static int op_T(spk_handle *h, const double *zv_in, double *zv_out, double gamma
   return op_prox_hconj(h, vbar, sigma, vbar);
 }
 
+// ---- fused operator evaluation (spk_fused.cuh): T(z,v) in 2(N-1) family-kernel launches.
+// Leaves xi1, xi2 of (zbar,vbar)-(z,v) in d_scal[0..1] and, if pnorm_slot >= 0, <r,Pr> in d_scal[pnorm_slot].
+static int fused_setup(spk_handle *h) {
+  const SpkDims &D = h->D;
+  h->fused_ok = false;
+  const char *env = getenv("SPK_DISABLE_FUSED");
+  if (env && env[0] == '1') return SPK_OK;
+  if (std::max(D.nx, D.nu) > 256) return SPK_OK;
+  // threads per family: enough slices of the inner dimension to keep every mat-vec short
+  int Tb = 32, Tf = 32;
+  while (Tb < 4 * std::max(D.nx, D.nu) && Tb < 256) Tb <<= 1;
+  while (Tf < 2 * (D.nu + D.d * D.nx) && Tf < 256) Tf <<= 1;
+  if (SPK_EMU) Tb = Tf = 1;
+  h->fused_threads_bwd = Tb;
+  h->fused_threads_fwd = Tf;
+  h->fused_smem_bwd = (size_t)spk_bwd_smem_doubles(D, Tb) * sizeof(double);
+  h->fused_smem_fwd = (size_t)spk_fwd_smem_doubles(D, Tf) * sizeof(double);
+  h->dual_warps = SPK_EMU ? 1 : 4;
+  h->fused_smem_dual = (size_t)spk_dual_warp_doubles(D) * h->dual_warps * sizeof(double);
+#ifndef SPK_HOST_EMU
+  if (std::max(h->fused_smem_bwd, h->fused_smem_fwd) > 227 * 1024 || h->fused_smem_dual > 200 * 1024) return SPK_OK;
+  RT_CHECK(cudaFuncSetAttribute(spk_k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
+  RT_CHECK(cudaFuncSetAttribute(spk_k_fwd_s1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
+  RT_CHECK(cudaFuncSetAttribute(spk_k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_dual));
+  cudaDeviceProp prop;
+  RT_CHECK(cudaGetDeviceProperties(&prop, h->device));
+  h->num_sms = prop.multiProcessorCount;
+  RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, spk_k_bwd, Tb, h->fused_smem_bwd));
+  RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, spk_k_fwd_s1, Tf, h->fused_smem_fwd));
+  h->occ_bwd = std::max(1, h->occ_bwd);
+  h->occ_fwd = std::max(1, h->occ_fwd);
+#endif
+  h->fused_ok = true;
+  return SPK_OK;
+}
+
+static unsigned fused_grid(const spk_handle *h, long count, int occ) {
+  // per-node factors: one family per CTA (every CTA streams its own matrices); per-stage factors: a resident wave of
+  // CTAs that fetch the level's matrices once and stride over the families
+  long g = count;
+  if (!h->D.per_node) g = std::min(count, (long)h->num_sms * occ);
+  if (SPK_EMU) g = std::min(count, 4L);
+  return (unsigned)std::max(1L, g);
+}
+
+static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
+  const SpkDims &D = h->D;
+  SpkFusedArgs A;
+  A.gamma = gamma; A.sigma = sigma;
+  A.z = zv_in; A.v = zv_in + D.nz; A.zbar = zv_out; A.vbar = zv_out + D.nz;
+  A.q = h->ric_q; A.dd = h->ric_d; A.xi = h->d_scal; A.pnorm = pnorm_slot >= 0 ? h->d_pnorm : nullptr;
+  A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0;
+  {  // 3. S2 (independent of the sweeps)
+    ProfScope ps(h, PC_S2);
+    const int b = SPK_EMU ? 1 : 128;
+    SPK_LAUNCH(spk_k_s2t, grid_for(D.nnl, b), b, 0, h->stream, D, h->P, A);
+    COUNT_LAUNCH(h, PC_S2);
+  }
+  for (int t = D.N - 2; t >= 0; --t) {  // 1. backward sweep
+    ProfScope ps(h, PC_FUSED_BWD);
+    A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
+    SPK_LAUNCH(spk_k_bwd, fused_grid(h, spk_level_count(D.d, t), h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd,
+               h->stream, D, h->P, A);
+    COUNT_LAUNCH(h, PC_FUSED_BWD);
+  }
+  A.reset_xi = 0;
+  for (int t = 0; t <= D.N - 2; ++t) {  // 2. forward sweep
+    ProfScope ps(h, PC_FUSED_FWD);
+    A.t = t; A.children_are_leaves = (t == D.N - 2);
+    SPK_LAUNCH(spk_k_fwd_s1, fused_grid(h, spk_level_count(D.d, t), h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd,
+               h->stream, D, h->P, A);
+    COUNT_LAUNCH(h, PC_FUSED_FWD);
+  }
+  {  // 4. dual blocks and residuals, all families in one launch
+    ProfScope ps(h, PC_PROX_H);
+    const int T = SPK_EMU ? 1 : 32 * h->dual_warps;
+    long g = (D.nnl + h->dual_warps - 1) / h->dual_warps;
+    g = std::min(g, (long)h->num_sms * 32);
+    if (SPK_EMU) g = std::min(g, 4L);
+    SPK_LAUNCH(spk_k_dual, (unsigned)std::max(1L, g), T, h->fused_smem_dual, h->stream, D, h->P, A);
+    COUNT_LAUNCH(h, PC_PROX_H);
+  }
+  SPK_TRY(rt_launch_check());
+  if (pnorm_slot >= 0) SPK_TRY(op_reduce(h, D.nnl, 2, h->d_pnorm, nullptr, pnorm_slot, 0));
+  return SPK_OK;
+}
+
 // spock_dot (implicit_l.jl:485-516): d_scal[slot] = <a, P b>, P(b) = (b_z - gamma L'b_v, b_v - sigma L b_z)
 static int op_pdot(spk_handle *h, const double *a_zv, const double *b_zv, double gamma, double sigma, int slot) {
   const long nz = h->D.nz, nv = h->D.nv;
@@ -422,8 +515,15 @@ static bool decide_termination(spk_handle *h, const LoopState &S, double *xi, do
 // one pass of run_cp! (cp.jl:205-228) up to and including the launches of should_terminate!
 static int cp_pass_launch(spk_handle *h, const LoopState &S) {
   const long nzv = h->D.nz + h->D.nv;
+  if (h->fused_ok && !S.verbose_log) {
+    // z_old is the input buffer itself and should_terminate!'s xi1, xi2 come out of the forward sweep (d_scal[0..1])
+    SPK_TRY(op_T_fused(h, h->zv, h->zvbar, S.gamma, S.sigma, -1));
+    std::swap(h->zv, h->zvbar);
+    return SPK_OK;
+  }
   SPK_TRY(rt_d2d(h->zv_old, h->zv, sizeof(double) * nzv, h->stream));  // :207-208
-  SPK_TRY(op_T(h, h->zv, h->zvbar, S.gamma, S.sigma));                 // :210-211
+  if (h->fused_ok) SPK_TRY(op_T_fused(h, h->zv, h->zvbar, S.gamma, S.sigma, -1));
+  else SPK_TRY(op_T(h, h->zv, h->zvbar, S.gamma, S.sigma));            // :210-211
   std::swap(h->zv, h->zvbar);                                          // :213-214 with lambda = 1
   return launch_termination(h, S);
 }
@@ -474,9 +574,14 @@ static int anderson(spk_handle *h, int iter) {
 static int sp_pass_launch(spk_handle *h, LoopState &S, int *bc) {
   const long nz = h->D.nz, nv = h->D.nv, nr = nz + nv;
   const double c1 = 0.99, q = 0.99, sigma_k2 = 0.1, lambda_sp = 1.0;  // sp.jl:366-372
-  SPK_TRY(op_T(h, h->zv, h->zvbar, S.gamma, S.sigma));                                 // :389-390
-  SPK_TRY(op_axpby(h, nr, 1.0, h->zv, -1.0, h->zvbar, h->rzv));                        // update_residual! :34-51
-  SPK_TRY(op_pdot(h, h->rzv, h->rzv, S.gamma, S.sigma, 4));
+  if (h->fused_ok) {  // T and <r,Pr> in one pair of sweeps (r = -(zbar - z, vbar - v))
+    SPK_TRY(op_T_fused(h, h->zv, h->zvbar, S.gamma, S.sigma, 4));
+    SPK_TRY(op_axpby(h, nr, 1.0, h->zv, -1.0, h->zvbar, h->rzv));
+  } else {
+    SPK_TRY(op_T(h, h->zv, h->zvbar, S.gamma, S.sigma));                               // :389-390
+    SPK_TRY(op_axpby(h, nr, 1.0, h->zv, -1.0, h->zvbar, h->rzv));                      // update_residual! :34-51
+    SPK_TRY(op_pdot(h, h->rzv, h->rzv, S.gamma, S.sigma, 4));
+  }
   SPK_TRY(op_axpby(h, nr, 1.0, h->rzv, -1.0, h->rzv_old, h->drzv));                    // update_delta_r! :257-268
   SPK_TRY(rt_d2d(h->zv_old, h->zv, sizeof(double) * nr, h->stream));                   // update_sy! :232-255
   SPK_TRY(rt_d2d(h->rzv_old, h->rzv, sizeof(double) * nr, h->stream));
@@ -487,9 +592,14 @@ static int sp_pass_launch(spk_handle *h, LoopState &S, int *bc) {
   // the same candidate.  It is evaluated once; a failed K1/K2 test reports backtrack_count = 9 like the reference.
   const double tau = 1.0;
   SPK_TRY(op_axpby(h, nr, 1.0, h->zv, tau, h->dir, h->wu));                            // generate_candidate_update! :118-131
-  SPK_TRY(op_T(h, h->wu, h->wubar, S.gamma, S.sigma));                                 // update_candidate_residual! :133-164
-  SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
-  SPK_TRY(op_pdot(h, h->rwu, h->rwu, S.gamma, S.sigma, 5));
+  if (h->fused_ok) {
+    SPK_TRY(op_T_fused(h, h->wu, h->wubar, S.gamma, S.sigma, 5));
+    SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
+  } else {
+    SPK_TRY(op_T(h, h->wu, h->wubar, S.gamma, S.sigma));                               // update_candidate_residual! :133-164
+    SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
+    SPK_TRY(op_pdot(h, h->rwu, h->rwu, S.gamma, S.sigma, 5));
+  }
   SPK_TRY(fetch_scalars(h, 6));
   const double rtilde_norm = std::sqrt(h->h_scal[5]);
   int backtrack_count = 0;
@@ -680,6 +790,8 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   h->red_blocks = SPK_EMU ? 8 : 148 * 8;
   SPK_TRY(dev_alloc(h, &h->d_partial, h->red_blocks));
   SPK_TRY(dev_alloc(h, &h->d_scal, 32));
+  SPK_TRY(dev_alloc(h, &h->d_pnorm, std::max(nnl, 1L)));
+  SPK_TRY(fused_setup(h));
   h->res_0[0] = h->res_0[1] = -INFINITY;
   if (h->alg == SPK_SP) {  // spock.jl:160-202
     SPK_TRY(dev_alloc(h, &h->rzv, nr));

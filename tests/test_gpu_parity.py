@@ -156,3 +156,26 @@ def test_large_tree_matches_oracle_k_steps(cuda_lib):
     flat = flatten_problem(*get_server_heat_specs(11, 10, 2))
     for fm in (0, 1):
         check_k_steps(cuda_lib, flat, CP, 50, factor_mode=fm)
+
+
+@pytest.mark.parametrize("name", ["fixture_N3_d2", "heat_N4_d3_nx3", "random_N3_d4_nx35_nu17", "heat_dense_N5_d2_nx4"])
+@pytest.mark.parametrize("factor_mode", [0, 1])
+def test_fused_sweeps_equal_modular_kernels(cuda_lib, name, factor_mode, monkeypatch):
+    """One operator evaluation by the fused family kernels (TMA-staged factors) == the modular kernels, and the
+    residuals that come out of the forward sweep == the ones from the explicit L / L' passes."""
+    flat = flat_of(name)
+    rng = np.random.default_rng(3)
+    monkeypatch.setenv("SPK_DISABLE_FUSED", "1")
+    hm = Handle(flat, CP, factor_mode=factor_mode, lib=cuda_lib)
+    monkeypatch.setenv("SPK_DISABLE_FUSED", "0")
+    hf = Handle(flat, CP, factor_mode=factor_mode, lib=cuda_lib)
+    z0, v0, x0 = rng.standard_normal(hm.nz), rng.standard_normal(hm.nv), rng.standard_normal(flat.nx)
+    for h in (hm, hf):
+        h.set_x0(x0)
+        h.set_iterate(z0, v0)
+        h.step(3)
+    (zm, vm), (zf, vf) = hm.get_iterate(), hf.get_iterate()
+    assert relerr(zf, zm) < 1e-12 and relerr(vf, vm) < 1e-12
+    xm, xf = hm.residuals(), hf.residuals()
+    assert abs(xm[0] - xf[0]) < 1e-11 * xm[0] and abs(xm[1] - xf[1]) < 1e-11 * xm[1]
+    assert hf.launch_count() < hm.launch_count()
