@@ -160,6 +160,10 @@ int spk_device_bytes(const spk_handle *h, int64_t *bytes);
 
 /* multi-GPU bootstrap: rank 0 fills 128 bytes, the host broadcasts them to every rank's spk_problem.comm_id */
 int spk_comm_unique_id(uint8_t id[128]);
+/* The non-leaf nodes whose families this rank computes, as contiguous ranges of 1-based node numbers (at most 64
+ * ranges; the replicated levels above the cut stage come first).  With world_size > 1 spk_get_iterate returns the
+ * rank's local view: entries of owned families (and of the replicated top) are valid, the rest is stale. */
+int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int64_t *count);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ EXPORTS = [
     "spk_last_error", "spk_version", "spk_create", "spk_destroy", "spk_sizes", "spk_offsets", "spk_tree_maps",
     "spk_set_x0", "spk_set_iterate", "spk_get_iterate", "spk_apply", "spk_dot", "spk_get_factors", "spk_step",
     "spk_solve", "spk_get_residuals", "spk_profile", "spk_profile_get", "spk_launch_count", "spk_device_bytes",
-    "spk_comm_unique_id",
+    "spk_comm_unique_id", "spk_owned_ranges",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -84,6 +84,7 @@ def bind(path: str) -> C.CDLL:
     lib.spk_launch_count.argtypes = [vp, _i64p]
     lib.spk_device_bytes.argtypes = [vp, _i64p]
     lib.spk_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    lib.spk_owned_ranges.argtypes = [vp, _i32p, _i64p, _i64p]
     for name in EXPORTS:
         if name not in ("spk_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -101,9 +101,47 @@ struct SpkFusedArgs {
   double *xi;              // xi[0] = xi1, xi[1] = xi2 (atomic max; reset by the first backward launch of the pass)
   double *pnorm;           // per-family partial of <r, P r> (nnl doubles), or NULL
   int reset_xi;            // this launch zeroes xi[0..1] (block 0)
+  // ownership (multi-GPU subtree partition; a single GPU owns everything):
+  long p_lo, p_cnt;        // kernels 1, 2: positions [p_lo, p_lo + p_cnt) of level t are processed by this rank
+  int n_ranges;            // kernels 3, 4: the owned families are n_ranges contiguous node ranges
+  long r_start[SPK_MAX_LEVELS], r_prefix[SPK_MAX_LEVELS + 1];  // range k = nodes r_start[k] .. , flat offsets r_prefix
 };
 
+// flat owned-family index -> node number
+SPK_HD long spk_owned_family(const SpkFusedArgs &A, long f) {
+  int k = 0;
+  while (k + 1 < A.n_ranges && f >= A.r_prefix[k + 1]) ++k;
+  return A.r_start[k] + (f - A.r_prefix[k]);
+}
+
 SPK_HD int spk_slices(int T, int rows) { return T / rows > 1 ? T / rows : 1; }
+
+// sum_{m in [m0, m1)} Mr[m * ld] * x[m]  -- Mr points at the row's first element; 4-way unrolled, two accumulators
+SPK_D double spk_row_dot(const double *__restrict__ Mr, int ld, const double *__restrict__ x, int m0, int m1) {
+  double a0 = 0.0, a1 = 0.0;
+  const double *Mp = Mr + (long)m0 * ld;
+  int m = m0;
+  for (; m + 4 <= m1; m += 4) {
+    a0 += Mp[0] * x[m];
+    a1 += Mp[ld] * x[m + 1];
+    a0 += Mp[2 * ld] * x[m + 2];
+    a1 += Mp[3 * ld] * x[m + 3];
+    Mp += 4 * ld;
+  }
+  for (; m < m1; ++m) {
+    a0 += Mp[0] * x[m];
+    Mp += ld;
+  }
+  return a0 + a1;
+}
+// chunk [m0, m1) of slice sl out of S over n columns
+SPK_D void spk_chunk(int n, int S, int sl, int &m0, int &m1) {
+  const int per = (n + S - 1) / S;
+  m0 = sl * per;
+  m1 = m0 + per < n ? m0 + per : n;
+  if (m0 > n) m0 = n;
+}
+
 
 // ------------------------------------------------------------------------------------------------ 1. backward S1
 
@@ -117,7 +155,7 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
   const int nx = D.nx, nu = D.nu, d = D.d, T = blockDim.x, tid = threadIdx.x, t = A.t;
   const int SA = spk_slices(T, nx), SB = spk_slices(T, nu);
-  const long count = spk_level_count(d, t), first0 = spk_level_first0(d, t);
+  const long count = A.p_cnt, first0 = spk_level_first0(d, t) + A.p_lo;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   double *mABKt = smem + 2, *mG = mABKt + (long)d * D.abk_stride, *mKt = mG + D.k_stride, *mRinv = mKt + D.k_stride;
   double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *rhs = tx + nx, *dv = rhs + nu, *dmt = dv + nu,
@@ -172,12 +210,11 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     // ---- P1: partial sums of sum_c B_w' q_c (:590-596; B' is a small table that stays in L1) and of sum_c ABK_c' q_c
     for (int o = tid; o < nu * SB; o += T) {
       const int k = o % nu, sl = o / nu;
+      int m0, m1;
+      spk_chunk(nx, SB, sl, m0, m1);
       double acc = 0.0;
-      for (int c = 0; c < d; ++c) {
-        const double *Bt = P.Bt + (long)((cfirst + c + 1) % d) * nx * nu + k;
-        const double *qj = qc + c * nx;
-        for (int m = sl; m < nx; m += SB) acc += Bt[(long)m * nu] * qj[m];
-      }
+      for (int c = 0; c < d; ++c)
+        acc += spk_row_dot(P.Bt + (long)((cfirst + c + 1) % d) * nx * nu + k, nu, qc + c * nx, m0, m1);
       partB[o] = acc;
     }
     if (fetch) {
@@ -187,12 +224,10 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     }
     for (int o = tid; o < nx * SA; o += T) {
       const int r = o % nx, sl = o / nx;
+      int m0, m1;
+      spk_chunk(nx, SA, sl, m0, m1);
       double acc = 0.0;
-      for (int c = 0; c < d; ++c) {
-        const double *At = mABKt + (long)c * D.abk_stride + r;
-        const double *qj = qc + c * nx;
-        for (int m = sl; m < nx; m += SA) acc += At[(long)m * nx] * qj[m];
-      }
+      for (int c = 0; c < d; ++c) acc += spk_row_dot(mABKt + (long)c * D.abk_stride + r, nx, qc + c * nx, m0, m1);
       partA[o] = acc;
     }
     SPK_SYNCTHREADS();
@@ -205,8 +240,7 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     SPK_SYNCTHREADS();
     // ---- P3: d_i = Rtilde^{-1} rhs (:601)
     for (int k = tid; k < nu; k += T) {
-      double acc = 0.0;
-      for (int l = 0; l < nu; ++l) acc += mRinv[k + (long)l * nu] * rhs[l];
+      const double acc = spk_row_dot(mRinv + k, nu, rhs, 0, nu);
       dv[k] = acc;
       dmt[k] = acc - tu[k];
       A.dd[i0 * nu + k] = acc;
@@ -215,9 +249,9 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     // ---- P4: + G d + K'(d - ubar) (:610-632)
     for (int o = tid; o < nx * SA; o += T) {
       const int r = o % nx, sl = o / nx;
-      double acc = partA[o];
-      for (int k = sl; k < nu; k += SA) acc += mG[r + (long)k * nx] * dv[k] + mKt[r + (long)k * nx] * dmt[k];
-      partA[o] = acc;
+      int k0, k1;
+      spk_chunk(nu, SA, sl, k0, k1);
+      partA[o] += spk_row_dot(mG + r, nx, dv, k0, k1) + spk_row_dot(mKt + r, nx, dmt, k0, k1);
     }
     SPK_SYNCTHREADS();
     // ---- P5: q_i (:634-636)
@@ -241,7 +275,7 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
   const int nx = D.nx, nu = D.nu, d = D.d, T = blockDim.x, tid = threadIdx.x, t = A.t;
   const int R = nu + d * nx, S = spk_slices(T, R);
-  const long count = spk_level_count(d, t), first0 = spk_level_first0(d, t);
+  const long count = A.p_cnt, first0 = spk_level_first0(d, t) + A.p_lo;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   double *mABK = smem + 2, *mK = mABK + (long)d * D.abk_stride, *xb = mK + D.k_stride, *ds = xb + nx, *part = ds + nu;
   const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double));
@@ -274,16 +308,17 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     // rows 0..nu-1: K x_i (:670); rows nu + c*nx + rr: ABK_c x_i + B_w d_i (:675-679)
     for (int o = tid; o < R * S; o += T) {
       const int r = o % R, sl = o / R;
-      double acc = 0.0;
+      double acc;
+      int m0, m1;
+      spk_chunk(nx, S, sl, m0, m1);
       if (r < nu) {
-        const double *Kr = mK + r;
-        for (int m = sl; m < nx; m += S) acc += Kr[(long)m * nu] * xb[m];
+        acc = spk_row_dot(mK + r, nu, xb, m0, m1);
       } else {
         const int c = (r - nu) / nx, rr = (r - nu) - c * nx;
-        const double *Ar = mABK + (long)c * D.abk_stride + rr;
-        for (int m = sl; m < nx; m += S) acc += Ar[(long)m * nx] * xb[m];
-        const double *Bw = P.B + (long)((cfirst + c + 1) % d) * nx * nu + rr;
-        for (int k = sl; k < nu; k += S) acc += Bw[(long)k * nx] * ds[k];
+        int k0, k1;
+        spk_chunk(nu, S, sl, k0, k1);
+        acc = spk_row_dot(mABK + (long)c * D.abk_stride + rr, nx, xb, m0, m1) +
+              spk_row_dot(P.B + (long)((cfirst + c + 1) % d) * nx * nu + rr, nx, ds, k0, k1);
       }
       part[o] = acc;
     }
@@ -304,8 +339,9 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
 // multiplies by the kernel projector (projection_S2! :688-727) and writes zbar; thread 0 also does prox_f!'s
 // s_1 -= gamma (:741), the only s entry outside every S2 group.
 SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
-  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 >= D.nnl) return;
+  const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= A.r_prefix[A.n_ranges]) return;
+  const long i0 = spk_owned_family(A, f);
   const int ny = D.ny, d = D.d, nls = D.nls;
   const double gamma = A.gamma;
   const long cfirst = (long)d * i0 + 1;
@@ -345,6 +381,9 @@ SPK_HD long spk_dual_warp_doubles(const SpkDims &D) {
   return 3L * D.nx + 3L * D.nu + 3L * D.ny + (long)D.d * (5L * D.nx + D.nu) + 8;
 }
 
+#if !SPK_EMU
+__launch_bounds__(128, 6)
+#endif
 SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
   const int nx = D.nx, nu = D.nu, d = D.d, ny = D.ny, T = blockDim.x, tid = threadIdx.x;
@@ -357,7 +396,8 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
          *dxc = wxc + (long)d * nx, *dv11 = dxc + (long)d * nx, *dv14 = dv11 + (long)d * nx;
   double my_xi1 = 0.0, my_xi2 = 0.0;
   const long nfam_stride = (long)gridDim.x * wpb;
-  for (long i0 = (long)blockIdx.x * wpb + warp; i0 < D.nnl; i0 += nfam_stride) {
+  for (long f = (long)blockIdx.x * wpb + warp; f < A.r_prefix[A.n_ranges]; f += nfam_stride) {
+    const long i0 = spk_owned_family(A, f);
     const long cfirst = (long)d * i0 + 1;
     const bool leaves = cfirst >= D.nnl;
     const long lfirst = cfirst - D.nnl;

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/spock_b200.h"
+#include "spk_comm.h"
 #include "spk_fused.cuh"
 #include "spk_kernels.cuh"
 #include "spk_offline.h"
@@ -129,6 +130,10 @@ struct spk_handle {
   double aaR[AA_M * AA_M];  // column-major upper triangular (spock.jl:200)
   double res_0[2];
   double last_xi1 = NAN, last_xi2 = NAN;
+  // subtree partition: levels < t_cut are replicated, rank g owns subtrees g*m_sub .. (g+1)*m_sub-1
+  SpkComm comm;
+  int rank = 0, world = 1, t_cut = 0;
+  long m_sub = 1;
   // fused path (spk_fused.cuh)
   bool fused_ok = false;
   int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1, num_sms = 148;
@@ -290,6 +295,10 @@ static int op_reduce(spk_handle *h, long n, int mode, const double *x, const dou
   return rt_launch_check();
 }
 static int fetch_scalars(spk_handle *h, int count) {
+  if (h->world > 1) {  // xi1, xi2 are maxima over the ranks' owned families
+    std::string cerr;
+    if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+  }
   return rt_d2h(h->h_scal, h->d_scal, sizeof(double) * count, h->stream);
 }
 
@@ -376,6 +385,41 @@ static int op_T(spk_handle *h, const double *zv_in, double *zv_out, double gamma
 
 // ---- fused operator evaluation (spk_fused.cuh): T(z,v) in 2(N-1) family-kernel launches.
 // Leaves xi1, xi2 of (zbar,vbar)-(z,v) in d_scal[0..1] and, if pnorm_slot >= 0, <r,Pr> in d_scal[pnorm_slot].
+// positions [lo, lo+cnt) of level t processed by this rank
+static void level_range(const spk_handle *h, int t, long &lo, long &cnt) {
+  const long full = spk_level_count(h->D.d, t);
+  if (h->world <= 1 || t < h->t_cut) { lo = 0; cnt = full; return; }
+  const long sub = spk_level_count(h->D.d, t - h->t_cut);  // nodes of level t below one cut-level node
+  lo = (long)h->rank * h->m_sub * sub;
+  cnt = h->m_sub * sub;
+}
+// owned non-leaf families as contiguous node ranges (kernels 3 and 4)
+static void fill_ranges(const spk_handle *h, SpkFusedArgs &A) {
+  const SpkDims &D = h->D;
+  if (h->world <= 1) {
+    A.n_ranges = 1; A.r_start[0] = 0; A.r_prefix[0] = 0; A.r_prefix[1] = D.nnl;
+    return;
+  }
+  int k = 0;
+  long pre = 0;
+  if (h->t_cut > 0) {
+    A.r_start[k] = 0; A.r_prefix[k] = 0;
+    pre = spk_level_first0(D.d, h->t_cut);
+    ++k;
+  }
+  for (int t = h->t_cut; t <= D.N - 2; ++t) {
+    long lo, cnt;
+    level_range(h, t, lo, cnt);
+    A.r_start[k] = spk_level_first0(D.d, t) + lo;
+    A.r_prefix[k] = pre;
+    pre += cnt;
+    ++k;
+  }
+  A.n_ranges = k;
+  A.r_prefix[k] = pre;
+}
+static int comm_fail(const std::string &err) { return fail(SPK_ERR_COMM, err); }
+
 static int fused_setup(spk_handle *h) {
   const SpkDims &D = h->D;
   h->fused_ok = false;
@@ -425,36 +469,53 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
   A.gamma = gamma; A.sigma = sigma;
   A.z = zv_in; A.v = zv_in + D.nz; A.zbar = zv_out; A.vbar = zv_out + D.nz;
   A.q = h->ric_q; A.dd = h->ric_d; A.xi = h->d_scal; A.pnorm = pnorm_slot >= 0 ? h->d_pnorm : nullptr;
-  A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0;
+  A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0; A.p_lo = 0; A.p_cnt = 0;
+  fill_ranges(h, A);
+  const long owned = A.r_prefix[A.n_ranges];
+  std::string cerr;
   {  // 3. S2 (independent of the sweeps)
     ProfScope ps(h, PC_S2);
     const int b = SPK_EMU ? 1 : 128;
-    SPK_LAUNCH(spk_k_s2t, grid_for(D.nnl, b), b, 0, h->stream, D, h->P, A);
+    SPK_LAUNCH(spk_k_s2t, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_S2);
   }
   for (int t = D.N - 2; t >= 0; --t) {  // 1. backward sweep
-    ProfScope ps(h, PC_FUSED_BWD);
-    A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
-    SPK_LAUNCH(spk_k_bwd, fused_grid(h, spk_level_count(D.d, t), h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd,
-               h->stream, D, h->P, A);
-    COUNT_LAUNCH(h, PC_FUSED_BWD);
+    {
+      ProfScope ps(h, PC_FUSED_BWD);
+      A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
+      level_range(h, t, A.p_lo, A.p_cnt);
+      SPK_LAUNCH(spk_k_bwd, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, h->stream, D,
+                 h->P, A);
+      COUNT_LAUNCH(h, PC_FUSED_BWD);
+    }
+    if (h->world > 1 && t == h->t_cut) {  // the replicated levels above the cut need every subtree root's q
+      ProfScope ps(h, PC_VEC);
+      if (!h->comm.allgather_inplace(h->ric_q + spk_level_first0(D.d, t) * D.nx, h->m_sub * D.nx, h->stream, cerr))
+        return comm_fail(cerr);
+    }
   }
   A.reset_xi = 0;
   for (int t = 0; t <= D.N - 2; ++t) {  // 2. forward sweep
     ProfScope ps(h, PC_FUSED_FWD);
     A.t = t; A.children_are_leaves = (t == D.N - 2);
-    SPK_LAUNCH(spk_k_fwd_s1, fused_grid(h, spk_level_count(D.d, t), h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd,
-               h->stream, D, h->P, A);
+    level_range(h, t, A.p_lo, A.p_cnt);
+    SPK_LAUNCH(spk_k_fwd_s1, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D,
+               h->P, A);
     COUNT_LAUNCH(h, PC_FUSED_FWD);
   }
-  {  // 4. dual blocks and residuals, all families in one launch
+  {  // 4. dual blocks and residuals, all owned families in one launch
     ProfScope ps(h, PC_PROX_H);
     const int T = SPK_EMU ? 1 : 32 * h->dual_warps;
-    long g = (D.nnl + h->dual_warps - 1) / h->dual_warps;
+    long g = (owned + h->dual_warps - 1) / h->dual_warps;
     g = std::min(g, (long)h->num_sms * 32);
     if (SPK_EMU) g = std::min(g, 4L);
     SPK_LAUNCH(spk_k_dual, (unsigned)std::max(1L, g), T, h->fused_smem_dual, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_PROX_H);
+  }
+  if (h->world > 1) {  // v2 of the subtree roots is read by the replicated family above the cut in the next evaluation
+    ProfScope ps(h, PC_VEC);
+    if (!h->comm.allgather_inplace(A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub, h->stream, cerr))
+      return comm_fail(cerr);
   }
   SPK_TRY(rt_launch_check());
   if (pnorm_slot >= 0) SPK_TRY(op_reduce(h, D.nnl, 2, h->d_pnorm, nullptr, pnorm_slot, 0));
@@ -654,7 +715,11 @@ static int check_problem(const spk_problem *p) {
   if (sum != p->ny) return fail(SPK_ERR_INVALID, "sub-cone dimensions must add up to ny");
   if (p->factor_mode != SPK_FACTORS_PER_NODE && p->factor_mode != SPK_FACTORS_PER_STAGE)
     return fail(SPK_ERR_INVALID, "unknown factor_mode");
-  if (p->world_size > 1) return fail(SPK_ERR_INVALID, "multi-GPU sharding is not available in this build");
+  if (p->world_size > 1) {
+    if (!p->comm_id) return fail(SPK_ERR_INVALID, "world_size > 1 needs comm_id (spk_comm_unique_id)");
+    if (p->rank < 0 || p->rank >= p->world_size) return fail(SPK_ERR_INVALID, "rank out of range");
+    if (p->algorithm != SPK_CP) return fail(SPK_ERR_INVALID, "the subtree partition supports the CP algorithm only");
+  }
   double dn = 1.0;
   for (int k = 0; k < p->N; ++k) dn *= p->d;
   if (dn > 4.0e9) return fail(SPK_ERR_INVALID, "tree too large");
@@ -681,6 +746,7 @@ int spk_tree_maps(int32_t N, int32_t d, int64_t *child_first, int64_t *anc, int3
 int spk_destroy(spk_handle *h) {
   if (!h) return SPK_OK;
   rt_sync(h->stream);
+  h->comm.destroy();
   for (void *p : h->allocs) rt_free(p);
 #ifndef SPK_HOST_EMU
   for (auto &s : h->prof_open) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
@@ -792,6 +858,18 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(dev_alloc(h, &h->d_scal, 32));
   SPK_TRY(dev_alloc(h, &h->d_pnorm, std::max(nnl, 1L)));
   SPK_TRY(fused_setup(h));
+  h->rank = p->rank; h->world = p->world_size > 1 ? p->world_size : 1;
+  if (h->world > 1) {
+    if (!h->fused_ok) return fail(SPK_ERR_INVALID, "the subtree partition needs the fused kernels (problem too large for shared memory)");
+    int tc = -1;
+    for (int t = 1; t <= D.N - 2; ++t)
+      if (spk_level_count(d, t) % h->world == 0) { tc = t; break; }
+    if (tc < 0) return fail(SPK_ERR_INVALID, "no tree level splits evenly over world_size ranks: report this tree at 1 GPU");
+    h->t_cut = tc;
+    h->m_sub = spk_level_count(d, tc) / h->world;
+    std::string cerr;
+    if (!h->comm.init(h->rank, h->world, p->comm_id, cerr)) return fail(SPK_ERR_COMM, cerr);
+  }
   h->res_0[0] = h->res_0[1] = -INFINITY;
   if (h->alg == SPK_SP) {  // spock.jl:160-202
     SPK_TRY(dev_alloc(h, &h->rzv, nr));
@@ -1028,6 +1106,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
     if (z0 == nullptr || v0 == nullptr) return fail(SPK_ERR_INVALID, "z0 and v0 must be given together");
     SPK_TRY(spk_set_iterate(h, z0, v0));
   }
+  if (h->world > 1 && verbose_log) return fail(SPK_ERR_INVALID, "verbose=LOG is single-GPU only");
   SPK_TRY(spk_set_x0(h, x0));                      // :185
   h->res_0[0] = h->res_0[1] = -INFINITY;           // :186
   LoopState S;
@@ -1081,6 +1160,21 @@ int spk_profile_get(spk_handle *h, int32_t cls, double *ms, int64_t *launches) {
 }
 
 int spk_comm_unique_id(uint8_t id[128]) {
-  (void)id;
-  return fail(SPK_ERR_COMM, "multi-GPU sharding is not available in this build");
+  if (!id) return fail(SPK_ERR_INVALID, "NULL argument");
+  SpkComm c;
+  std::string cerr;
+  if (!c.make_id(id, cerr)) return fail(SPK_ERR_COMM, cerr);
+  return SPK_OK;
+}
+
+int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int64_t *count) {
+  if (!h || !n_ranges) return fail(SPK_ERR_INVALID, "NULL argument");
+  SpkFusedArgs A;
+  fill_ranges(h, A);
+  *n_ranges = A.n_ranges;
+  for (int k = 0; k < A.n_ranges; ++k) {
+    if (start) start[k] = A.r_start[k] + 1;  // 1-based node numbers like the reference
+    if (count) count[k] = A.r_prefix[k + 1] - A.r_prefix[k];
+  }
+  return SPK_OK;
 }

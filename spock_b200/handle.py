@@ -161,6 +161,13 @@ class Handle:
         check(self.lib, self.lib.spk_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def owned_ranges(self):
+        """[(first node (1-based), count), ...] of the non-leaf nodes whose families this rank computes."""
+        n = C.c_int32()
+        st, ct = (C.c_int64 * 64)(), (C.c_int64 * 64)()
+        check(self.lib, self.lib.spk_owned_ranges(self._h, C.byref(n), st, ct))
+        return [(int(st[k]), int(ct[k])) for k in range(n.value)]
+
     def device_bytes(self) -> int:
         n = C.c_int64()
         check(self.lib, self.lib.spk_device_bytes(self._h, C.byref(n)))

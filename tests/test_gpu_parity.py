@@ -179,3 +179,23 @@ def test_fused_sweeps_equal_modular_kernels(cuda_lib, name, factor_mode, monkeyp
     xm, xf = hm.residuals(), hf.residuals()
     assert abs(xm[0] - xf[0]) < 1e-11 * xm[0] and abs(xm[1] - xf[1]) < 1e-11 * xm[1]
     assert hf.launch_count() < hm.launch_count()
+
+
+def test_subtree_partition_over_gpus():
+    """1-GPU vs G-GPU equality of the CP iterate (NCCL exchange of the cut-level entries); needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if g < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+         "--master-port", "29517", os.path.join(root, "tools", "multigpu_check.py")],
+        capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0 and "MULTIGPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

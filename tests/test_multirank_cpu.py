@@ -1,0 +1,118 @@
+"""The subtree partition on CPU: G ranks of the host-emulation build exchange the cut-level
+entries through the emulated communicator and must reproduce the single-rank iterate.  Ranks are threads of one
+process in the first test and world_size-2 `gloo` processes (torch.distributed) in the second."""
+import ctypes as C
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from oracle.oracle import CP
+from spock_b200 import _lib
+from spock_b200.handle import Handle
+from tests.helpers import flat_of, relerr
+from tests.multirank_helpers import assemble
+
+
+def _comm_id(lib):
+    raw = (C.c_uint8 * 128)()
+    _lib.check(lib, lib.spk_comm_unique_id(raw))
+    return np.frombuffer(bytes(raw), dtype=np.uint8).copy()
+
+
+def _run_rank(lib, flat, fm, rank, world, cid, K, out):
+    try:
+        h = Handle(flat, CP, factor_mode=fm, rank=rank, world_size=world, comm_id=cid, lib=lib)
+        h.set_x0(0.1 * np.ones(flat.nx))
+        h.step(K)
+        z, v = h.get_iterate()
+        out[rank] = (h.owned_ranges(), z, v, h.residuals(), h.z_off, h.v_off)
+        h.close()
+    except Exception as e:  # surface the failure in the main thread
+        out[rank] = e
+
+
+@pytest.mark.parametrize("name,world", [("heat_N7_d2_nx5", 2), ("heat_N7_d2_nx5", 4), ("heat_N4_d3_nx3", 3),
+                                        ("random_N5_d2_nx6_nu3", 8), ("l2ball_N4_d3_nx3", 3)])
+def test_partition_matches_single_rank_threads(emu_lib, name, world):
+    flat = flat_of(name)
+    K = 25
+    ref = Handle(flat, CP, lib=emu_lib)
+    ref.set_x0(0.1 * np.ones(flat.nx))
+    ref.step(K)
+    zr, vr = ref.get_iterate()
+    xr = ref.residuals()
+    cid = _comm_id(emu_lib)
+    out = {}
+    threads = [threading.Thread(target=_run_rank, args=(emu_lib, flat, g % 2, g, world, cid, K, out)) for g in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    for g in range(world):
+        assert g in out and not isinstance(out[g], Exception), out.get(g)
+    z, v, worst = assemble(flat, out[0][4], out[0][5], [(out[g][0], out[g][1], out[g][2]) for g in range(world)])
+    assert worst < 1e-12                      # replicated levels agree across ranks
+    assert relerr(z, zr) < 1e-12 and relerr(v, vr) < 1e-12
+    for g in range(world):                   # xi1, xi2 are global maxima on every rank
+        assert abs(out[g][3][0] - xr[0]) < 1e-12 * xr[0] and abs(out[g][3][1] - xr[1]) < 1e-12 * xr[1]
+    # ownership: every non-leaf node of the levels below the cut belongs to exactly one rank
+    owned = np.zeros(flat.n_non_leaf, int)
+    for g in range(world):
+        for first, count in out[g][0]:
+            owned[first - 1: first - 1 + count] += 1
+    assert owned.min() >= 1 and (owned[owned > 1] == world).all()
+
+
+def test_uneven_split_is_rejected(emu_lib):
+    flat = flat_of("heat_N4_d3_nx3")  # d = 3 never splits over 2 ranks
+    with pytest.raises(_lib.SpockLibraryError):
+        Handle(flat, CP, rank=0, world_size=2, comm_id=_comm_id(emu_lib), lib=emu_lib)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests.hostemu.build_hostemu import build
+
+    lib = _lib.bind(build())
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf.copy_(torch.from_numpy(_comm_id(lib)))
+    dist.broadcast(buf, 0)
+    flat = flat_of("heat_N7_d2_nx5")
+    h = Handle(flat, CP, rank=rank, world_size=world, comm_id=buf.numpy(), lib=lib)
+    res, _ = h.solve(0.1 * np.ones(5), tol=1e-3)
+    z, v = h.get_iterate()
+    q.put((rank, h.owned_ranges(), z, v, res["passes"], res["xi1"], h.z_off, h.v_off))
+    h.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_world2_gloo_processes(emu_lib):
+    import torch.multiprocessing as mp
+
+    flat = flat_of("heat_N7_d2_nx5")
+    ref = Handle(flat, CP, lib=emu_lib)
+    r0, _ = ref.solve(0.1 * np.ones(5), tol=1e-3)
+    zr, vr = ref.get_iterate()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(g, 2, port, q)) for g in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    got.sort(key=lambda t: t[0])
+    assert got[0][4] == got[1][4] == r0["passes"]          # same stopping pass on every rank as on one rank
+    assert abs(got[0][5] - r0["xi1"]) < 1e-12 * r0["xi1"]
+    z, v, worst = assemble(flat, got[0][6], got[0][7], [(g[1], g[2], g[3]) for g in got])
+    assert worst < 1e-12 and relerr(z, zr) < 1e-12 and relerr(v, vr) < 1e-12
