@@ -143,65 +143,120 @@ SPK_D void spk_chunk(int n, int S, int sl, int &m0, int &m1) {
 }
 
 
+// compile-time-length variant: PER columns starting at m0, clipped at n; fully unrolled, offsets become immediates
+template <int PER>
+SPK_D double spk_dot_fixed(const double *__restrict__ Mr, int ld, const double *__restrict__ x, int m0, int n) {
+  double a0 = 0.0, a1 = 0.0;
+  const double *Mp = Mr + (long)m0 * ld;
+  const double *xp = x + m0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    if (m0 + j < n) {
+      if (j & 1) a1 += Mp[j * ld] * xp[j];
+      else a0 += Mp[j * ld] * xp[j];
+    }
+  }
+  return a0 + a1;
+}
+// PER > 0: specialised shape (slice length known at compile time), PER == 0: runtime sizes
+template <int PER>
+SPK_D double spk_dot_any(const double *Mr, int ld, const double *x, int m0, int m1, int n) {
+  if constexpr (PER > 0) return spk_dot_fixed<PER>(Mr, ld, x, m0, n);
+  else return spk_row_dot(Mr, ld, x, m0, m1);
+}
+SPK_CONSTEXPR_HD int spk_cslices(int T, int rows) { return (T > 0 && rows > 0) ? (T / rows > 1 ? T / rows : 1) : 0; }
+SPK_CONSTEXPR_HD int spk_cper(int n, int S) { return S > 0 ? (n + S - 1) / S : 0; }
+
 // ------------------------------------------------------------------------------------------------ 1. backward S1
 
-SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
-  const long SA = spk_slices(T, D.nx), SB = spk_slices(T, D.nu);
-  return 2 + (long)D.d * D.abk_stride + 2 * D.k_stride + D.r_stride + (long)D.d * D.nx + 4L * D.nu + D.nx + SA * D.nx +
-         SB * D.nu + 4;
+// Work item of a CTA-wide mat-vec: output row r, slice sl of the inner dimension, i.e. columns [m0, m1) of an nx-wide
+// and [k0, k1) of an nu-wide operand.  The items of a thread do not depend on the family, so they are computed once
+// per kernel (runtime integer divisions are the most expensive instructions of these kernels).
+struct SpkItem {
+  int r, m0, m1, k0, k1;
+};
+SPK_D SpkItem spk_make_item(int o, int rows, int S, int nx, int nu) {
+  SpkItem it;
+  it.r = o % rows;
+  const int sl = o / rows;
+  spk_chunk(nx, S, sl, it.m0, it.m1);
+  spk_chunk(nu, S, sl, it.k0, it.k1);
+  return it;
+}
+SPK_D int spk_child_mode_dev(int d, int c) {  // mode of child ordinal c: (j0 + 1) % d with j0 = d*i0 + 1 + c
+  int m = c + 2;
+  while (m >= d) m -= d;
+  return m;
 }
 
+SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
+  const long SA = spk_slices(T, D.nx), SB = spk_slices(T, D.nu), nw = (T + 31) / 32;
+  return 2 + (long)D.d * D.abk_stride + 2 * D.k_stride + D.r_stride + (long)D.d * D.nx + D.nu + D.nx + SA * D.nx + SB * D.nu +
+         nw * 3L * D.nu + 4;
+}
+
+// NX_, NU_, D_, T_ > 0: sizes fixed at compile time (every loop unrolls, index arithmetic folds); 0: runtime sizes
+template <int NX_, int NU_, int D_, int T_>
 SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
-  const int nx = D.nx, nu = D.nu, d = D.d, T = blockDim.x, tid = threadIdx.x, t = A.t;
+  const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
+  const int tid = threadIdx.x, t = A.t;
+  const int WL = T < 32 ? T : 32, warp = tid / WL, lane = tid % WL;
   const int SA = spk_slices(T, nx), SB = spk_slices(T, nu);
+  constexpr int cSA = spk_cslices(T_, NX_), cSB = spk_cslices(T_, NU_);
+  constexpr int PER_AX = spk_cper(NX_, cSA), PER_AU = spk_cper(NU_, cSA), PER_BX = spk_cper(NX_, cSB);
   const long count = A.p_cnt, first0 = spk_level_first0(d, t) + A.p_lo;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   double *mABKt = smem + 2, *mG = mABKt + (long)d * D.abk_stride, *mKt = mG + D.k_stride, *mRinv = mKt + D.k_stride;
-  double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *rhs = tx + nx, *dv = rhs + nu, *dmt = dv + nu,
-         *partA = dmt + nu, *partB = partA + (long)SA * nx;
+  double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *partA = tx + nx, *partB = partA + (long)SA * nx,
+         *wrhs = partB + (long)SB * nu + (long)warp * 3 * nu, *wdv = wrhs + nu, *wdmt = wdv + nu;
   const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double)),
                  bytes_r = (uint32_t)(D.r_stride * sizeof(double));
+  const bool leaves = A.children_are_leaves != 0;
+  const double gamma = A.gamma;
   if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
     A.xi[0] = 0.0;
     A.xi[1] = 0.0;
   }
   if (tid == 0) spk_mbar_init(bar, 1);
+  // family-independent work items of this thread
+  const SpkItem itA = spk_make_item(tid, nx, SA, nx, nu), itB = spk_make_item(tid, nu, SB, nx, nu);
+  const int qc_c = tid / nx, qc_k = tid - qc_c * nx;  // (child, component) of this thread's q entry
   SPK_SYNCTHREADS();
   uint32_t phase = 0;
-  bool loaded = false;
+  auto fetch = [&](long i0) {  // TMA: the family's factor slots are contiguous
+    const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+    spk_mbar_expect_tx(bar, bytes_abk + 2 * bytes_k + bytes_r);
+    spk_bulk_g2s(mABKt, P.ABKt + aslot * D.abk_stride, bytes_abk, bar);
+    spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
+    spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
+    spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
+  };
+  if ((long)blockIdx.x < count && tid == 0) fetch(first0 + blockIdx.x);
+  bool pending = true;  // a fetch is in flight / not yet consumed
   for (long p = blockIdx.x; p < count; p += gridDim.x) {
     const long i0 = first0 + p;
-    const bool fetch = D.per_node || !loaded;
-    if (fetch && tid == 0) {  // TMA: the family's factor slots are contiguous
-      const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
-      spk_mbar_expect_tx(bar, bytes_abk + 2 * bytes_k + bytes_r);
-      spk_bulk_g2s(mABKt, P.ABKt + aslot * D.abk_stride, bytes_abk, bar);
-      spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
-      spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
-      spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
-    }
     // ---- P0: gather (z - gamma L'v) for u_i, x_i and the children's q while the matrices are in flight
     const long cfirst = (long)d * i0 + 1;  // first child (0-based node), children are consecutive
     for (int k = tid; k < nu; k += T) {    // L_transpose! :399-420
       double val = A.v[D.vo[6] + i0 * (nx + nu) + nx + k];
       for (int c = 0; c < d; ++c)
         val += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, A.v + D.vo[3] + (cfirst + c - 1) * nu);
-      tu[k] = A.z[D.zo[1] + i0 * nu + k] - A.gamma * val;
+      tu[k] = A.z[D.zo[1] + i0 * nu + k] - gamma * val;
     }
     for (int k = tid; k < nx; k += T) {  // :351-373
       double val = A.v[D.vo[6] + i0 * (nx + nu) + k];
       for (int c = 0; c < d; ++c)
         val += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, A.v + D.vo[2] + (cfirst + c - 1) * nx);
-      tx[k] = A.z[i0 * nx + k] - A.gamma * val;
+      tx[k] = A.z[i0 * nx + k] - gamma * val;
     }
     for (int idx = tid; idx < d * nx; idx += T) {
-      if (A.children_are_leaves) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
-        const int c = idx / nx, k = idx - c * nx;
+      if (leaves) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
+        const int c = (idx == tid) ? qc_c : idx / nx, k = (idx == tid) ? qc_k : idx - (idx / nx) * nx;
         const long l = cfirst + c - D.nnl;
         double val = A.v[D.vo[10] + l * nx + k];
         val += spk_cost_row(spk_sqrtQN(D, P, l), D.cost_dense, nx, k, A.v + D.vo[7] + l * nx);
-        qc[idx] = -(A.z[(cfirst + c) * nx + k] - A.gamma * val);
+        qc[idx] = -(A.z[(cfirst + c) * nx + k] - gamma * val);
       } else {
         qc[idx] = A.q[cfirst * nx + idx];
       }
@@ -209,58 +264,57 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     SPK_SYNCTHREADS();
     // ---- P1: partial sums of sum_c B_w' q_c (:590-596; B' is a small table that stays in L1) and of sum_c ABK_c' q_c
     for (int o = tid; o < nu * SB; o += T) {
-      const int k = o % nu, sl = o / nu;
-      int m0, m1;
-      spk_chunk(nx, SB, sl, m0, m1);
+      const SpkItem it = (o == tid) ? itB : spk_make_item(o, nu, SB, nx, nu);
       double acc = 0.0;
       for (int c = 0; c < d; ++c)
-        acc += spk_row_dot(P.Bt + (long)((cfirst + c + 1) % d) * nx * nu + k, nu, qc + c * nx, m0, m1);
+        acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_child_mode_dev(d, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
       partB[o] = acc;
     }
-    if (fetch) {
+    if (pending && (D.per_node || p == (long)blockIdx.x)) {
       spk_mbar_wait(bar, phase);
       phase ^= 1;
-      loaded = true;
     }
+    pending = false;
     for (int o = tid; o < nx * SA; o += T) {
-      const int r = o % nx, sl = o / nx;
-      int m0, m1;
-      spk_chunk(nx, SA, sl, m0, m1);
+      const SpkItem it = (o == tid) ? itA : spk_make_item(o, nx, SA, nx, nu);
       double acc = 0.0;
-      for (int c = 0; c < d; ++c) acc += spk_row_dot(mABKt + (long)c * D.abk_stride + r, nx, qc + c * nx, m0, m1);
+      for (int c = 0; c < d; ++c)
+        acc += spk_dot_any<PER_AX>(mABKt + (long)c * D.abk_stride + it.r, nx, qc + c * nx, it.m0, it.m1, nx);
       partA[o] = acc;
     }
     SPK_SYNCTHREADS();
-    // ---- P2: right-hand side (:598-600)
-    for (int k = tid; k < nu; k += T) {
-      double s = 0.0;
-      for (int sl = 0; sl < SB; ++sl) s += partB[sl * nu + k];
-      rhs[k] = tu[k] - s;
+    // ---- P2+P3, redundantly in every warp (no CTA barrier): rhs (:598-600), d_i = Rtilde^{-1} rhs (:601)
+    for (int k = lane; k < nu; k += WL) {
+      double s2 = 0.0;
+      for (int sl = 0; sl < SB; ++sl) s2 += partB[sl * nu + k];
+      wrhs[k] = tu[k] - s2;
     }
-    SPK_SYNCTHREADS();
-    // ---- P3: d_i = Rtilde^{-1} rhs (:601)
-    for (int k = tid; k < nu; k += T) {
-      const double acc = spk_row_dot(mRinv + k, nu, rhs, 0, nu);
-      dv[k] = acc;
-      dmt[k] = acc - tu[k];
-      A.dd[i0 * nu + k] = acc;
+    SPK_SYNCWARP();
+    for (int k = lane; k < nu; k += WL) {
+      const double acc = spk_dot_any<NU_>(mRinv + k, nu, wrhs, 0, nu, nu);
+      wdv[k] = acc;
+      wdmt[k] = acc - tu[k];
+      if (warp == 0) A.dd[i0 * nu + k] = acc;
     }
-    SPK_SYNCTHREADS();
+    SPK_SYNCWARP();
     // ---- P4: + G d + K'(d - ubar) (:610-632)
     for (int o = tid; o < nx * SA; o += T) {
-      const int r = o % nx, sl = o / nx;
-      int k0, k1;
-      spk_chunk(nu, SA, sl, k0, k1);
-      partA[o] += spk_row_dot(mG + r, nx, dv, k0, k1) + spk_row_dot(mKt + r, nx, dmt, k0, k1);
+      const SpkItem it = (o == tid) ? itA : spk_make_item(o, nx, SA, nx, nu);
+      partA[o] += spk_dot_any<PER_AU>(mG + it.r, nx, wdv, it.k0, it.k1, nu) + spk_dot_any<PER_AU>(mKt + it.r, nx, wdmt, it.k0, it.k1, nu);
     }
     SPK_SYNCTHREADS();
+    // the matrices are consumed: start the next family's transfer before finishing this one
+    if (D.per_node && p + gridDim.x < count) {
+      if (tid == 0) fetch(i0 + gridDim.x);
+      pending = true;
+    }
     // ---- P5: q_i (:634-636)
     for (int r = tid; r < nx; r += T) {
       double acc = 0.0;
       for (int sl = 0; sl < SA; ++sl) acc += partA[sl * nx + r];
       A.q[i0 * nx + r] = acc - tx[r];
     }
-    SPK_SYNCTHREADS();  // shared buffers are reused by the next family
+    SPK_SYNCTHREADS();  // work buffers are reused by the next family
   }
 }
 
@@ -271,28 +325,35 @@ SPK_HD long spk_fwd_smem_doubles(const SpkDims &D, int T) {
   return 2 + (long)D.d * D.abk_stride + D.k_stride + D.nx + D.nu + R * S + 4;
 }
 
+template <int NX_, int NU_, int D_, int T_>
 SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
-  const int nx = D.nx, nu = D.nu, d = D.d, T = blockDim.x, tid = threadIdx.x, t = A.t;
+  const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
+  const int tid = threadIdx.x, t = A.t;
   const int R = nu + d * nx, S = spk_slices(T, R);
+  constexpr int cS = spk_cslices(T_, NU_ + D_ * NX_);
+  constexpr int PER_X = spk_cper(NX_, cS), PER_U = spk_cper(NU_, cS);
   const long count = A.p_cnt, first0 = spk_level_first0(d, t) + A.p_lo;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   double *mABK = smem + 2, *mK = mABK + (long)d * D.abk_stride, *xb = mK + D.k_stride, *ds = xb + nx, *part = ds + nu;
   const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double));
   if (tid == 0) spk_mbar_init(bar, 1);
+  // family-independent work item of this thread: row r of [K; ABK_0; ..; ABK_{d-1}] and an inner-dimension slice
+  const SpkItem it0 = spk_make_item(tid, R, S, nx, nu);
+  const int c0 = it0.r < nu ? 0 : (it0.r - nu) / nx, rr0 = it0.r < nu ? it0.r : (it0.r - nu) - c0 * nx;
   SPK_SYNCTHREADS();
   uint32_t phase = 0;
-  bool loaded = false;
+  auto fetch = [&](long i0) {
+    const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+    spk_mbar_expect_tx(bar, bytes_abk + bytes_k);
+    spk_bulk_g2s(mABK, P.ABK + aslot * D.abk_stride, bytes_abk, bar);
+    spk_bulk_g2s(mK, P.K + kslot * D.k_stride, bytes_k, bar);
+  };
+  if ((long)blockIdx.x < count && tid == 0) fetch(first0 + blockIdx.x);
+  bool pending = true;
   for (long p = blockIdx.x; p < count; p += gridDim.x) {
     const long i0 = first0 + p;
     const long cfirst = (long)d * i0 + 1;
-    const bool fetch = D.per_node || !loaded;
-    if (fetch && tid == 0) {
-      const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
-      spk_mbar_expect_tx(bar, bytes_abk + bytes_k);
-      spk_bulk_g2s(mABK, P.ABK + aslot * D.abk_stride, bytes_abk, bar);
-      spk_bulk_g2s(mK, P.K + kslot * D.k_stride, bytes_k, bar);
-    }
     for (int k = tid; k < nx; k += T) {
       const double xv = (t == 0) ? P.x0[k] : A.zbar[i0 * nx + k];  // :667
       xb[k] = xv;
@@ -300,29 +361,34 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     }
     for (int k = tid; k < nu; k += T) ds[k] = A.dd[i0 * nu + k];
     SPK_SYNCTHREADS();
-    if (fetch) {
+    if (pending && (D.per_node || p == (long)blockIdx.x)) {
       spk_mbar_wait(bar, phase);
       phase ^= 1;
-      loaded = true;
     }
+    pending = false;
     // rows 0..nu-1: K x_i (:670); rows nu + c*nx + rr: ABK_c x_i + B_w d_i (:675-679)
     for (int o = tid; o < R * S; o += T) {
-      const int r = o % R, sl = o / R;
+      SpkItem it = it0;
+      int c = c0, rr = rr0;
+      if (o != tid) {
+        it = spk_make_item(o, R, S, nx, nu);
+        c = it.r < nu ? 0 : (it.r - nu) / nx;
+        rr = it.r < nu ? it.r : (it.r - nu) - c * nx;
+      }
       double acc;
-      int m0, m1;
-      spk_chunk(nx, S, sl, m0, m1);
-      if (r < nu) {
-        acc = spk_row_dot(mK + r, nu, xb, m0, m1);
+      if (it.r < nu) {
+        acc = spk_dot_any<PER_X>(mK + rr, nu, xb, it.m0, it.m1, nx);
       } else {
-        const int c = (r - nu) / nx, rr = (r - nu) - c * nx;
-        int k0, k1;
-        spk_chunk(nu, S, sl, k0, k1);
-        acc = spk_row_dot(mABK + (long)c * D.abk_stride + rr, nx, xb, m0, m1) +
-              spk_row_dot(P.B + (long)((cfirst + c + 1) % d) * nx * nu + rr, nx, ds, k0, k1);
+        acc = spk_dot_any<PER_X>(mABK + (long)c * D.abk_stride + rr, nx, xb, it.m0, it.m1, nx) +
+              spk_dot_any<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
       }
       part[o] = acc;
     }
     SPK_SYNCTHREADS();
+    if (D.per_node && p + gridDim.x < count) {  // matrices consumed: start the next family's transfer
+      if (tid == 0) fetch(i0 + gridDim.x);
+      pending = true;
+    }
     for (int r = tid; r < R; r += T) {
       double acc = 0.0;
       for (int sl = 0; sl < S; ++sl) acc += part[sl * R + r];

@@ -20,6 +20,7 @@
 
 #define SPK_HD __host__ __device__ __forceinline__
 #define SPK_D __device__ __forceinline__
+#define SPK_CONSTEXPR_HD __host__ __device__ constexpr
 #define SPK_KERNEL __global__
 #define SPK_SMEM_DECL(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type *name = reinterpret_cast<type *>(name##_raw)
 #define SPK_SYNCTHREADS() __syncthreads()
@@ -39,6 +40,7 @@ typedef cudaEvent_t spk_event_t;
 
 #define SPK_HD inline
 #define SPK_D inline
+#define SPK_CONSTEXPR_HD constexpr
 #define SPK_KERNEL static
 #define SPK_SYNCTHREADS() ((void)0)
 #define SPK_SYNCWARP() ((void)0)

@@ -135,7 +135,9 @@ struct spk_handle {
   int rank = 0, world = 1, t_cut = 0;
   long m_sub = 1;
   // fused path (spk_fused.cuh)
-  bool fused_ok = false;
+  bool fused_ok = false, shape_specialised = false;
+  void (*k_bwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
+  void (*k_fwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1, num_sms = 148;
   size_t fused_smem_bwd = 0, fused_smem_fwd = 0, fused_smem_dual = 0;
   double *d_pnorm = nullptr;
@@ -420,6 +422,20 @@ static void fill_ranges(const spk_handle *h, SpkFusedArgs &A) {
 }
 static int comm_fail(const std::string &err) { return fail(SPK_ERR_COMM, err); }
 
+// Shape-specialised instantiations of the two factor-streaming kernels (nx, nu, d, threads); anything else runs
+// the runtime-size instantiation <0,0,0,0>.
+typedef void (*spk_fused_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs);
+struct ShapeEntry {
+  int nx, nu, d, Tb, Tf;
+  spk_fused_kernel_t bwd, fwd;
+};
+#define SPK_SHAPE(NX, NU, DD, TB, TF) {NX, NU, DD, TB, TF, spk_k_bwd<NX, NU, DD, TB>, spk_k_fwd_s1<NX, NU, DD, TF>}
+static const ShapeEntry g_shapes[] = {
+    SPK_SHAPE(50, 20, 2, 256, 256), SPK_SHAPE(50, 50, 2, 256, 256), SPK_SHAPE(20, 20, 2, 128, 128),
+    SPK_SHAPE(10, 10, 4, 64, 128),  SPK_SHAPE(10, 10, 2, 64, 64),   SPK_SHAPE(5, 5, 2, 32, 32),
+    SPK_SHAPE(20, 20, 3, 128, 256), SPK_SHAPE(10, 10, 3, 64, 128),
+};
+
 static int fused_setup(spk_handle *h) {
   const SpkDims &D = h->D;
   h->fused_ok = false;
@@ -430,23 +446,33 @@ static int fused_setup(spk_handle *h) {
   int Tb = 32, Tf = 32;
   while (Tb < 4 * std::max(D.nx, D.nu) && Tb < 256) Tb <<= 1;
   while (Tf < 2 * (D.nu + D.d * D.nx) && Tf < 256) Tf <<= 1;
+  h->k_bwd = spk_k_bwd<0, 0, 0, 0>;
+  h->k_fwd = spk_k_fwd_s1<0, 0, 0, 0>;
+  const char *gen = getenv("SPK_GENERIC_KERNELS");
+  if (!SPK_EMU && !(gen && gen[0] == '1'))
+    for (const ShapeEntry &e : g_shapes)
+      if (e.nx == D.nx && e.nu == D.nu && e.d == D.d) {
+        Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd;
+        h->shape_specialised = true;
+      }
   if (SPK_EMU) Tb = Tf = 1;
   h->fused_threads_bwd = Tb;
   h->fused_threads_fwd = Tf;
   h->fused_smem_bwd = (size_t)spk_bwd_smem_doubles(D, Tb) * sizeof(double);
   h->fused_smem_fwd = (size_t)spk_fwd_smem_doubles(D, Tf) * sizeof(double);
+
   h->dual_warps = SPK_EMU ? 1 : 4;
   h->fused_smem_dual = (size_t)spk_dual_warp_doubles(D) * h->dual_warps * sizeof(double);
 #ifndef SPK_HOST_EMU
   if (std::max(h->fused_smem_bwd, h->fused_smem_fwd) > 227 * 1024 || h->fused_smem_dual > 200 * 1024) return SPK_OK;
-  RT_CHECK(cudaFuncSetAttribute(spk_k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
-  RT_CHECK(cudaFuncSetAttribute(spk_k_fwd_s1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
+  RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
+  RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
   RT_CHECK(cudaFuncSetAttribute(spk_k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_dual));
   cudaDeviceProp prop;
   RT_CHECK(cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
-  RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, spk_k_bwd, Tb, h->fused_smem_bwd));
-  RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, spk_k_fwd_s1, Tf, h->fused_smem_fwd));
+  RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, (const void *)h->k_bwd, Tb, h->fused_smem_bwd));
+  RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, (const void *)h->k_fwd, Tf, h->fused_smem_fwd));
   h->occ_bwd = std::max(1, h->occ_bwd);
   h->occ_fwd = std::max(1, h->occ_fwd);
 #endif
@@ -455,11 +481,10 @@ static int fused_setup(spk_handle *h) {
 }
 
 static unsigned fused_grid(const spk_handle *h, long count, int occ) {
-  // per-node factors: one family per CTA (every CTA streams its own matrices); per-stage factors: a resident wave of
-  // CTAs that fetch the level's matrices once and stride over the families
-  long g = count;
-  if (!h->D.per_node) g = std::min(count, (long)h->num_sms * occ);
-  if (SPK_EMU) g = std::min(count, 4L);
+  // persistent CTAs: one resident wave strides over the families of the level, so the per-thread index arithmetic is
+  // paid once per kernel; with per-stage factors the level's matrices are also fetched only once per CTA
+  long g = std::min(count, (long)h->num_sms * occ);
+  if (SPK_EMU) g = std::min(count, 3L);
   return (unsigned)std::max(1L, g);
 }
 
@@ -484,8 +509,8 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
       ProfScope ps(h, PC_FUSED_BWD);
       A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
       level_range(h, t, A.p_lo, A.p_cnt);
-      SPK_LAUNCH(spk_k_bwd, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, h->stream, D,
-                 h->P, A);
+      spk_fused_kernel_t kfn = h->k_bwd;
+      SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, h->stream, D, h->P, A);
       COUNT_LAUNCH(h, PC_FUSED_BWD);
     }
     if (h->world > 1 && t == h->t_cut) {  // the replicated levels above the cut need every subtree root's q
@@ -499,8 +524,8 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
     ProfScope ps(h, PC_FUSED_FWD);
     A.t = t; A.children_are_leaves = (t == D.N - 2);
     level_range(h, t, A.p_lo, A.p_cnt);
-    SPK_LAUNCH(spk_k_fwd_s1, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D,
-               h->P, A);
+    spk_fused_kernel_t kfn = h->k_fwd;
+    SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_FUSED_FWD);
   }
   {  // 4. dual blocks and residuals, all owned families in one launch
