@@ -25,6 +25,9 @@
 #include "spk_kernels.cuh"
 
 #define SPK_FUSED_MAX_D 8
+#ifndef SPK_DUAL_MINB
+#define SPK_DUAL_MINB 4
+#endif
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier
 
@@ -80,6 +83,20 @@ SPK_D double spk_warp_max(double v) {
 #endif
   return v;
 }
+// 8-byte asynchronous global->shared copies (LDGSTS); the reference layout guarantees no more than 8-byte alignment
+#if !SPK_EMU
+SPK_D void spk_cp_async8(double *dst_smem, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(spk_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+SPK_D void spk_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+#else
+SPK_D void spk_cp_async8(double *dst, const double *src) { *dst = *src; }
+SPK_D void spk_cp_async_wait_all() {}
+#endif
+
 // max of non-negative doubles: the IEEE bit pattern is monotone, so an integer atomicMax is exact and order-free
 SPK_D void spk_atomic_max_nonneg(double *addr, double val) {
 #if !SPK_EMU
@@ -447,12 +464,14 @@ SPK_HD long spk_dual_warp_doubles(const SpkDims &D) {
   return 3L * D.nx + 3L * D.nu + 3L * D.ny + (long)D.d * (5L * D.nx + D.nu) + 8;
 }
 
+template <int NX_, int NU_, int D_>
 #if !SPK_EMU
-__launch_bounds__(128, 6)
+__launch_bounds__(128, SPK_DUAL_MINB)
 #endif
 SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
-  const int nx = D.nx, nu = D.nu, d = D.d, ny = D.ny, T = blockDim.x, tid = threadIdx.x;
+  const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, ny = D.ny;
+  const int T = blockDim.x, tid = threadIdx.x;
   const int WL = T < 32 ? T : 32;  // lanes per warp (1 in the host-emulation test build)
   const int wpb = T / WL, warp = tid / WL, lane = tid % WL;
   const double gamma = A.gamma, sigma = A.sigma, inv_sigma = 1.0 / sigma, inv_gamma = 1.0 / gamma;
@@ -469,12 +488,12 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     const long lfirst = cfirst - D.nnl;
     double my_pn = 0.0;
     // ---- w = 2 zbar - z and delta = zbar - z of the family's primal entries
-    for (int k = lane; k < nx; k += WL) {
+    _Pragma("unroll") for (int k = lane; k < nx; k += WL) {
       const double nb = A.zbar[i0 * nx + k], old = A.z[i0 * nx + k];
       wx[k] = 2.0 * nb - old;
       dx[k] = nb - old;
     }
-    for (int k = lane; k < nu; k += WL) {
+    _Pragma("unroll") for (int k = lane; k < nu; k += WL) {
       const double nb = A.zbar[D.zo[1] + i0 * nu + k], old = A.z[D.zo[1] + i0 * nu + k];
       wu[k] = 2.0 * nb - old;
       du[k] = nb - old;
@@ -548,7 +567,7 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         my_pn += dv2 * (dv2 - sigma * l2);
       }
     }
-    for (int k = lane; k < nx + nu; k += WL) {
+    _Pragma("unroll") for (int k = lane; k < nx + nu; k += WL) {
       const long e = D.vo[6] + i0 * (nx + nu) + k;
       const double vold = A.v[e];
       const double w = (vold + sigma * (k < nx ? wx[k] : wu[k - nx])) / sigma;  // L! :275-282
@@ -557,18 +576,18 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     }
     // ---- children: SOC(nx+nu+2) on (t = v6; v3, v4, v5) (:854-900); leaf children: SOC(nx+2) on (v13; v11, v12), v14 box
     double xi1_tau = 0.0;
-    for (int c = 0; c < d; ++c) {
+    _Pragma("unroll") for (int c = 0; c < d; ++c) {
       const long j0 = cfirst + c, jm = j0 - 1;
       const double *sQ = spk_sqrtQ(D, P, j0), *sR = spk_sqrtR(D, P, j0);
       const double tb = A.zbar[D.zo[3] + jm], to = A.z[D.zo[3] + jm];
       const double wtau = 2.0 * tb - to, dtau = tb - to;
       double part = 0.0;
-      for (int k = lane; k < nx; k += WL) {  // L! :226-235
+      _Pragma("unroll") for (int k = lane; k < nx; k += WL) {  // L! :226-235
         const double w = (A.v[D.vo[2] + jm * nx + k] + sigma * spk_cost_row(sQ, D.cost_dense, nx, k, wx)) / sigma;
         dv3[c * nx + k] = w;
         part += w * w;
       }
-      for (int k = lane; k < nu; k += WL) {  // :239-248
+      _Pragma("unroll") for (int k = lane; k < nu; k += WL) {  // :239-248
         const double w = (A.v[D.vo[3] + jm * nu + k] + sigma * spk_cost_row(sR, D.cost_dense, nu, k, wu)) / sigma;
         dv4[c * nu + k] = w;
         part += w * w;
@@ -580,12 +599,12 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
       int mode;
       double tp;
       spk_soc_coeffs(tt, nrm, mode, tp);
-      for (int k = lane; k < nx; k += WL) {
+      _Pragma("unroll") for (int k = lane; k < nx; k += WL) {
         const double w = dv3[c * nx + k];
         SPK_FIN(w, A.v[D.vo[2] + jm * nx + k], spk_cost_row(sQ, D.cost_dense, nx, k, dx), spk_soc_apply(mode, tp, nrm, w),
                 D.vo[2] + jm * nx + k, dv3[c * nx + k]);
       }
-      for (int k = lane; k < nu; k += WL) {
+      _Pragma("unroll") for (int k = lane; k < nu; k += WL) {
         const double w = dv4[c * nu + k];
         SPK_FIN(w, A.v[D.vo[3] + jm * nu + k], spk_cost_row(sR, D.cost_dense, nu, k, du), spk_soc_apply(mode, tp, nrm, w),
                 D.vo[3] + jm * nu + k, dv4[c * nu + k]);
@@ -611,7 +630,7 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         const double sb = A.zbar[D.zo[2] + j0], so = A.z[D.zo[2] + j0];
         const double wsl = 2.0 * sb - so, dsl = sb - so;
         double pl = 0.0;
-        for (int k = lane; k < nx; k += WL) {  // L! :288-294
+        _Pragma("unroll") for (int k = lane; k < nx; k += WL) {  // L! :288-294
           const double w = (A.v[D.vo[7] + l * nx + k] + sigma * spk_cost_row(sQN, D.cost_dense, nx, k, wxl)) / sigma;
           dv11[c * nx + k] = w;
           pl += w * w;
@@ -623,7 +642,7 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         int ml;
         double tpl;
         spk_soc_coeffs(tl, nrl, ml, tpl);
-        for (int k = lane; k < nx; k += WL) {
+        _Pragma("unroll") for (int k = lane; k < nx; k += WL) {
           const double w = dv11[c * nx + k];
           SPK_FIN(w, A.v[D.vo[7] + l * nx + k], spk_cost_row(sQN, D.cost_dense, nx, k, dxl), spk_soc_apply(ml, tpl, nrl, w),
                   D.vo[7] + l * nx + k, dv11[c * nx + k]);
@@ -655,12 +674,12 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
     my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
   }
-    for (int k = lane; k < nx; k += WL) {  // x_i :351-373
+    _Pragma("unroll") for (int k = lane; k < nx; k += WL) {  // x_i :351-373
       double lt = dv7[k];
       for (int c = 0; c < d; ++c) lt += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, dv3 + c * nx);
       SPK_Z(dx[k], lt);
     }
-    for (int k = lane; k < nu; k += WL) {  // u_i :399-420
+    _Pragma("unroll") for (int k = lane; k < nu; k += WL) {  // u_i :399-420
       double lt = dv7[nx + k];
       for (int c = 0; c < d; ++c) lt += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, dv4 + c * nu);
       SPK_Z(du[k], lt);
@@ -684,5 +703,318 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   if (lane == 0) {
     spk_atomic_max_nonneg(A.xi + 0, m1);
     spk_atomic_max_nonneg(A.xi + 1, m2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 4b. batched dual kernel
+//
+// Same arithmetic as spk_k_dual, organised for memory-level parallelism: a CTA takes F consecutive families (all their
+// segments are contiguous in the reference layout), stages every input with one burst of coalesced loads while forming
+// w = 2 zbar - z and delta = zbar - z, and then runs element-parallel phases out of shared memory:
+//   P2  W = (v + sigma L w)/sigma (+-1/2)      P3  SOC norms, one warp per block
+//   P4  projection, vbar store, delta v, xi2   P5  xi1 and the z-part of <r, P r>
+// A launch covers families whose children are all non-leaf or all leaf (A.children_are_leaves).
+struct SpkDualMap {
+  long wx, dx, wu, du, wy, dy, ws, ds, wsc, dsc, wtau, dtau, wxc, dxc;          // primal: w and delta
+  long v1, v2, v7, v3, v4, v5, v6, v11, v12, v13, v14;                          // old dual values
+  long W1, W2, W7, W3, W4, W5, W6, W11, W12, W13, W14;                          // W, later delta v
+  long nrm, red, total;
+};
+SPK_HD SpkDualMap spk_dual_map(int nx, int nu, int d, int ny, int F, bool leaves) {
+  SpkDualMap m;
+  long o = 0;
+  auto take = [&](long cnt) { const long r = o; o += cnt; return r; };
+  const long fx = (long)F * nx, fu = (long)F * nu, fy = (long)F * ny, fd = (long)F * d, fdx = fd * nx, fdu = fd * nu;
+  m.wx = take(fx); m.dx = take(fx); m.wu = take(fu); m.du = take(fu); m.wy = take(fy); m.dy = take(fy);
+  m.ws = take(F); m.ds = take(F); m.wsc = take(fd); m.dsc = take(fd); m.wtau = take(fd); m.dtau = take(fd);
+  m.wxc = take(leaves ? fdx : 0); m.dxc = take(leaves ? fdx : 0);
+  m.v1 = take(fy); m.v2 = take(F); m.v7 = take(fx + fu); m.v3 = take(fdx); m.v4 = take(fdu); m.v5 = take(fd); m.v6 = take(fd);
+  m.v11 = take(leaves ? fdx : 0); m.v12 = take(leaves ? fd : 0); m.v13 = take(leaves ? fd : 0); m.v14 = take(leaves ? fdx : 0);
+  m.W1 = take(fy); m.W2 = take(F); m.W7 = take(fx + fu); m.W3 = take(fdx); m.W4 = take(fdu); m.W5 = take(fd); m.W6 = take(fd);
+  m.W11 = take(leaves ? fdx : 0); m.W12 = take(leaves ? fd : 0); m.W13 = take(leaves ? fd : 0); m.W14 = take(leaves ? fdx : 0);
+  m.nrm = take(2 * fd); m.red = take(3 * 32);
+  m.total = o + 2;
+  return m;
+}
+
+template <int NX_, int NU_, int D_>
+#if !SPK_EMU
+__launch_bounds__(256, 4)
+#endif
+SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fam_lo, long fam_cnt) {
+  SPK_SMEM_DECL(double, S);
+  const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, ny = D.ny;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int WL = T < 32 ? T : 32, nwarps = (T + WL - 1) / WL, warp = tid / WL, lane = tid % WL;
+  const double gamma = A.gamma, sigma = A.sigma, inv_sigma = 1.0 / sigma, inv_gamma = 1.0 / gamma;
+  const bool leaves = A.children_are_leaves != 0;
+  const SpkDualMap M = spk_dual_map(nx, nu, d, ny, F, leaves);
+  const int nxu = nx + nu;
+  double my_xi1 = 0.0, my_xi2 = 0.0, my_pn = 0.0;
+  const long nbatch = (fam_cnt + F - 1) / F;
+  for (long b = blockIdx.x; b < nbatch; b += gridDim.x) {
+    const long i0 = fam_lo + b * F;                                  // first family of the batch
+    const int f = (int)((fam_cnt - b * F) < F ? (fam_cnt - b * F) : F);  // families in this batch
+    const long cfirst = (long)d * i0 + 1, lfirst = cfirst - D.nnl;
+    const int fd = f * d;
+    // ---- P1: stage every input with asynchronous copies (all in flight at once), then turn the primal pairs
+    //      (z, zbar) into w = 2 zbar - z and delta = zbar - z in place
+#define SPK_LOADWD(cnt_, zoff_, wslot_, dslot_)                     \
+  for (int e = tid; e < (cnt_); e += T) {                           \
+    spk_cp_async8(S + (wslot_) + e, A.z + (zoff_) + e);             \
+    spk_cp_async8(S + (dslot_) + e, A.zbar + (zoff_) + e);          \
+  }
+#define SPK_LOADV(cnt_, voff_, slot_) \
+  for (int e = tid; e < (cnt_); e += T) spk_cp_async8(S + (slot_) + e, A.v + (voff_) + e);
+    SPK_LOADWD(f * nx, i0 * nx, M.wx, M.dx)
+    SPK_LOADWD(f * nu, D.zo[1] + i0 * nu, M.wu, M.du)
+    SPK_LOADWD(f * ny, D.zo[4] + i0 * ny, M.wy, M.dy)
+    SPK_LOADWD(f, D.zo[2] + i0, M.ws, M.ds)
+    SPK_LOADWD(fd, D.zo[2] + cfirst, M.wsc, M.dsc)
+    SPK_LOADWD(fd, D.zo[3] + cfirst - 1, M.wtau, M.dtau)
+    SPK_LOADV(f * ny, i0 * ny, M.v1)
+    SPK_LOADV(f, D.vo[1] + i0, M.v2)
+    SPK_LOADV(f * nxu, D.vo[6] + i0 * nxu, M.v7)
+    SPK_LOADV(fd * nx, D.vo[2] + (cfirst - 1) * nx, M.v3)
+    SPK_LOADV(fd * nu, D.vo[3] + (cfirst - 1) * nu, M.v4)
+    SPK_LOADV(fd, D.vo[4] + cfirst - 1, M.v5)
+    SPK_LOADV(fd, D.vo[5] + cfirst - 1, M.v6)
+    if (leaves) {
+      SPK_LOADWD(fd * nx, cfirst * nx, M.wxc, M.dxc)
+      SPK_LOADV(fd * nx, D.vo[7] + lfirst * nx, M.v11)
+      SPK_LOADV(fd, D.vo[8] + lfirst, M.v12)
+      SPK_LOADV(fd, D.vo[9] + lfirst, M.v13)
+      SPK_LOADV(fd * nx, D.vo[10] + lfirst * nx, M.v14)
+    }
+#undef SPK_LOADWD
+#undef SPK_LOADV
+    spk_cp_async_wait_all();
+    SPK_SYNCTHREADS();
+    // the primal slots are laid out as consecutive (w, delta) pairs of equal length: wx,dx | wu,du | wy,dy | ws,ds | ...
+#define SPK_WD(cnt_, wslot_, dslot_)                                \
+  for (int e = tid; e < (cnt_); e += T) {                           \
+    const double old_ = S[(wslot_) + e], nb_ = S[(dslot_) + e];     \
+    S[(wslot_) + e] = 2.0 * nb_ - old_;                             \
+    S[(dslot_) + e] = nb_ - old_;                                   \
+  }
+    SPK_WD(f * nx, M.wx, M.dx)
+    SPK_WD(f * nu, M.wu, M.du)
+    SPK_WD(f * ny, M.wy, M.dy)
+    SPK_WD(f, M.ws, M.ds)
+    SPK_WD(fd, M.wsc, M.dsc)
+    SPK_WD(fd, M.wtau, M.dtau)
+    if (leaves) SPK_WD(fd * nx, M.wxc, M.dxc)
+#undef SPK_WD
+    SPK_SYNCTHREADS();
+    // ---- P2: W = (v + sigma L(2zbar - z)) / sigma with the +-1/2 shifts (prox_h_conj! :923-939, L! :177-318)
+    for (int e = tid; e < f * ny; e += T) S[M.W1 + e] = (S[M.v1 + e] + sigma * S[M.wy + e]) / sigma;
+    for (int ff = tid; ff < f; ff += T) {
+      double bwy = 0.0;
+      for (int k = 0; k < ny; ++k) bwy += P.b[k] * S[M.wy + ff * ny + k];
+      S[M.W2 + ff] = (S[M.v2 + ff] + sigma * (S[M.ws + ff] - bwy)) / sigma;
+    }
+    for (int e = tid; e < f * nxu; e += T) {
+      const int ff = e / nxu, k = e - ff * nxu;
+      S[M.W7 + e] = (S[M.v7 + e] + sigma * (k < nx ? S[M.wx + ff * nx + k] : S[M.wu + ff * nu + k - nx])) / sigma;
+    }
+    for (int e = tid; e < fd * nx; e += T) {
+      const int fc = e / nx, k = e - fc * nx, ff = fc / d;
+      S[M.W3 + e] = (S[M.v3 + e] + sigma * spk_cost_row(spk_sqrtQ(D, P, cfirst + fc), D.cost_dense, nx, k, S + M.wx + ff * nx)) / sigma;
+      if (leaves) {
+        const double *wxl = S + M.wxc + fc * nx;
+        S[M.W11 + e] = (S[M.v11 + e] + sigma * spk_cost_row(spk_sqrtQN(D, P, lfirst + fc), D.cost_dense, nx, k, wxl)) / sigma;
+        S[M.W14 + e] = (S[M.v14 + e] + sigma * wxl[k]) / sigma;
+      }
+    }
+    for (int e = tid; e < fd * nu; e += T) {
+      const int fc = e / nu, k = e - fc * nu, ff = fc / d;
+      S[M.W4 + e] = (S[M.v4 + e] + sigma * spk_cost_row(spk_sqrtR(D, P, cfirst + fc), D.cost_dense, nu, k, S + M.wu + ff * nu)) / sigma;
+    }
+    for (int fc = tid; fc < fd; fc += T) {
+      S[M.W5 + fc] = (S[M.v5 + fc] + sigma * (0.5 * S[M.wtau + fc])) / sigma - 0.5;
+      S[M.W6 + fc] = (S[M.v6 + fc] + sigma * (0.5 * S[M.wtau + fc])) / sigma + 0.5;
+      if (leaves) {
+        S[M.W12 + fc] = (S[M.v12 + fc] + sigma * (0.5 * S[M.wsc + fc])) / sigma - 0.5;
+        S[M.W13 + fc] = (S[M.v13 + fc] + sigma * (0.5 * S[M.wsc + fc])) / sigma + 0.5;
+      }
+    }
+    SPK_SYNCTHREADS();
+    // ---- P3: SOC norms, one warp per block: [0, fd) children (v3, v4, v5), [fd, 2fd) leaf children (v11, v12)
+    for (int bb = warp; bb < (leaves ? 2 * fd : fd); bb += nwarps) {
+      double part = 0.0;
+      if (bb < fd) {
+        for (int k = lane; k < nx; k += WL) { const double w = S[M.W3 + bb * nx + k]; part += w * w; }
+        for (int k = lane; k < nu; k += WL) { const double w = S[M.W4 + bb * nu + k]; part += w * w; }
+        if (lane == 0) part += S[M.W5 + bb] * S[M.W5 + bb];
+      } else {
+        const int fc = bb - fd;
+        for (int k = lane; k < nx; k += WL) { const double w = S[M.W11 + fc * nx + k]; part += w * w; }
+        if (lane == 0) part += S[M.W12 + fc] * S[M.W12 + fc];
+      }
+      part = spk_warp_sum(part);
+      if (lane == 0) S[M.nrm + bb] = sqrt(part);
+    }
+    SPK_SYNCTHREADS();
+    // ---- P4: projections (:752-909), vbar = sigma (W - Proj W), delta v (into the W slots), xi2, v-part of <r, P r>
+#define SPK_FIN(Wslot, vold_, Ld_, pr_, gidx_)                          \
+  {                                                                     \
+    const double vnew_ = sigma * (S[Wslot] - (pr_));                    \
+    A.vbar[gidx_] = vnew_;                                              \
+    const double dl_ = vnew_ - (vold_);                                 \
+    S[Wslot] = dl_;                                                     \
+    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
+    my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
+  }
+    {  // v1: dual-cone projection per family (:833-845); SOC sub-cones are handled by one thread per family
+      bool has_soc = false;
+      for (int c = 0; c < D.n_cones; ++c) has_soc |= (D.cone_type[c] == 4);
+      if (!has_soc) {
+        for (int e = tid; e < f * ny; e += T) {
+          const int ff = e / ny, k = e - ff * ny;
+          int off = 0, type = 0;
+          for (int c = 0; c < D.n_cones; ++c) {
+            if (k < off + D.cone_dim[c]) { type = D.cone_type[c]; break; }
+            off += D.cone_dim[c];
+          }
+          const double w = S[M.W1 + e];
+          const double pr = type == 0 ? w : (type == 1 ? (w < 0.0 ? 0.0 : w) : (type == 2 ? (w > 0.0 ? 0.0 : w) : 0.0));
+          SPK_FIN(M.W1 + e, S[M.v1 + e], S[M.dy + e], pr, (i0 + ff) * ny + k);
+        }
+      } else {
+        for (int ff = tid; ff < f; ff += T) {
+          double pr[SPK_MAX_LS];
+          for (int k = 0; k < ny; ++k) pr[k] = S[M.W1 + ff * ny + k];
+          int off = 0;
+          for (int c = 0; c < D.n_cones; ++c) {
+            const int dim = D.cone_dim[c];
+            switch (D.cone_type[c]) {
+              case 0: break;
+              case 1: for (int k = 0; k < dim; ++k) if (pr[off + k] < 0.0) pr[off + k] = 0.0; break;
+              case 2: for (int k = 0; k < dim; ++k) if (pr[off + k] > 0.0) pr[off + k] = 0.0; break;
+              case 3: for (int k = 0; k < dim; ++k) pr[off + k] = 0.0; break;
+              case 4: spk_project_soc_serial(pr + off, dim); break;
+            }
+            off += dim;
+          }
+          for (int k = 0; k < ny; ++k)
+            SPK_FIN(M.W1 + ff * ny + k, S[M.v1 + ff * ny + k], S[M.dy + ff * ny + k], pr[k], (i0 + ff) * ny + k);
+        }
+      }
+    }
+    for (int ff = tid; ff < f; ff += T) {  // v2 (:849-851)
+      double bdy = 0.0;
+      for (int k = 0; k < ny; ++k) bdy += P.b[k] * S[M.dy + ff * ny + k];
+      const double w2 = S[M.W2 + ff];
+      SPK_FIN(M.W2 + ff, S[M.v2 + ff], S[M.ds + ff] - bdy, (w2 >= 0 ? w2 : 0.0), D.vo[1] + i0 + ff);
+    }
+    for (int e = tid; e < f * nxu; e += T) {  // v7 box (:903-908)
+      const int ff = e / nxu, k = e - ff * nxu;
+      const double w = S[M.W7 + e];
+      const double pr = k < nx ? spk_clip(w, D.x_min, D.x_max) : spk_clip(w, D.u_min, D.u_max);
+      SPK_FIN(M.W7 + e, S[M.v7 + e], (k < nx ? S[M.dx + ff * nx + k] : S[M.du + ff * nu + k - nx]), pr,
+              D.vo[6] + i0 * nxu + e);
+    }
+    for (int e = tid; e < fd * nx; e += T) {  // v3 (:854-900) and, for leaf children, v11, v14 (:768-809)
+      const int fc = e / nx, k = e - fc * nx, ff = fc / d;
+      int mode;
+      double tp;
+      const double nrm = S[M.nrm + fc];
+      spk_soc_coeffs(S[M.W6 + fc], nrm, mode, tp);
+      const double ld = spk_cost_row(spk_sqrtQ(D, P, cfirst + fc), D.cost_dense, nx, k, S + M.dx + ff * nx);
+      SPK_FIN(M.W3 + e, S[M.v3 + e], ld, spk_soc_apply(mode, tp, nrm, S[M.W3 + e]), D.vo[2] + (cfirst - 1) * nx + e);
+      if (leaves) {
+        const double nrl = S[M.nrm + fd + fc];
+        spk_soc_coeffs(S[M.W13 + fc], nrl, mode, tp);
+        const double *dxl = S + M.dxc + fc * nx;
+        const double ld11 = spk_cost_row(spk_sqrtQN(D, P, lfirst + fc), D.cost_dense, nx, k, dxl);
+        SPK_FIN(M.W11 + e, S[M.v11 + e], ld11, spk_soc_apply(mode, tp, nrl, S[M.W11 + e]), D.vo[7] + lfirst * nx + e);
+        SPK_FIN(M.W14 + e, S[M.v14 + e], dxl[k], spk_clip(S[M.W14 + e], D.x_min, D.x_max), D.vo[10] + lfirst * nx + e);
+      }
+    }
+    for (int e = tid; e < fd * nu; e += T) {  // v4
+      const int fc = e / nu, k = e - fc * nu, ff = fc / d;
+      int mode;
+      double tp;
+      const double nrm = S[M.nrm + fc];
+      spk_soc_coeffs(S[M.W6 + fc], nrm, mode, tp);
+      const double ld = spk_cost_row(spk_sqrtR(D, P, cfirst + fc), D.cost_dense, nu, k, S + M.du + ff * nu);
+      SPK_FIN(M.W4 + e, S[M.v4 + e], ld, spk_soc_apply(mode, tp, nrm, S[M.W4 + e]), D.vo[3] + (cfirst - 1) * nu + e);
+    }
+    SPK_SYNCTHREADS();  // every reader of W6 / W13 (the t components) is done before they are overwritten
+    for (int fc = tid; fc < fd; fc += T) {  // v5, v6; v12, v13 of leaf children
+      int mode;
+      double tp;
+      const double nrm = S[M.nrm + fc], tt = S[M.W6 + fc];
+      spk_soc_coeffs(tt, nrm, mode, tp);
+      const double ld = 0.5 * S[M.dtau + fc];
+      SPK_FIN(M.W5 + fc, S[M.v5 + fc], ld, spk_soc_apply(mode, tp, nrm, S[M.W5 + fc]), D.vo[4] + cfirst - 1 + fc);
+      SPK_FIN(M.W6 + fc, S[M.v6 + fc], ld, (mode == 0 ? tt : (mode == 1 ? 0.0 : tp)), D.vo[5] + cfirst - 1 + fc);
+      if (leaves) {
+        const double nrl = S[M.nrm + fd + fc], tl = S[M.W13 + fc];
+        spk_soc_coeffs(tl, nrl, mode, tp);
+        const double lds = 0.5 * S[M.dsc + fc];
+        SPK_FIN(M.W12 + fc, S[M.v12 + fc], lds, spk_soc_apply(mode, tp, nrl, S[M.W12 + fc]), D.vo[8] + lfirst + fc);
+        SPK_FIN(M.W13 + fc, S[M.v13 + fc], lds, (mode == 0 ? tl : (mode == 1 ? 0.0 : tp)), D.vo[9] + lfirst + fc);
+      }
+    }
+#undef SPK_FIN
+    SPK_SYNCTHREADS();
+    // ---- P5: xi1 = || L'dv - dz/gamma ||_inf and the z-part of <r, P r> (L_transpose! :320-449 on delta v)
+#define SPK_Z(dz_, lt_)                                        \
+  {                                                            \
+    const double dzv_ = (dz_), ltv_ = (lt_);                   \
+    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
+    my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
+  }
+    for (int e = tid; e < f * nx; e += T) {  // x_i :351-373
+      const int ff = e / nx, k = e - ff * nx;
+      double lt = S[M.W7 + ff * nxu + k];
+      for (int c = 0; c < d; ++c)
+        lt += spk_cost_row(spk_sqrtQ(D, P, cfirst + ff * d + c), D.cost_dense, nx, k, S + M.W3 + (ff * d + c) * nx);
+      SPK_Z(S[M.dx + e], lt);
+    }
+    for (int e = tid; e < f * nu; e += T) {  // u_i :399-420
+      const int ff = e / nu, k = e - ff * nu;
+      double lt = S[M.W7 + ff * nxu + nx + k];
+      for (int c = 0; c < d; ++c)
+        lt += spk_cost_row(spk_sqrtR(D, P, cfirst + ff * d + c), D.cost_dense, nu, k, S + M.W4 + (ff * d + c) * nu);
+      SPK_Z(S[M.du + e], lt);
+    }
+    for (int e = tid; e < f * ny; e += T) {  // y_i :423-429
+      const int ff = e / ny, k = e - ff * ny;
+      SPK_Z(S[M.dy + e], S[M.W1 + e] - P.b[k] * S[M.W2 + ff]);
+    }
+    for (int ff = tid; ff < f; ff += T) SPK_Z(S[M.ds + ff], S[M.W2 + ff]);  // s_i :440-442
+    for (int fc = tid; fc < fd; fc += T) {
+      SPK_Z(S[M.dtau + fc], 0.5 * S[M.W5 + fc] + 0.5 * S[M.W6 + fc]);                 // tau_c :432-437
+      if (leaves) SPK_Z(S[M.dsc + fc], 0.5 * S[M.W12 + fc] + 0.5 * S[M.W13 + fc]);    // s_leaf :445-448
+    }
+    if (leaves)
+      for (int e = tid; e < fd * nx; e += T) {  // x_leaf :376-396
+        const int fc = e / nx, k = e - fc * nx;
+        const double lt = S[M.W14 + e] + spk_cost_row(spk_sqrtQN(D, P, lfirst + fc), D.cost_dense, nx, k, S + M.W11 + fc * nx);
+        SPK_Z(S[M.dxc + e], lt);
+      }
+#undef SPK_Z
+    SPK_SYNCTHREADS();  // the staging buffers are reused by the next batch
+  }
+  // ---- CTA-level folds: maxima by atomicMax; <r, P r> as one deterministic partial per CTA
+  const double m1 = spk_warp_max(my_xi1), m2 = spk_warp_max(my_xi2), ps = spk_warp_sum(my_pn);
+  if (lane == 0) {
+    S[M.red + warp] = m1;
+    S[M.red + 32 + warp] = m2;
+    S[M.red + 64 + warp] = ps;
+  }
+  SPK_SYNCTHREADS();
+  if (tid == 0) {
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int w2 = 0; w2 < nwarps; ++w2) {
+      a1 = fmax(a1, S[M.red + w2]);
+      a2 = fmax(a2, S[M.red + 32 + w2]);
+      a3 += S[M.red + 64 + w2];
+    }
+    spk_atomic_max_nonneg(A.xi + 0, a1);
+    spk_atomic_max_nonneg(A.xi + 1, a2);
+    if (A.pnorm) A.pnorm[blockIdx.x] = a3;
   }
 }

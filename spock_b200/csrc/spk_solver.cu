@@ -138,6 +138,11 @@ struct spk_handle {
   bool fused_ok = false, shape_specialised = false;
   void (*k_bwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_fwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
+  void (*k_dual)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
+  void (*k_dual2)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long) = nullptr;
+  int dual2_F = 1;          // families per batch of the batched dual kernel
+  size_t dual2_smem = 0;
+  bool use_dual2 = true;
   int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1, num_sms = 148;
   size_t fused_smem_bwd = 0, fused_smem_fwd = 0, fused_smem_dual = 0;
   double *d_pnorm = nullptr;
@@ -425,11 +430,14 @@ static int comm_fail(const std::string &err) { return fail(SPK_ERR_COMM, err); }
 // Shape-specialised instantiations of the two factor-streaming kernels (nx, nu, d, threads); anything else runs
 // the runtime-size instantiation <0,0,0,0>.
 typedef void (*spk_fused_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs);
+typedef void (*spk_dual2_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long);
 struct ShapeEntry {
   int nx, nu, d, Tb, Tf;
-  spk_fused_kernel_t bwd, fwd;
+  spk_fused_kernel_t bwd, fwd, dual;
+  spk_dual2_kernel_t dual2;
 };
-#define SPK_SHAPE(NX, NU, DD, TB, TF) {NX, NU, DD, TB, TF, spk_k_bwd<NX, NU, DD, TB>, spk_k_fwd_s1<NX, NU, DD, TF>}
+#define SPK_SHAPE(NX, NU, DD, TB, TF) \
+  {NX, NU, DD, TB, TF, spk_k_bwd<NX, NU, DD, TB>, spk_k_fwd_s1<NX, NU, DD, TF>, spk_k_dual<NX, NU, DD>, spk_k_dual2<NX, NU, DD>}
 static const ShapeEntry g_shapes[] = {
     SPK_SHAPE(50, 20, 2, 256, 256), SPK_SHAPE(50, 50, 2, 256, 256), SPK_SHAPE(20, 20, 2, 128, 128),
     SPK_SHAPE(10, 10, 4, 64, 128),  SPK_SHAPE(10, 10, 2, 64, 64),   SPK_SHAPE(5, 5, 2, 32, 32),
@@ -448,11 +456,13 @@ static int fused_setup(spk_handle *h) {
   while (Tf < 2 * (D.nu + D.d * D.nx) && Tf < 256) Tf <<= 1;
   h->k_bwd = spk_k_bwd<0, 0, 0, 0>;
   h->k_fwd = spk_k_fwd_s1<0, 0, 0, 0>;
+  h->k_dual = spk_k_dual<0, 0, 0>;
+  h->k_dual2 = spk_k_dual2<0, 0, 0>;
   const char *gen = getenv("SPK_GENERIC_KERNELS");
   if (!SPK_EMU && !(gen && gen[0] == '1'))
     for (const ShapeEntry &e : g_shapes)
       if (e.nx == D.nx && e.nu == D.nu && e.d == D.d) {
-        Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd;
+        Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd; h->k_dual = e.dual; h->k_dual2 = e.dual2;
         h->shape_specialised = true;
       }
   if (SPK_EMU) Tb = Tf = 1;
@@ -461,13 +471,23 @@ static int fused_setup(spk_handle *h) {
   h->fused_smem_bwd = (size_t)spk_bwd_smem_doubles(D, Tb) * sizeof(double);
   h->fused_smem_fwd = (size_t)spk_fwd_smem_doubles(D, Tf) * sizeof(double);
 
+  {  // batched dual kernel: as many families per CTA as fit in ~44 KB of shared memory
+    int F = 16;
+    while (F > 1 && spk_dual_map(D.nx, D.nu, D.d, D.ny, F, true).total * 8 > 44 * 1024) F >>= 1;
+    h->dual2_F = F;
+    h->dual2_smem = (size_t)spk_dual_map(D.nx, D.nu, D.d, D.ny, F, true).total * sizeof(double);
+    const char *e1 = getenv("SPK_DUAL_V1");
+    h->use_dual2 = !(e1 && e1[0] == '1') && h->dual2_smem <= 200 * 1024;
+  }
   h->dual_warps = SPK_EMU ? 1 : 4;
   h->fused_smem_dual = (size_t)spk_dual_warp_doubles(D) * h->dual_warps * sizeof(double);
 #ifndef SPK_HOST_EMU
   if (std::max(h->fused_smem_bwd, h->fused_smem_fwd) > 227 * 1024 || h->fused_smem_dual > 200 * 1024) return SPK_OK;
   RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
   RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
-  RT_CHECK(cudaFuncSetAttribute(spk_k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_dual));
+  RT_CHECK(cudaFuncSetAttribute((const void *)h->k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_dual));
+  if (h->use_dual2)
+    RT_CHECK(cudaFuncSetAttribute((const void *)h->k_dual2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dual2_smem));
   cudaDeviceProp prop;
   RT_CHECK(cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
@@ -528,13 +548,38 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
     SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_FUSED_FWD);
   }
-  {  // 4. dual blocks and residuals, all owned families in one launch
+  long pn_parts = owned;  // number of <r,Pr> partials in d_pnorm
+  if (h->use_dual2) {  // 4b. batched dual kernel: one launch per owned range, split where the children become leaves
+    ProfScope ps(h, PC_PROX_H);
+    const long leaf_parents0 = spk_level_first0(D.d, D.N - 2);  // first family whose children are leaves
+    const int T = SPK_EMU ? 1 : 256;
+    long pn_off = 0;
+    for (int r = 0; r < A.n_ranges; ++r) {
+      const long lo = A.r_start[r], hi = lo + (A.r_prefix[r + 1] - A.r_prefix[r]);
+      for (int part = 0; part < 2; ++part) {
+        const long a = part == 0 ? lo : std::max(lo, leaf_parents0), b = part == 0 ? std::min(hi, leaf_parents0) : hi;
+        if (b <= a) continue;
+        SpkFusedArgs A2 = A;
+        A2.children_are_leaves = part;
+        A2.pnorm = A.pnorm ? A.pnorm + pn_off : nullptr;
+        const long nbatch = (b - a + h->dual2_F - 1) / h->dual2_F;
+        long g = std::min(nbatch, (long)h->num_sms * 8);
+        if (SPK_EMU) g = std::min(g, 3L);
+        spk_dual2_kernel_t kfn = h->k_dual2;
+        SPK_LAUNCH(kfn, (unsigned)g, T, h->dual2_smem, h->stream, D, h->P, A2, h->dual2_F, a, b - a);
+        COUNT_LAUNCH(h, PC_PROX_H);
+        pn_off += g;
+      }
+    }
+    pn_parts = pn_off;
+  } else {  // 4. dual blocks and residuals, all owned families in one launch (one warp per family)
     ProfScope ps(h, PC_PROX_H);
     const int T = SPK_EMU ? 1 : 32 * h->dual_warps;
     long g = (owned + h->dual_warps - 1) / h->dual_warps;
     g = std::min(g, (long)h->num_sms * 32);
     if (SPK_EMU) g = std::min(g, 4L);
-    SPK_LAUNCH(spk_k_dual, (unsigned)std::max(1L, g), T, h->fused_smem_dual, h->stream, D, h->P, A);
+    spk_fused_kernel_t kfn = h->k_dual;
+    SPK_LAUNCH(kfn, (unsigned)std::max(1L, g), T, h->fused_smem_dual, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_PROX_H);
   }
   if (h->world > 1) {  // v2 of the subtree roots is read by the replicated family above the cut in the next evaluation
@@ -543,7 +588,7 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
       return comm_fail(cerr);
   }
   SPK_TRY(rt_launch_check());
-  if (pnorm_slot >= 0) SPK_TRY(op_reduce(h, D.nnl, 2, h->d_pnorm, nullptr, pnorm_slot, 0));
+  if (pnorm_slot >= 0) SPK_TRY(op_reduce(h, pn_parts, 2, h->d_pnorm, nullptr, pnorm_slot, 0));
   return SPK_OK;
 }
 
