@@ -92,9 +92,13 @@ SPK_D void spk_cp_async_wait_all() {
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
+SPK_D void spk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SPK_D void spk_cp_async_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }  // all but the newest group
 #else
 SPK_D void spk_cp_async8(double *dst, const double *src) { *dst = *src; }
 SPK_D void spk_cp_async_wait_all() {}
+SPK_D void spk_cp_async_commit() {}
+SPK_D void spk_cp_async_wait_prev() {}
 #endif
 
 // max of non-negative doubles: the IEEE bit pattern is monotone, so an integer atomicMax is exact and order-free
@@ -208,8 +212,9 @@ SPK_D int spk_child_mode_dev(int d, int c) {  // mode of child ordinal c: (j0 + 
 
 SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
   const long SA = spk_slices(T, D.nx), SB = spk_slices(T, D.nu), nw = (T + 31) / 32;
+  const long raw = 2L * D.nu + 2L * D.nx + (long)D.d * D.nu + 4L * D.d * D.nx;  // zu, zx, v7, v4c, v3c, qraw, v14c, v11c
   return 2 + (long)D.d * D.abk_stride + 2 * D.k_stride + D.r_stride + (long)D.d * D.nx + D.nu + D.nx + SA * D.nx + SB * D.nu +
-         nw * 3L * D.nu + 4;
+         nw * 3L * D.nu + raw + 4;
 }
 
 // NX_, NU_, D_, T_ > 0: sizes fixed at compile time (every loop unrolls, index arithmetic folds); 0: runtime sizes
@@ -227,6 +232,9 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   double *mABKt = smem + 2, *mG = mABKt + (long)d * D.abk_stride, *mKt = mG + D.k_stride, *mRinv = mKt + D.k_stride;
   double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *partA = tx + nx, *partB = partA + (long)SA * nx,
          *wrhs = partB + (long)SB * nu + (long)warp * 3 * nu, *wdv = wrhs + nu, *wdmt = wdv + nu;
+  // raw staging of the next family's vector entries (asynchronous copies)
+  double *rzu = partB + (long)SB * nu + (long)((T + WL - 1) / WL) * 3 * nu, *rzx = rzu + nu, *rv7 = rzx + nx, *rv4 = rv7 + nx + nu,
+         *rv3 = rv4 + (long)d * nu, *rq = rv3 + (long)d * nx, *rv14 = rq + (long)d * nx, *rv11 = rv14 + (long)d * nx;
   const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double)),
                  bytes_r = (uint32_t)(D.r_stride * sizeof(double));
   const bool leaves = A.children_are_leaves != 0;
@@ -249,36 +257,57 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
     spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
   };
-  if ((long)blockIdx.x < count && tid == 0) fetch(first0 + blockIdx.x);
+  // asynchronous copies of one family's vector entries into the raw staging buffer
+  auto stage_raw = [&](long i0) {
+    const long cf = (long)d * i0 + 1;
+    for (int k = tid; k < nu; k += T) spk_cp_async8(rzu + k, A.z + D.zo[1] + i0 * nu + k);
+    for (int k = tid; k < nx; k += T) spk_cp_async8(rzx + k, A.z + i0 * nx + k);
+    for (int k = tid; k < nx + nu; k += T) spk_cp_async8(rv7 + k, A.v + D.vo[6] + i0 * (nx + nu) + k);
+    for (int k = tid; k < d * nu; k += T) spk_cp_async8(rv4 + k, A.v + D.vo[3] + (cf - 1) * nu + k);
+    for (int k = tid; k < d * nx; k += T) {
+      spk_cp_async8(rv3 + k, A.v + D.vo[2] + (cf - 1) * nx + k);
+      if (leaves) {
+        const long lf = cf - D.nnl;
+        spk_cp_async8(rq + k, A.z + cf * nx + k);
+        spk_cp_async8(rv14 + k, A.v + D.vo[10] + lf * nx + k);
+        spk_cp_async8(rv11 + k, A.v + D.vo[7] + lf * nx + k);
+      } else {
+        spk_cp_async8(rq + k, A.q + cf * nx + k);
+      }
+    }
+  };
+  if ((long)blockIdx.x < count) {
+    if (tid == 0) fetch(first0 + blockIdx.x);
+    stage_raw(first0 + blockIdx.x);
+  }
   bool pending = true;  // a fetch is in flight / not yet consumed
   for (long p = blockIdx.x; p < count; p += gridDim.x) {
     const long i0 = first0 + p;
-    // ---- P0: gather (z - gamma L'v) for u_i, x_i and the children's q while the matrices are in flight
     const long cfirst = (long)d * i0 + 1;  // first child (0-based node), children are consecutive
-    for (int k = tid; k < nu; k += T) {    // L_transpose! :399-420
-      double val = A.v[D.vo[6] + i0 * (nx + nu) + nx + k];
-      for (int c = 0; c < d; ++c)
-        val += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, A.v + D.vo[3] + (cfirst + c - 1) * nu);
-      tu[k] = A.z[D.zo[1] + i0 * nu + k] - gamma * val;
+    spk_cp_async_wait_all();  // this thread's raw copies have landed
+    SPK_SYNCTHREADS();
+    // ---- P0: (z - gamma L'v) for u_i, x_i (L_transpose! :351-373, :399-420) and the children's q, from the raw staging
+    for (int k = tid; k < nu; k += T) {
+      double val = rv7[nx + k];
+      for (int c = 0; c < d; ++c) val += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, rv4 + c * nu);
+      tu[k] = rzu[k] - gamma * val;
     }
-    for (int k = tid; k < nx; k += T) {  // :351-373
-      double val = A.v[D.vo[6] + i0 * (nx + nu) + k];
-      for (int c = 0; c < d; ++c)
-        val += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, A.v + D.vo[2] + (cfirst + c - 1) * nx);
-      tx[k] = A.z[i0 * nx + k] - gamma * val;
+    for (int k = tid; k < nx; k += T) {
+      double val = rv7[k];
+      for (int c = 0; c < d; ++c) val += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, rv3 + c * nx);
+      tx[k] = rzx[k] - gamma * val;
     }
     for (int idx = tid; idx < d * nx; idx += T) {
       if (leaves) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
         const int c = (idx == tid) ? qc_c : idx / nx, k = (idx == tid) ? qc_k : idx - (idx / nx) * nx;
-        const long l = cfirst + c - D.nnl;
-        double val = A.v[D.vo[10] + l * nx + k];
-        val += spk_cost_row(spk_sqrtQN(D, P, l), D.cost_dense, nx, k, A.v + D.vo[7] + l * nx);
-        qc[idx] = -(A.z[(cfirst + c) * nx + k] - gamma * val);
+        const double val = rv14[idx] + spk_cost_row(spk_sqrtQN(D, P, cfirst + c - D.nnl), D.cost_dense, nx, k, rv11 + c * nx);
+        qc[idx] = -(rq[idx] - gamma * val);
       } else {
-        qc[idx] = A.q[cfirst * nx + idx];
+        qc[idx] = rq[idx];
       }
     }
     SPK_SYNCTHREADS();
+    if (p + gridDim.x < count) stage_raw(i0 + gridDim.x);  // the staging buffer is free: prefetch the next family's entries
     // ---- P1: partial sums of sum_c B_w' q_c (:590-596; B' is a small table that stays in L1) and of sum_c ABK_c' q_c
     for (int o = tid; o < nu * SB; o += T) {
       const SpkItem it = (o == tid) ? itB : spk_make_item(o, nu, SB, nx, nu);
@@ -339,7 +368,7 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
 
 SPK_HD long spk_fwd_smem_doubles(const SpkDims &D, int T) {
   const long R = D.nu + (long)D.d * D.nx, S = spk_slices(T, (int)R);
-  return 2 + (long)D.d * D.abk_stride + D.k_stride + D.nx + D.nu + R * S + 4;
+  return 2 + (long)D.d * D.abk_stride + D.k_stride + 2L * (D.nx + D.nu) + R * S + 4;
 }
 
 template <int NX_, int NU_, int D_, int T_>
@@ -352,7 +381,7 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   constexpr int PER_X = spk_cper(NX_, cS), PER_U = spk_cper(NU_, cS);
   const long count = A.p_cnt, first0 = spk_level_first0(d, t) + A.p_lo;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-  double *mABK = smem + 2, *mK = mABK + (long)d * D.abk_stride, *xb = mK + D.k_stride, *ds = xb + nx, *part = ds + nu;
+  double *mABK = smem + 2, *mK = mABK + (long)d * D.abk_stride, *raw0 = mK + D.k_stride, *part = raw0 + 2L * (nx + nu);
   const uint32_t bytes_abk = (uint32_t)(d * D.abk_stride * sizeof(double)), bytes_k = (uint32_t)(D.k_stride * sizeof(double));
   if (tid == 0) spk_mbar_init(bar, 1);
   // family-independent work item of this thread: row r of [K; ABK_0; ..; ABK_{d-1}] and an inner-dimension slice
@@ -366,18 +395,29 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     spk_bulk_g2s(mABK, P.ABK + aslot * D.abk_stride, bytes_abk, bar);
     spk_bulk_g2s(mK, P.K + kslot * D.k_stride, bytes_k, bar);
   };
-  if ((long)blockIdx.x < count && tid == 0) fetch(first0 + blockIdx.x);
+  // x_i (:667: x0 at the root) and d_i of a family, asynchronously into one of the two small staging buffers
+  auto stage_raw = [&](long i0, int buf) {
+    double *dst = raw0 + (long)buf * (nx + nu);
+    for (int k = tid; k < nx; k += T) spk_cp_async8(dst + k, (t == 0) ? P.x0 + k : A.zbar + i0 * nx + k);
+    for (int k = tid; k < nu; k += T) spk_cp_async8(dst + nx + k, A.dd + i0 * nu + k);
+  };
+  if ((long)blockIdx.x < count) {
+    if (tid == 0) fetch(first0 + blockIdx.x);
+    stage_raw(first0 + blockIdx.x, 0);
+  }
+  spk_cp_async_commit();
   bool pending = true;
-  for (long p = blockIdx.x; p < count; p += gridDim.x) {
+  int buf = 0;
+  for (long p = blockIdx.x; p < count; p += gridDim.x, buf ^= 1) {
     const long i0 = first0 + p;
     const long cfirst = (long)d * i0 + 1;
-    for (int k = tid; k < nx; k += T) {
-      const double xv = (t == 0) ? P.x0[k] : A.zbar[i0 * nx + k];  // :667
-      xb[k] = xv;
-      if (t == 0) A.zbar[k] = xv;
-    }
-    for (int k = tid; k < nu; k += T) ds[k] = A.dd[i0 * nu + k];
+    if (p + gridDim.x < count) stage_raw(i0 + gridDim.x, buf ^ 1);  // one family ahead
+    spk_cp_async_commit();
+    spk_cp_async_wait_prev();  // this family's entries have landed
     SPK_SYNCTHREADS();
+    const double *xb = raw0 + (long)buf * (nx + nu), *ds = xb + nx;
+    if (t == 0)
+      for (int k = tid; k < nx; k += T) A.zbar[k] = xb[k];
     if (pending && (D.per_node || p == (long)blockIdx.x)) {
       spk_mbar_wait(bar, phase);
       phase ^= 1;
