@@ -199,3 +199,34 @@ def test_subtree_partition_over_gpus():
          "--master-port", "29517", os.path.join(root, "tools", "multigpu_check.py")],
         capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0 and "MULTIGPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(50, 20, 2, 6), (50, 50, 2, 5), (20, 20, 2, 7), (10, 10, 4, 5), (10, 10, 2, 8),
+                                       (5, 5, 2, 9), (20, 20, 3, 5), (10, 10, 3, 6)])
+@pytest.mark.parametrize("factor_mode", [0, 1])
+def test_shape_specialised_kernels_match_oracle(cuda_lib, nx, nu, d, N, factor_mode, monkeypatch):
+    """Every compile-time-specialised instantiation of the S1 / dual kernels (spk_solver.cu g_shapes) against the
+    oracle after K passes, and against the runtime-size instantiation of the same kernels."""
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    K = 25
+    o = Oracle(flat, CP)
+    o.set_x0(0.1 * np.ones(nx))
+    o.step(K)
+    res = []
+    for generic in ("0", "1"):
+        monkeypatch.setenv("SPK_GENERIC_KERNELS", generic)
+        h = Handle(flat, CP, factor_mode=factor_mode, lib=cuda_lib)
+        h.set_x0(0.1 * np.ones(nx))
+        h.step(K)
+        res.append(h.get_iterate())
+        h.close()
+    (zs, vs), (zg, vg) = res
+    assert relerr(zs, o.z) < 1e-9 and relerr(vs, o.v) < 1e-9
+    assert relerr(zs, zg) < 1e-12 and relerr(vs, vg) < 1e-12
+
+
+def test_sp_uses_fused_operator_and_matches_oracle_medium(cuda_lib):
+    """SuperMann on a medium tree (N=9, nx=nu=10): 12 passes against the oracle (SP parity is defined for K <= 30)."""
+    flat = flatten_problem(*get_server_heat_specs(9, 10, 2))
+    check_k_steps(cuda_lib, flat, SP, 12, factor_mode=1)
+    check_k_steps(cuda_lib, flat, SP, 12, factor_mode=0)
