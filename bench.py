@@ -30,9 +30,14 @@ WORKLOADS = {
     "config3_half": ("random", 19, 2, 50, 20, "config 3 with N=19 (524287 nodes)"),
     "heat15": ("heat", 15, 2, 50, 50, "reference scaling.jl largest case: server_heat N=15 d=2 nx=nu=50, 32767 nodes"),
     "config5_slice": ("heat_l2", 11, 4, 10, 10, "config 5 weak-scaling slice: server_heat N=11 d=4 nx=nu=10, SOC risk, 1398101 nodes"),
+    "config5": ("heat_l2", 13, 4, 10, 10, "SURVEY 8(d) config 5: server_heat N=13 d=4 nx=nu=10, l2-ball (SOC) risk, 22369621 nodes"),
+    "config5_n12": ("heat_l2", 12, 4, 10, 10, "config 5 strong-scaling slice: N=12, 5592405 nodes"),
     "small": ("random", 12, 2, 50, 20, "development size: random N=12 d=2 nx=50 nu=20, 4095 nodes"),
 }
-CPU_SAMPLE_N = {"config3": 14, "config3_half": 14, "heat15": 12, "config5_slice": 7, "small": 10}
+CPU_SAMPLE_N = {"config3": 14, "config3_half": 14, "heat15": 12, "config5_slice": 8, "config5": 8, "config5_n12": 8, "small": 10}
+# DRAM traffic of the dominant kernel from `ncu --set full` (profiles/r01b_bwd_config3_ncu.txt): deepest-level launch
+# (262144 of the 524287 families) read 16.768 GB + wrote 0.151 GB; scaled to all level launches of one pass
+NCU_TRAFFIC = {("config3", "per_node"): (16.767805e9 + 0.150771712e9) * 524287 / 262144}
 
 
 def make_spec(name, N_override=None):
@@ -301,7 +306,10 @@ def main():
         roofline = {
             "bound": "hbm", "kernel": "spk_k_bwd (backward S1 sweep: all N-1 level launches of one pass)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": (NCU_TRAFFIC.get((args.workload, args.factor_mode)) / world) if NCU_TRAFFIC.get((args.workload, args.factor_mode)) else None,
+            "traffic_source": "ncu --set full, deepest-level launch scaled to one pass (profiles/r01b_bwd_config3_ncu.txt)"
+            if NCU_TRAFFIC.get((args.workload, args.factor_mode)) else None,
+            "peak_source": peak_src,
             "algorithmic_bytes_per_pass": b_bwd / world, "avg_launch_ms": bwd["ms"] / max(bwd["launches"], 1),
             "share_of_step": (bwd["ms"] / ms) if ms else None,
             "whole_pass": {"algorithmic_bytes": (b_vec + b_fac) / world, "achieved": (b_vec + b_fac) / world / 1e9 / (ms_per_step / 1e3),

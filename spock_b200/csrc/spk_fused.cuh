@@ -758,7 +758,7 @@ struct SpkDualMap {
   long wx, dx, wu, du, wy, dy, ws, ds, wsc, dsc, wtau, dtau, wxc, dxc;          // primal: w and delta
   long v1, v2, v7, v3, v4, v5, v6, v11, v12, v13, v14;                          // old dual values
   long W1, W2, W7, W3, W4, W5, W6, W11, W12, W13, W14;                          // W, later delta v
-  long nrm, red, total;
+  long nrm, nrm1, red, total;
 };
 SPK_HD SpkDualMap spk_dual_map(int nx, int nu, int d, int ny, int F, bool leaves) {
   SpkDualMap m;
@@ -772,7 +772,7 @@ SPK_HD SpkDualMap spk_dual_map(int nx, int nu, int d, int ny, int F, bool leaves
   m.v11 = take(leaves ? fdx : 0); m.v12 = take(leaves ? fd : 0); m.v13 = take(leaves ? fd : 0); m.v14 = take(leaves ? fdx : 0);
   m.W1 = take(fy); m.W2 = take(F); m.W7 = take(fx + fu); m.W3 = take(fdx); m.W4 = take(fdu); m.W5 = take(fd); m.W6 = take(fd);
   m.W11 = take(leaves ? fdx : 0); m.W12 = take(leaves ? fd : 0); m.W13 = take(leaves ? fd : 0); m.W14 = take(leaves ? fdx : 0);
-  m.nrm = take(2 * fd); m.red = take(3 * 32);
+  m.nrm = take(2 * fd); m.nrm1 = take(2L * F * SPK_MAX_CONES); m.red = take(3 * 32);
   m.total = o + 2;
   return m;
 }
@@ -894,6 +894,17 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
       part = spk_warp_sum(part);
       if (lane == 0) S[M.nrm + bb] = sqrt(part);
     }
+    for (int idx = tid; idx < f * D.n_cones; idx += T) {  // SecondOrderCone sub-cones of the risk cone: (t, ||x||) per family
+      const int ff = idx / D.n_cones, c = idx - ff * D.n_cones;
+      if (D.cone_type[c] == 4) {
+        int off = 0;
+        for (int c2 = 0; c2 < c; ++c2) off += D.cone_dim[c2];
+        double nn = 0.0;
+        for (int k = 1; k < D.cone_dim[c]; ++k) nn += S[M.W1 + ff * ny + off + k] * S[M.W1 + ff * ny + off + k];
+        S[M.nrm1 + 2 * idx] = S[M.W1 + ff * ny + off];
+        S[M.nrm1 + 2 * idx + 1] = sqrt(nn);
+      }
+    }
     SPK_SYNCTHREADS();
     // ---- P4: projections (:752-909), vbar = sigma (W - Proj W), delta v (into the W slots), xi2, v-part of <r, P r>
 #define SPK_FIN(Wslot, vold_, Ld_, pr_, gidx_)                          \
@@ -905,41 +916,27 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
     my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
     my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
   }
-    {  // v1: dual-cone projection per family (:833-845); SOC sub-cones are handled by one thread per family
-      bool has_soc = false;
-      for (int c = 0; c < D.n_cones; ++c) has_soc |= (D.cone_type[c] == 4);
-      if (!has_soc) {
-        for (int e = tid; e < f * ny; e += T) {
-          const int ff = e / ny, k = e - ff * ny;
-          int off = 0, type = 0;
-          for (int c = 0; c < D.n_cones; ++c) {
-            if (k < off + D.cone_dim[c]) { type = D.cone_type[c]; break; }
-            off += D.cone_dim[c];
-          }
-          const double w = S[M.W1 + e];
-          const double pr = type == 0 ? w : (type == 1 ? (w < 0.0 ? 0.0 : w) : (type == 2 ? (w > 0.0 ? 0.0 : w) : 0.0));
-          SPK_FIN(M.W1 + e, S[M.v1 + e], S[M.dy + e], pr, (i0 + ff) * ny + k);
-        }
-      } else {
-        for (int ff = tid; ff < f; ff += T) {
-          double pr[SPK_MAX_LS];
-          for (int k = 0; k < ny; ++k) pr[k] = S[M.W1 + ff * ny + k];
-          int off = 0;
-          for (int c = 0; c < D.n_cones; ++c) {
-            const int dim = D.cone_dim[c];
-            switch (D.cone_type[c]) {
-              case 0: break;
-              case 1: for (int k = 0; k < dim; ++k) if (pr[off + k] < 0.0) pr[off + k] = 0.0; break;
-              case 2: for (int k = 0; k < dim; ++k) if (pr[off + k] > 0.0) pr[off + k] = 0.0; break;
-              case 3: for (int k = 0; k < dim; ++k) pr[off + k] = 0.0; break;
-              case 4: spk_project_soc_serial(pr + off, dim); break;
-            }
-            off += dim;
-          }
-          for (int k = 0; k < ny; ++k)
-            SPK_FIN(M.W1 + ff * ny + k, S[M.v1 + ff * ny + k], S[M.dy + ff * ny + k], pr[k], (i0 + ff) * ny + k);
-        }
+    for (int e = tid; e < f * ny; e += T) {  // v1: projection on the dual risk cone (:833-845), one thread per entry
+      const int ff = e / ny, k = e - ff * ny;
+      int off = 0, type = 0, c = 0;
+      for (; c < D.n_cones; ++c) {
+        if (k < off + D.cone_dim[c]) { type = D.cone_type[c]; break; }
+        off += D.cone_dim[c];
       }
+      const double w = S[M.W1 + e];
+      double pr;
+      if (type == 0) pr = w;                          // Zeros -> dual Reals
+      else if (type == 1) pr = w < 0.0 ? 0.0 : w;      // Nonnegatives
+      else if (type == 2) pr = w > 0.0 ? 0.0 : w;      // Nonpositives
+      else if (type == 3) pr = 0.0;                   // Reals -> dual Zeros
+      else {                                          // SecondOrderCone (t, x), self-dual
+        int mode;
+        double tp;
+        const double tt = S[M.nrm1 + 2 * (ff * D.n_cones + c)], nn = S[M.nrm1 + 2 * (ff * D.n_cones + c) + 1];
+        spk_soc_coeffs(tt, nn, mode, tp);
+        pr = (k == off) ? (mode == 0 ? w : (mode == 1 ? 0.0 : tp)) : spk_soc_apply(mode, tp, nn, w);
+      }
+      SPK_FIN(M.W1 + e, S[M.v1 + e], S[M.dy + e], pr, (i0 + ff) * ny + k);
     }
     for (int ff = tid; ff < f; ff += T) {  // v2 (:849-851)
       double bdy = 0.0;
