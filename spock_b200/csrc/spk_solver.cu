@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/spock_b200.h"
@@ -146,6 +148,12 @@ struct spk_handle {
   int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1, num_sms = 148;
   size_t fused_smem_bwd = 0, fused_smem_fwd = 0, fused_smem_dual = 0;
   double *d_pnorm = nullptr;
+  // CUDA graphs of the fused operator evaluation, keyed by (input, output, gamma, sigma, pnorm slot)
+  bool use_graphs = false;
+#ifndef SPK_HOST_EMU
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
+  std::map<std::tuple<const void *, void *, double, double, int>, GraphEntry> graphs;
+#endif
   // reductions
   double *d_partial = nullptr, *d_scal = nullptr;
   double h_scal[32];
@@ -497,6 +505,10 @@ static int fused_setup(spk_handle *h) {
   h->occ_fwd = std::max(1, h->occ_fwd);
 #endif
   h->fused_ok = true;
+  {
+    const char *ng = getenv("SPK_NO_GRAPH");
+    h->use_graphs = !SPK_EMU && !(ng && ng[0] == '1');
+  }
   return SPK_OK;
 }
 
@@ -508,7 +520,7 @@ static unsigned fused_grid(const spk_handle *h, long count, int occ) {
   return (unsigned)std::max(1L, g);
 }
 
-static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
+static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
   const SpkDims &D = h->D;
   SpkFusedArgs A;
   A.gamma = gamma; A.sigma = sigma;
@@ -590,6 +602,42 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
   SPK_TRY(rt_launch_check());
   if (pnorm_slot >= 0) SPK_TRY(op_reduce(h, pn_parts, 2, h->d_pnorm, nullptr, pnorm_slot, 0));
   return SPK_OK;
+}
+
+// One operator evaluation.  On a single GPU the whole launch sequence (2(N-1)+3 kernels, more with the P-norm) is
+// captured once per (input buffer, output buffer, step sizes) into a CUDA graph and replayed: for small and medium
+// trees a pass is launch-bound and a graph node costs a fraction of a stream launch.
+static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
+#ifndef SPK_HOST_EMU
+  if (h->use_graphs && !h->prof_on && h->world == 1) {
+    const auto key = std::make_tuple((const void *)zv_in, (void *)zv_out, gamma, sigma, pnorm_slot);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      if (h->graphs.size() >= 48) {  // bounded cache
+        for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+        h->graphs.clear();
+      }
+      const int64_t l0 = h->launches;
+      RT_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (rc != SPK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+      spk_handle::GraphEntry ge;
+      ge.kernels = h->launches - l0;
+      h->launches = l0;
+      const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+      it = h->graphs.emplace(key, ge).first;
+    }
+    RT_CHECK(cudaGraphLaunch(it->second.exec, h->stream));
+    h->launches += it->second.kernels;
+    return SPK_OK;
+  }
+#endif
+  return op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot);
 }
 
 // spock_dot (implicit_l.jl:485-516): d_scal[slot] = <a, P b>, P(b) = (b_z - gamma L'b_v, b_v - sigma L b_z)
@@ -819,6 +867,7 @@ int spk_destroy(spk_handle *h) {
   h->comm.destroy();
   for (void *p : h->allocs) rt_free(p);
 #ifndef SPK_HOST_EMU
+  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (auto &s : h->prof_open) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);

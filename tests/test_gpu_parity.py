@@ -230,3 +230,18 @@ def test_sp_uses_fused_operator_and_matches_oracle_medium(cuda_lib):
     flat = flatten_problem(*get_server_heat_specs(9, 10, 2))
     check_k_steps(cuda_lib, flat, SP, 12, factor_mode=1)
     check_k_steps(cuda_lib, flat, SP, 12, factor_mode=0)
+
+
+def test_cuda_graph_replay_equals_stream_launches(cuda_lib, monkeypatch):
+    """The cached CUDA graphs of the operator evaluation give bitwise the same iterate as plain stream launches (CP and SP)."""
+    flat = flat_of("heat_N7_d2_nx5")
+    for alg, K in ((CP, 60), (SP, 15)):
+        out = []
+        for ng in ("0", "1"):
+            monkeypatch.setenv("SPK_NO_GRAPH", ng)
+            h = Handle(flat, alg, factor_mode=1, lib=cuda_lib)
+            h.set_x0(0.1 * np.ones(5))
+            h.step(K)
+            out.append(h.get_iterate() + (h.residuals(),))
+            h.close()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
