@@ -24,7 +24,26 @@ def relerr(a, b):
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
 
 
+def _per_node_cost_specs():
+    """N=4, d=2, nx=3, nu=2 with a DIFFERENT dense SPD cost matrix at every node (the reference's Vector{Matrix} cost,
+    cost.jl:3-7 / implicit_l.jl:230,243,290) and the total-variation risk measure (risk_measures.jl:138-147, F != 0)."""
+    from spock_b200.problem import Cost, get_uniform_rms_tv_v2
+
+    scen_tree, _, dynamics, _, constraints = get_random_system_specs(4, 2, 3, 2)
+    rng = np.random.default_rng(7)
+
+    def spd(k):
+        M = rng.standard_normal((k, k))
+        return M @ M.T / k + 0.1 * np.eye(k)
+
+    cost = Cost([spd(3) for _ in range(scen_tree.n - 1)], [spd(2) for _ in range(scen_tree.n - 1)],
+                [spd(3) for _ in range(scen_tree.n_leaf_nodes)])
+    rms = get_uniform_rms_tv_v2([0.4, 0.6], 0.2, 2, 4)
+    return scen_tree, cost, dynamics, rms, constraints
+
+
 SMALL_PROBLEMS = {
+    "pernode_cost_tv_N4_d2_nx3": _per_node_cost_specs,
     "fixture_N3_d2": lambda: get_test_fixture_specs(),
     "heat_N7_d2_nx5": lambda: get_server_heat_specs(7, 5, 2),
     "heat_N4_d3_nx3": lambda: get_server_heat_specs(4, 3, 3),

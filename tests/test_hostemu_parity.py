@@ -34,7 +34,8 @@ def test_offline_factors(emu_lib, name):
 
 @pytest.mark.parametrize("name,alg,K", [
     ("fixture_N3_d2", CP, 200), ("heat_N7_d2_nx5", CP, 300), ("heat_N4_d3_nx3", CP, 200),
-    ("l2ball_N4_d3_nx3", CP, 200), ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
+    ("l2ball_N4_d3_nx3", CP, 200), ("pernode_cost_tv_N4_d2_nx3", CP, 150), ("pernode_cost_tv_N4_d2_nx3", SP, 15),
+    ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
 ])
 def test_k_step_iterates(emu_lib, name, alg, K):
     check_k_steps(emu_lib, flat_of(name), alg, K, factor_mode=K % 2)
