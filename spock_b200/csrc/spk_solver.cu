@@ -609,7 +609,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
 // trees a pass is launch-bound and a graph node costs a fraction of a stream launch.
 static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
 #ifndef SPK_HOST_EMU
-  if (h->use_graphs && !h->prof_on && h->world == 1) {
+  if (h->use_graphs && !h->prof_on && h->world == 1) {  // NCCL collectives inside a capture hung on this stack: 1 GPU only
     const auto key = std::make_tuple((const void *)zv_in, (void *)zv_out, gamma, sigma, pnorm_slot);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
