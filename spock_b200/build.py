@@ -1,25 +1,31 @@
 """Builds libspock_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
 
-    python -m spock_b200.build [--force]
+    python -m spock_b200.build [--force] [-v]
+
+The solver (spk_solver.cu), the offline phase (spk_offline.cpp) and one translation unit per shape-specialised kernel
+set (spk_shape.cu x the lines of spk_shapes.def) are compiled in parallel into csrc/_obj/ and linked.
 """
 from __future__ import annotations
 
+import concurrent.futures
+import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libspock_b200.so")
-SOURCES = ["spk_solver.cu", "spk_offline.cpp"]
-HEADERS = ["spk_kernels.cuh", "spk_types.h", "spk_runtime.h", "spk_offline.h", "spk_fused.cuh",
-           os.path.join("..", "..", "include", "spock_b200.h")]
+HEADERS = ["spk_kernels.cuh", "spk_types.h", "spk_runtime.h", "spk_offline.h", "spk_fused.cuh", "spk_shapes.h",
+           "spk_shapes.def", "spk_comm.h", os.path.join("..", "..", "include", "spock_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "--cudart", "static",
 ]
 
@@ -31,26 +37,75 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libspock_b200.so cannot be built (there is no CPU fallback)")
 
 
+def shapes():
+    """(nx, nu, d, threads_bwd, threads_fwd) per line of csrc/spk_shapes.def"""
+    txt = open(os.path.join(CSRC, "spk_shapes.def")).read()
+    return [tuple(int(x) for x in m) for m in
+            re.findall(r"^SPK_SHAPE_X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt, flags=re.M)]
+
+
+def _units():
+    """(object name, source, extra flags)"""
+    units = [("spk_solver.o", "spk_solver.cu", []), ("spk_offline.o", "spk_offline.cpp", [])]
+    for nx, nu, d, tb, tf in shapes():
+        units.append((f"spk_shape_{nx}_{nu}_{d}.o", "spk_shape.cu",
+                      [f"-DSPK_SHAPE_NX={nx}", f"-DSPK_SHAPE_NU={nu}", f"-DSPK_SHAPE_D={d}", f"-DSPK_SHAPE_TB={tb}",
+                       f"-DSPK_SHAPE_TF={tf}"]))
+    return units
+
+
+def _dep_stamp(src: str, extra) -> str:
+    h = hashlib.sha1()
+    for d in [src] + HEADERS:
+        p = os.path.join(CSRC, d)
+        if os.path.exists(p):
+            h.update(open(p, "rb").read())
+    h.update(" ".join(NVCC_FLAGS + list(extra)).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    for obj, src, extra in _units():
+        stamp = os.path.join(OBJ, obj + ".stamp")
+        if not os.path.exists(stamp) or open(stamp).read() != _dep_stamp(src, extra):
+            return True
+    return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a CC wrapper that nvcc must not pick up
+    logs = []
+
+    def compile_one(unit):
+        obj, src, extra = unit
+        out, stamp_p = os.path.join(OBJ, obj), os.path.join(OBJ, obj + ".stamp")
+        stamp = _dep_stamp(src, extra)
+        if not force and os.path.exists(out) and os.path.exists(stamp_p) and open(stamp_p).read() == stamp:
+            return
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + list(extra) + \
+            ["-c", os.path.join(CSRC, src), "-o", out]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        logs.append(res.stderr)
+        open(stamp_p, "w").write(stamp)
+
+    units = _units()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(units), os.cpu_count() or 1))) as ex:
+        list(ex.map(compile_one, units))
+    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(OBJ, u[0]) for u in units]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB
 
 

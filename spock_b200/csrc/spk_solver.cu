@@ -142,6 +142,8 @@ struct spk_handle {
   void (*k_fwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_dual)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_dual2)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long) = nullptr;
+  void (*k_dual3[2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {nullptr, nullptr};  // [children are leaves]
+  int occ_dual3 = 4;
   int dual2_F = 1;          // families per batch of the batched dual kernel
   size_t dual2_smem = 0;
   bool use_dual2 = true;
@@ -437,20 +439,21 @@ static int comm_fail(const std::string &err) { return fail(SPK_ERR_COMM, err); }
 
 // Shape-specialised instantiations of the two factor-streaming kernels (nx, nu, d, threads); anything else runs
 // the runtime-size instantiation <0,0,0,0>.
+#ifndef SPK_HOST_EMU
+#include "spk_shapes.h"
+#define SPK_SHAPE_X(NX, NU, DD, TB, TF) extern "C" const SpkShapeEntry *spk_shape_entry_##NX##_##NU##_##DD();
+#include "spk_shapes.def"
+#undef SPK_SHAPE_X
+typedef const SpkShapeEntry *(*spk_shape_getter_t)();
+#define SPK_SHAPE_X(NX, NU, DD, TB, TF) spk_shape_entry_##NX##_##NU##_##DD,
+static const spk_shape_getter_t g_shapes[] = {
+#include "spk_shapes.def"
+};
+#undef SPK_SHAPE_X
+#else
 typedef void (*spk_fused_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs);
 typedef void (*spk_dual2_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long);
-struct ShapeEntry {
-  int nx, nu, d, Tb, Tf;
-  spk_fused_kernel_t bwd, fwd, dual;
-  spk_dual2_kernel_t dual2;
-};
-#define SPK_SHAPE(NX, NU, DD, TB, TF) \
-  {NX, NU, DD, TB, TF, spk_k_bwd<NX, NU, DD, TB>, spk_k_fwd_s1<NX, NU, DD, TF>, spk_k_dual<NX, NU, DD>, spk_k_dual2<NX, NU, DD>}
-static const ShapeEntry g_shapes[] = {
-    SPK_SHAPE(50, 20, 2, 256, 256), SPK_SHAPE(50, 50, 2, 256, 256), SPK_SHAPE(20, 20, 2, 128, 128),
-    SPK_SHAPE(10, 10, 4, 64, 128),  SPK_SHAPE(10, 10, 2, 64, 64),   SPK_SHAPE(5, 5, 2, 32, 32),
-    SPK_SHAPE(20, 20, 3, 128, 256), SPK_SHAPE(10, 10, 3, 64, 128),
-};
+#endif
 
 static int fused_setup(spk_handle *h) {
   const SpkDims &D = h->D;
@@ -467,12 +470,25 @@ static int fused_setup(spk_handle *h) {
   h->k_dual = spk_k_dual<0, 0, 0>;
   h->k_dual2 = spk_k_dual2<0, 0, 0>;
   const char *gen = getenv("SPK_GENERIC_KERNELS");
-  if (!SPK_EMU && !(gen && gen[0] == '1'))
-    for (const ShapeEntry &e : g_shapes)
+#ifndef SPK_HOST_EMU
+  if (!(gen && gen[0] == '1'))
+    for (const spk_shape_getter_t getter : g_shapes) {
+      const SpkShapeEntry &e = *getter();
       if (e.nx == D.nx && e.nu == D.nu && e.d == D.d) {
         Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd; h->k_dual = e.dual; h->k_dual2 = e.dual2;
         h->shape_specialised = true;
+        // register-resident dual kernel: Diagonal sqrt-costs, risk cone and branching within one warp
+        const char *e3 = getenv("SPK_NO_DUAL3");
+        const bool uc = D.n_sqrtQ == 1 && D.n_sqrtQN == 1;
+        if (!D.cost_dense && D.ny <= 32 && D.d <= 32 && !(e3 && e3[0] == '1') && (uc || (D.n_sqrtQ > 1 && D.n_sqrtQN > 1))) {
+          h->k_dual3[0] = e.dual3[0][uc ? 1 : 0];
+          h->k_dual3[1] = e.dual3[1][uc ? 1 : 0];
+        }
       }
+    }
+#else
+  (void)gen;
+#endif
   if (SPK_EMU) Tb = Tf = 1;
   h->fused_threads_bwd = Tb;
   h->fused_threads_fwd = Tf;
@@ -502,6 +518,10 @@ static int fused_setup(spk_handle *h) {
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, (const void *)h->k_bwd, Tb, h->fused_smem_bwd));
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, (const void *)h->k_fwd, Tf, h->fused_smem_fwd));
   h->occ_bwd = std::max(1, h->occ_bwd);
+  if (h->k_dual3[1]) {
+    RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_dual3, (const void *)h->k_dual3[1], 128, 0));
+    h->occ_dual3 = std::max(1, h->occ_dual3);
+  }
   h->occ_fwd = std::max(1, h->occ_fwd);
 #endif
   h->fused_ok = true;
@@ -574,11 +594,21 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
         SpkFusedArgs A2 = A;
         A2.children_are_leaves = part;
         A2.pnorm = A.pnorm ? A.pnorm + pn_off : nullptr;
-        const long nbatch = (b - a + h->dual2_F - 1) / h->dual2_F;
-        long g = std::min(nbatch, (long)h->num_sms * 8);
-        if (SPK_EMU) g = std::min(g, 3L);
-        spk_dual2_kernel_t kfn = h->k_dual2;
-        SPK_LAUNCH(kfn, (unsigned)g, T, h->dual2_smem, h->stream, D, h->P, A2, h->dual2_F, a, b - a);
+        long g;
+#ifndef SPK_HOST_EMU
+        if (h->k_dual3[part]) {  // 4c. one warp per family, everything in registers
+          g = std::min((b - a + 3) / 4, (long)h->num_sms * h->occ_dual3);
+          spk_dual3_kernel_t k3 = h->k_dual3[part];
+          k3<<<(unsigned)g, 128, 0, h->stream>>>(D, h->P, A2, a, b - a);
+        } else
+#endif
+        {
+          const long nbatch = (b - a + h->dual2_F - 1) / h->dual2_F;
+          g = std::min(nbatch, (long)h->num_sms * 8);
+          if (SPK_EMU) g = std::min(g, 3L);
+          spk_dual2_kernel_t kfn = h->k_dual2;
+          SPK_LAUNCH(kfn, (unsigned)g, T, h->dual2_smem, h->stream, D, h->P, A2, h->dual2_F, a, b - a);
+        }
         COUNT_LAUNCH(h, PC_PROX_H);
         pn_off += g;
       }
