@@ -143,6 +143,21 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
               int32_t verbose_log, const double *z0, const double *v0, spk_result *result, double *log_xi,
               double *log_xi1, double *log_xi2, int32_t *log_backtrack, int32_t log_cap);
 
+/* Solver memory that persists ACROSS solves besides (z, v): checkpoint / resume and bit-exact warm starts (MPC).
+ * CP (model.jl:80-125): [z_old | v_old]                                                          -> nz+nv doubles.
+ * SP (model.jl:137-226, spock.jl:160-202): [z_old|v_old], [rz_old|rv_old], [delta_z|delta_v], the Anderson columns
+ * MP(:,1..3), MR(:,1..3), aa_Q(:,1..3) in the reference's column order, aa_R (3x3 column-major)     -> 12(nz+nv)+9 doubles.
+ * Together with spk_get_iterate / spk_set_iterate this is everything solve_model! reads from the previous solve. */
+int spk_state_size(const spk_handle *h, int64_t *doubles);
+int spk_get_state(spk_handle *h, double *state);
+int spk_set_state(spk_handle *h, const double *state);
+
+/* ||L||^2 by power iteration on L'L with the device L / L' kernels (iters <= 0: 50).  The reference hard-codes
+ * L_norm = 10 (cpock.jl:62-63) / 3.28 (spock.jl:63-64), which is only valid for its server_heat data;
+ * spk_set_L_norm replaces the value behind the default step sizes 0.99/sqrt(L_norm) (cp.jl:198-201). */
+int spk_estimate_L_norm(spk_handle *h, int32_t iters, double *L_norm);
+int spk_set_L_norm(spk_handle *h, double L_norm);
+
 /* Residuals of the last pass without a full D2H of the iterate: out[0] = xi1, out[1] = xi2 */
 int spk_get_residuals(spk_handle *h, double out[2]);
 

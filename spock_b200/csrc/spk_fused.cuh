@@ -1060,25 +1060,135 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
 
 // ------------------------------------------------------------------------------------------------ 4c. register-resident dual kernel
 //
-// Same arithmetic as spk_k_dual (one warp per family), organised as a pure streaming kernel for the specialised shapes
-// with Diagonal sqrt-costs (every reference workload): lane k owns COLUMN k of the family -- x_i[k], v7_i[k],
-// v3_c[k] and, for leaf children, x_c[k], v11_c[k], v14_c[k] (likewise the u-columns with v4_c) -- because L and L' with
-// diagonal costs only couple entries of the same column.  Every input of the family is loaded into registers up front
-// (~40 independent 8-byte loads per lane in flight), the only cross-lane work is the SOC norms (warp butterflies), and
-// there is no shared memory, no barrier and no integer division.  UC: the sqrt-cost diagonals are uniform over the
-// nodes (held in registers for the whole kernel) instead of per node.
+// Same arithmetic as spk_k_dual, organised as a pure streaming kernel for the specialised shapes with Diagonal
+// sqrt-costs (every reference workload).  A group of G lanes (G = 8, 16 or 32, the smallest power of two covering nx and
+// nu) owns one family and lane k of the group owns COLUMN k of the family -- x_i[k], v7_i[k], v3_c[k] and, for leaf
+// children, x_c[k], v11_c[k], v14_c[k] (likewise the u-columns with v4_c) -- because L and L' with diagonal costs only
+// couple entries of the same column.  Every input of the family is loaded into registers up front (~40 independent
+// 8-byte loads per lane in flight), the only cross-lane work is the SOC norms (butterflies inside the group), and there
+// is no shared-memory staging, no barrier in the main body and no integer division.  One family per group and no
+// grid-stride loop: address registers die as soon as the loads are issued, so more warps are resident.
+// UC: the sqrt-cost diagonals are uniform over the nodes instead of per node.
 #if !SPK_EMU
+SPK_CONSTEXPR_HD int spk_dual3_group(int nx, int nu, int d) {
+  int m = nx > nu ? nx : nu;
+  if (m > 32) return 32;
+  int g = 8;
+  while (g < m || g < d) g <<= 1;
+  return g;
+}
+// the residual maxima only ever grow: skip the atomic when the value cannot raise the maximum (a stale read only
+// causes a redundant atomic, never a missed one)
+SPK_D void spk_atomic_max_lazy(double *addr, double val) {
+  if (val > __ldcg(addr)) spk_atomic_max_nonneg(addr, val);
+}
+
 template <int NX, int NU, int DD, bool LEAVES, bool UC>
-__launch_bounds__(128, 3)
+__launch_bounds__(128, 4)
 __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, long fam_cnt) {
-  constexpr int RX = (NX + 31) / 32, RU = (NU + 31) / 32, CD = UC ? 1 : DD;
+  constexpr int G = spk_dual3_group(NX, NU, DD), FPW = 32 / G;  // lanes per family, families per warp
+  constexpr int RX = (NX + G - 1) / G, RU = (NU + G - 1) / G, CD = UC ? 1 : DD, LD = LEAVES ? DD : 1;
   __shared__ double s_red[3 * 4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int wlane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int lane = wlane & (G - 1);  // lane within the family's group
   const int ny = D.ny;
   const double gamma = A.gamma, sigma = A.sigma, inv_sigma = 1.0 / sigma, inv_gamma = 1.0 / gamma;
   const double *__restrict__ z = A.z, *__restrict__ zb = A.zbar, *__restrict__ v = A.v;
   double *__restrict__ vb = A.vbar;
   const double x_min = D.x_min, x_max = D.x_max, u_min = D.u_min, u_max = D.u_max;
+  // trailing groups of the last warp recompute the last family (identical stores; only their <r,Pr> share is dropped),
+  // so that every shuffle below is executed by full warps
+  long f = ((long)blockIdx.x * wpb + warp) * FPW + wlane / G;
+  const bool valid = f < fam_cnt;
+  if (!valid) f = fam_cnt - 1;
+  const long i0 = fam_lo + f, cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
+  double my_xi1 = 0.0, my_xi2 = 0.0, my_pn = 0.0;
+#define SPK_XON(r) ((NX % G == 0) || (r) < RX - 1 || lane + G * (r) < NX)
+#define SPK_UON(r) ((NU % G == 0) || (r) < RU - 1 || lane + G * (r) < NU)
+#define SPK_Z3(dz_, lt_)                                       \
+  {                                                            \
+    const double dzv_ = (dz_), ltv_ = (lt_);                   \
+    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
+    my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
+  }
+  // vbar = sigma (W - Proj W), delta v, xi2 and the v-part of <r, P r> of one dual entry
+#define SPK_FIN3(ptr_, w_, vold_, Ld_, pr_, dl_)                        \
+  {                                                                     \
+    const double vnew_ = sigma * ((w_) - (pr_));                        \
+    *(ptr_) = vnew_;                                                    \
+    dl_ = vnew_ - (vold_);                                              \
+    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
+    my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
+  }
+  // ---------------------------------------------------------------- loads (all independent)
+  double wx[RX], dx[RX], v7x[RX], v3[DD][RX], sQ[CD][RX], sQN[CD][RX];
+  double wu[RU], du[RU], v7u[RU], v4[DD][RU], sR[CD][RU];
+  double wxc[LD][RX], dxc[LD][RX], v11[LD][RX], v14[LD][RX];
+  {
+    const double *zx_p = z + i0 * NX, *bx_p = zb + i0 * NX, *v7_p = v + D.vo[6] + i0 * (NX + NU);
+    const double *v3_p = v + D.vo[2] + (cfirst - 1) * NX;
+#pragma unroll
+    for (int r = 0; r < RX; ++r) {
+      const int k = lane + G * r;
+      const bool on = SPK_XON(r);
+      wx[r] = on ? zx_p[k] : 0.0;
+      dx[r] = on ? bx_p[k] : 0.0;
+      v7x[r] = on ? v7_p[k] : 0.0;
+#pragma unroll
+      for (int c = 0; c < DD; ++c) v3[c][r] = on ? v3_p[c * NX + k] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CD; ++c) sQ[c][r] = on ? P.sqrtQ[(UC ? 0 : (cfirst - 1 + c) * NX) + k] : 0.0;
+      if (LEAVES) {
+        const double *zc_p = z + cfirst * NX, *bc_p = zb + cfirst * NX;
+        const double *v11_p = v + D.vo[7] + lfirst * NX, *v14_p = v + D.vo[10] + lfirst * NX;
+#pragma unroll
+        for (int c = 0; c < LD; ++c) {
+          wxc[c][r] = on ? zc_p[c * NX + k] : 0.0;
+          dxc[c][r] = on ? bc_p[c * NX + k] : 0.0;
+          v11[c][r] = on ? v11_p[c * NX + k] : 0.0;
+          v14[c][r] = on ? v14_p[c * NX + k] : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < CD; ++c) sQN[c][r] = on ? P.sqrtQN[(UC ? 0 : (lfirst + c) * NX) + k] : 0.0;
+      }
+    }
+    const double *zu_p = z + D.zo[1] + i0 * NU, *bu_p = zb + D.zo[1] + i0 * NU;
+    const double *v4_p = v + D.vo[3] + (cfirst - 1) * NU;
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      const int k = lane + G * r;
+      const bool on = SPK_UON(r);
+      wu[r] = on ? zu_p[k] : 0.0;
+      du[r] = on ? bu_p[k] : 0.0;
+      v7u[r] = on ? v7_p[NX + k] : 0.0;
+#pragma unroll
+      for (int c = 0; c < DD; ++c) v4[c][r] = on ? v4_p[c * NU + k] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CD; ++c) sR[c][r] = on ? P.sqrtR[(UC ? 0 : (cfirst - 1 + c) * NU) + k] : 0.0;
+    }
+  }
+  // y_i, v1_i on lanes < ny; the per-child scalars (tau_c, v5_c, v6_c; leaf: s_c, v12_c, v13_c) on lane c
+  double wy = 0.0, dy = 0.0, v1o = 0.0;
+  if (lane < ny) {
+    wy = z[D.zo[4] + i0 * ny + lane];
+    dy = zb[D.zo[4] + i0 * ny + lane];
+    v1o = v[i0 * ny + lane];
+  }
+  double wtau = 0.0, dtau = 0.0, v5o = 0.0, v6o = 0.0, wsl = 0.0, dsl = 0.0, v12o = 0.0, v13o = 0.0;
+  if (lane < DD) {
+    wtau = z[D.zo[3] + cfirst - 1 + lane];
+    dtau = zb[D.zo[3] + cfirst - 1 + lane];
+    v5o = v[D.vo[4] + cfirst - 1 + lane];
+    v6o = v[D.vo[5] + cfirst - 1 + lane];
+    if (LEAVES) {
+      wsl = z[D.zo[2] + cfirst + lane];
+      dsl = zb[D.zo[2] + cfirst + lane];
+      v12o = v[D.vo[8] + lfirst + lane];
+      v13o = v[D.vo[9] + lfirst + lane];
+    }
+  }
+  double ws_i = z[D.zo[2] + i0], ds_i = zb[D.zo[2] + i0];
+  const double v2o = v[D.vo[1] + i0];
   // lane -> risk sub-cone of its y entry (lanes >= ny are idle in the y phases)
   int y_type = 3, y_off = 0, y_cone = 0;
   bool has_soc = false;
@@ -1091,363 +1201,231 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     }
   }
   const double b_k = lane < ny ? P.b[lane] : 0.0;
-  double sQ[CD][RX], sR[CD][RU], sQN[CD][RX];
-  if (UC) {
+  // ---------------------------------------------------------------- w = 2 zbar - z, delta = zbar - z (in place)
+#define SPK_WD3(w_, d_) { const double old_ = (w_), nb_ = (d_); (w_) = 2.0 * nb_ - old_; (d_) = nb_ - old_; }
+#pragma unroll
+  for (int r = 0; r < RX; ++r) {
+    SPK_WD3(wx[r], dx[r]);
+    if (LEAVES) {
+#pragma unroll
+      for (int c = 0; c < LD; ++c) SPK_WD3(wxc[c][r], dxc[c][r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RU; ++r) SPK_WD3(wu[r], du[r]);
+  SPK_WD3(wy, dy);
+  SPK_WD3(wtau, dtau);
+  SPK_WD3(wsl, dsl);
+  SPK_WD3(ws_i, ds_i);
+#undef SPK_WD3
+  // ---------------------------------------------------------------- SOC norms: children (v3, v4, v5), leaf children (v11, v12)
+  // W = (v + sigma L(2zbar - z))/sigma with the +-1/2 shifts (prox_h_conj! :923-939, L! :226-260, :288-301)
+  const double w5 = v5o * inv_sigma + 0.5 * wtau - 0.5, tt = v6o * inv_sigma + 0.5 * wtau + 0.5;
+  const double w12 = v12o * inv_sigma + 0.5 * wsl - 0.5, tl = v13o * inv_sigma + 0.5 * wsl + 0.5;
+  double part[DD], partl[LD];
+#pragma unroll
+  for (int c = 0; c < DD; ++c) {
+    double acc = (lane == c) ? w5 * w5 : 0.0;
 #pragma unroll
     for (int r = 0; r < RX; ++r) {
-      const int k = lane + 32 * r;
-      sQ[0][r] = k < NX ? P.sqrtQ[k] : 0.0;
-      sQN[0][r] = (LEAVES && k < NX) ? P.sqrtQN[k] : 0.0;
+      const double w = v3[c][r] * inv_sigma + sQ[UC ? 0 : c][r] * wx[r];
+      acc += w * w;
     }
 #pragma unroll
     for (int r = 0; r < RU; ++r) {
-      const int k = lane + 32 * r;
-      sR[0][r] = k < NU ? P.sqrtR[k] : 0.0;
+      const double w = v4[c][r] * inv_sigma + sR[UC ? 0 : c][r] * wu[r];
+      acc += w * w;
     }
-  }
-  double my_xi1 = 0.0, my_xi2 = 0.0, my_pn = 0.0;
-#define SPK_FIN3(w_, vold_, Ld_, pr_, gidx_, dl_)                       \
-  {                                                                     \
-    const double vnew_ = sigma * ((w_) - (pr_));                        \
-    vb[gidx_] = vnew_;                                                  \
-    dl_ = vnew_ - (vold_);                                              \
-    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
-    my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
-  }
-#define SPK_Z3(dz_, lt_)                                       \
-  {                                                            \
-    const double dzv_ = (dz_), ltv_ = (lt_);                   \
-    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
-    my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
-  }
-  for (long f = (long)blockIdx.x * wpb + warp; f < fam_cnt; f += (long)gridDim.x * wpb) {
-    const long i0 = fam_lo + f, cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
-    // ---------------------------------------------------------------- loads (all independent)
-    double wx[RX], dx[RX], v7x[RX], v3[DD][RX];
-    double wu[RU], du[RU], v7u[RU], v4[DD][RU];
-    double wxc[LEAVES ? DD : 1][RX], dxc[LEAVES ? DD : 1][RX], v11[LEAVES ? DD : 1][RX], v14[LEAVES ? DD : 1][RX];
-    {
-      const double *zx_p = z + i0 * NX, *bx_p = zb + i0 * NX, *v7_p = v + D.vo[6] + i0 * (NX + NU);
-      const double *v3_p = v + D.vo[2] + (cfirst - 1) * NX;
+    part[c] = acc;
+    if (LEAVES) {
+      double al = (lane == c) ? w12 * w12 : 0.0;
 #pragma unroll
       for (int r = 0; r < RX; ++r) {
-        const int k = lane + 32 * r;
-        const bool on = (NX % 32 == 0) || r < RX - 1 || k < NX;
-        wx[r] = on ? zx_p[k] : 0.0;
-        dx[r] = on ? bx_p[k] : 0.0;
-        v7x[r] = on ? v7_p[k] : 0.0;
-#pragma unroll
-        for (int c = 0; c < DD; ++c) v3[c][r] = on ? v3_p[c * NX + k] : 0.0;
-        if (!UC) {
-#pragma unroll
-          for (int c = 0; c < CD; ++c) sQ[c][r] = on ? P.sqrtQ[(cfirst - 1 + c) * NX + k] : 0.0;
-        }
-        if (LEAVES) {
-          const double *zc_p = z + cfirst * NX, *bc_p = zb + cfirst * NX;
-          const double *v11_p = v + D.vo[7] + lfirst * NX, *v14_p = v + D.vo[10] + lfirst * NX;
-#pragma unroll
-          for (int c = 0; c < (LEAVES ? DD : 1); ++c) {
-            wxc[c][r] = on ? zc_p[c * NX + k] : 0.0;
-            dxc[c][r] = on ? bc_p[c * NX + k] : 0.0;
-            v11[c][r] = on ? v11_p[c * NX + k] : 0.0;
-            v14[c][r] = on ? v14_p[c * NX + k] : 0.0;
-          }
-          if (!UC) {
-#pragma unroll
-            for (int c = 0; c < CD; ++c) sQN[c][r] = on ? P.sqrtQN[(lfirst + c) * NX + k] : 0.0;
-          }
-        }
+        const double w = v11[c][r] * inv_sigma + sQN[UC ? 0 : c][r] * wxc[c][r];
+        al += w * w;
       }
-      const double *zu_p = z + D.zo[1] + i0 * NU, *bu_p = zb + D.zo[1] + i0 * NU;
-      const double *v4_p = v + D.vo[3] + (cfirst - 1) * NU;
-#pragma unroll
-      for (int r = 0; r < RU; ++r) {
-        const int k = lane + 32 * r;
-        const bool on = (NU % 32 == 0) || r < RU - 1 || k < NU;
-        wu[r] = on ? zu_p[k] : 0.0;
-        du[r] = on ? bu_p[k] : 0.0;
-        v7u[r] = on ? v7_p[NX + k] : 0.0;
-#pragma unroll
-        for (int c = 0; c < DD; ++c) v4[c][r] = on ? v4_p[c * NU + k] : 0.0;
-        if (!UC) {
-#pragma unroll
-          for (int c = 0; c < CD; ++c) sR[c][r] = on ? P.sqrtR[(cfirst - 1 + c) * NU + k] : 0.0;
-        }
-      }
+      partl[c] = al;
     }
-    // y_i, v1_i on lanes < ny; the per-child scalars (tau_c, v5_c, v6_c; leaf: s_c, v12_c, v13_c) on lane c
-    double wy = 0.0, dy = 0.0, v1o = 0.0;
-    if (lane < ny) {
-      wy = z[D.zo[4] + i0 * ny + lane];
-      dy = zb[D.zo[4] + i0 * ny + lane];
-      v1o = v[i0 * ny + lane];
-    }
-    double wtau = 0.0, dtau = 0.0, v5o = 0.0, v6o = 0.0, wsl = 0.0, dsl = 0.0, v12o = 0.0, v13o = 0.0;
-    if (lane < DD) {
-      wtau = z[D.zo[3] + cfirst - 1 + lane];
-      dtau = zb[D.zo[3] + cfirst - 1 + lane];
-      v5o = v[D.vo[4] + cfirst - 1 + lane];
-      v6o = v[D.vo[5] + cfirst - 1 + lane];
-      if (LEAVES) {
-        wsl = z[D.zo[2] + cfirst + lane];
-        dsl = zb[D.zo[2] + cfirst + lane];
-        v12o = v[D.vo[8] + lfirst + lane];
-        v13o = v[D.vo[9] + lfirst + lane];
-      }
-    }
-    double ws_i = z[D.zo[2] + i0], ds_i = zb[D.zo[2] + i0];
-    const double v2o = v[D.vo[1] + i0];
-    // ---------------------------------------------------------------- w = 2 zbar - z, delta = zbar - z (in place)
-#define SPK_WD3(w_, d_) { const double old_ = (w_), nb_ = (d_); (w_) = 2.0 * nb_ - old_; (d_) = nb_ - old_; }
+  }
 #pragma unroll
-    for (int r = 0; r < RX; ++r) {
-      SPK_WD3(wx[r], dx[r]);
-      if (LEAVES) {
-#pragma unroll
-        for (int c = 0; c < (LEAVES ? DD : 1); ++c) SPK_WD3(wxc[c][r], dxc[c][r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RU; ++r) SPK_WD3(wu[r], du[r]);
-    SPK_WD3(wy, dy);
-    SPK_WD3(wtau, dtau);
-    SPK_WD3(wsl, dsl);
-    SPK_WD3(ws_i, ds_i);
-#undef SPK_WD3
-    // ---------------------------------------------------------------- SOC norms: children (v3, v4, v5), leaf children (v11, v12)
-    // W = (v + sigma L(2zbar - z))/sigma with the +-1/2 shifts (prox_h_conj! :923-939, L! :226-260, :288-301)
-    const double w5 = v5o * inv_sigma + 0.5 * wtau - 0.5, tt = v6o * inv_sigma + 0.5 * wtau + 0.5;
-    const double w12 = v12o * inv_sigma + 0.5 * wsl - 0.5, tl = v13o * inv_sigma + 0.5 * wsl + 0.5;
-    double part[DD], partl[LEAVES ? DD : 1];
+  for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
     for (int c = 0; c < DD; ++c) {
-      double acc = (lane == c) ? w5 * w5 : 0.0;
+      part[c] += __shfl_xor_sync(0xffffffffu, part[c], o);
+      if (LEAVES) partl[c] += __shfl_xor_sync(0xffffffffu, partl[c], o);
+    }
+  }
+  // lane c turns (t_c, ||.||_c) into the SOC projection coefficients of child c (risk_measures.jl:57-70):
+  // Proj(t, x) = (pt, a x) with a = 1 | 0 | t'/||x||, pt = t | 0 | t'
+  double my_a = 1.0, my_pt = 0.0, my_al = 1.0, my_ptl = 0.0;
+  {
+    double my_n = 0.0, my_nl = 0.0;
 #pragma unroll
-      for (int r = 0; r < RX; ++r) {
-        const double w = v3[c][r] * inv_sigma + sQ[UC ? 0 : c][r] * wx[r];
-        acc += w * w;
+    for (int c = 0; c < DD; ++c) {
+      if (lane == c) {
+        my_n = part[c];
+        if (LEAVES) my_nl = partl[c];
       }
-#pragma unroll
-      for (int r = 0; r < RU; ++r) {
-        const double w = v4[c][r] * inv_sigma + sR[UC ? 0 : c][r] * wu[r];
-        acc += w * w;
-      }
-      part[c] = acc;
+    }
+    if (lane < DD) {
+      int mode;
+      double tp;
+      const double nrm = sqrt(my_n);
+      spk_soc_coeffs(tt, nrm, mode, tp);
+      my_a = mode == 0 ? 1.0 : (mode == 1 ? 0.0 : tp / nrm);
+      my_pt = mode == 0 ? tt : (mode == 1 ? 0.0 : tp);
       if (LEAVES) {
-        double al = (lane == c) ? w12 * w12 : 0.0;
-#pragma unroll
-        for (int r = 0; r < RX; ++r) {
-          const double w = v11[c][r] * inv_sigma + sQN[UC ? 0 : c][r] * wxc[c][r];
-          al += w * w;
-        }
-        partl[c] = al;
+        const double nrl = sqrt(my_nl);
+        spk_soc_coeffs(tl, nrl, mode, tp);
+        my_al = mode == 0 ? 1.0 : (mode == 1 ? 0.0 : tp / nrl);
+        my_ptl = mode == 0 ? tl : (mode == 1 ? 0.0 : tp);
       }
     }
+  }
+  // ---------------------------------------------------------------- own blocks v1_i (:833-845), v2_i (:849-851)
+  double dv1 = 0.0, dv2;
+  {
+    const double W1 = v1o * inv_sigma + wy;  // L! :207-210
+    double pr;
+    if (y_type == 0) pr = W1;                            // Zeros -> dual Reals
+    else if (y_type == 1) pr = W1 < 0.0 ? 0.0 : W1;       // Nonnegatives
+    else if (y_type == 2) pr = W1 > 0.0 ? 0.0 : W1;       // Nonpositives
+    else pr = 0.0;                                       // Reals -> dual Zeros (SecondOrderCone below)
+    if (has_soc) {
+      for (int c = 0; c < D.n_cones; ++c) {
+        if (D.cone_type[c] != 4) continue;
+        int off = 0;
+        for (int c2 = 0; c2 < c; ++c2) off += D.cone_dim[c2];
+        double sq = (lane > off && lane < off + D.cone_dim[c]) ? W1 * W1 : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int c = 0; c < DD; ++c) {
-        part[c] += __shfl_xor_sync(0xffffffffu, part[c], o);
-        if (LEAVES) partl[c] += __shfl_xor_sync(0xffffffffu, partl[c], o);
-      }
-    }
-    // lane c turns (t_c, ||.||_c) into the SOC projection coefficients of child c (risk_measures.jl:57-70):
-    // Proj(t, x) = (pt, a x) with a = 1 | 0 | t'/||x||, pt = t | 0 | t'
-    double my_a = 1.0, my_pt = 0.0, my_al = 1.0, my_ptl = 0.0;
-    {
-      double my_n = 0.0, my_nl = 0.0;
-#pragma unroll
-      for (int c = 0; c < DD; ++c) {
-        if (lane == c) {
-          my_n = part[c];
-          if (LEAVES) my_nl = partl[c];
-        }
-      }
-      if (lane < DD) {
+        for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const double snrm = sqrt(sq);
+        const double st = __shfl_sync(0xffffffffu, W1, off, G);
         int mode;
         double tp;
-        const double nrm = sqrt(my_n);
-        spk_soc_coeffs(tt, nrm, mode, tp);
-        my_a = mode == 0 ? 1.0 : (mode == 1 ? 0.0 : tp / nrm);
-        my_pt = mode == 0 ? tt : (mode == 1 ? 0.0 : tp);
-        if (LEAVES) {
-          const double nrl = sqrt(my_nl);
-          spk_soc_coeffs(tl, nrl, mode, tp);
-          my_al = mode == 0 ? 1.0 : (mode == 1 ? 0.0 : tp / nrl);
-          my_ptl = mode == 0 ? tl : (mode == 1 ? 0.0 : tp);
-        }
+        spk_soc_coeffs(st, snrm, mode, tp);
+        if (y_type == 4 && y_cone == c)
+          pr = (lane == y_off) ? (mode == 0 ? W1 : (mode == 1 ? 0.0 : tp)) : spk_soc_apply(mode, tp, snrm, W1);
       }
     }
-    // ---------------------------------------------------------------- own blocks v1_i (:833-845), v2_i (:849-851)
-    double dv1 = 0.0, dv2;
-    {
-      const double W1 = v1o * inv_sigma + wy;  // L! :207-210
-      double pr;
-      if (y_type == 0) pr = W1;                            // Zeros -> dual Reals
-      else if (y_type == 1) pr = W1 < 0.0 ? 0.0 : W1;       // Nonnegatives
-      else if (y_type == 2) pr = W1 > 0.0 ? 0.0 : W1;       // Nonpositives
-      else pr = 0.0;                                       // Reals -> dual Zeros (SecondOrderCone below)
-      if (has_soc) {
-        for (int c = 0; c < D.n_cones; ++c) {
-          if (D.cone_type[c] != 4) continue;
-          int off = 0;
-          for (int c2 = 0; c2 < c; ++c2) off += D.cone_dim[c2];
-          const double sq = (lane > off && lane < off + D.cone_dim[c]) ? W1 * W1 : 0.0;
-          const double snrm = sqrt(spk_warp_sum(sq));
-          const double st = __shfl_sync(0xffffffffu, W1, off);
-          int mode;
-          double tp;
-          spk_soc_coeffs(st, snrm, mode, tp);
-          if (y_type == 4 && y_cone == c)
-            pr = (lane == y_off) ? (mode == 0 ? W1 : (mode == 1 ? 0.0 : tp)) : spk_soc_apply(mode, tp, snrm, W1);
-        }
-      }
-      if (lane < ny) SPK_FIN3(W1, v1o, dy, pr, i0 * ny + lane, dv1);
-      const double bwy = spk_warp_sum(b_k * wy), bdy = spk_warp_sum(b_k * dy);
-      const double w2 = v2o * inv_sigma + (ws_i - bwy);  // L! :214-222
-      const double v2new = sigma * (w2 - (w2 >= 0 ? w2 : 0.0));
-      dv2 = v2new - v2o;
-      if (lane == 0) {
-        vb[D.vo[1] + i0] = v2new;
-        const double l2 = ds_i - bdy;
-        my_xi2 = fmax(my_xi2, fabs(l2 - dv2 * inv_sigma));
-        my_pn += dv2 * (dv2 - sigma * l2);
-      }
+    if (lane < ny) SPK_FIN3(vb + i0 * ny + lane, W1, v1o, dy, pr, dv1);
+    double bwy = b_k * wy, bdy = b_k * dy;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      bwy += __shfl_xor_sync(0xffffffffu, bwy, o);
+      bdy += __shfl_xor_sync(0xffffffffu, bdy, o);
     }
-    // ---------------------------------------------------------------- v7_i box (:903-908); starts the L'dv accumulators
-    double ltx[RX], ltu[RU];
-    {
-      double *vb7 = vb + D.vo[6] + i0 * (NX + NU);
-#pragma unroll
-      for (int r = 0; r < RX; ++r) {
-        const int k = lane + 32 * r;
-        ltx[r] = 0.0;
-        if ((NX % 32 == 0) || r < RX - 1 || k < NX) {
-          const double w = v7x[r] * inv_sigma + wx[r];  // L! :275-282
-          const double vnew_ = sigma * (w - spk_clip(w, x_min, x_max));
-          vb7[k] = vnew_;
-          const double dl = vnew_ - v7x[r];
-          my_xi2 = fmax(my_xi2, fabs(dx[r] - dl * inv_sigma));
-          my_pn += dl * (dl - sigma * dx[r]);
-          ltx[r] = dl;
-        }
-      }
-      vb7 += NX;
-#pragma unroll
-      for (int r = 0; r < RU; ++r) {
-        const int k = lane + 32 * r;
-        ltu[r] = 0.0;
-        if ((NU % 32 == 0) || r < RU - 1 || k < NU) {
-          const double w = v7u[r] * inv_sigma + wu[r];
-          const double vnew_ = sigma * (w - spk_clip(w, u_min, u_max));
-          vb7[k] = vnew_;
-          const double dl = vnew_ - v7u[r];
-          my_xi2 = fmax(my_xi2, fabs(du[r] - dl * inv_sigma));
-          my_pn += dl * (dl - sigma * du[r]);
-          ltu[r] = dl;
-        }
-      }
+    const double w2 = v2o * inv_sigma + (ws_i - bwy);  // L! :214-222
+    const double v2new = sigma * (w2 - (w2 >= 0 ? w2 : 0.0));
+    dv2 = v2new - v2o;
+    if (lane == 0) {
+      vb[D.vo[1] + i0] = v2new;
+      const double l2 = ds_i - bdy;
+      my_xi2 = fmax(my_xi2, fabs(l2 - dv2 * inv_sigma));
+      my_pn += dv2 * (dv2 - sigma * l2);
     }
-    // ---------------------------------------------------------------- children
-#pragma unroll
-    for (int c = 0; c < DD; ++c) {
-      const long jm = cfirst - 1 + c;
-      const double a = __shfl_sync(0xffffffffu, my_a, c);
-      double *vb3 = vb + D.vo[2] + jm * NX, *vb4 = vb + D.vo[3] + jm * NU;
-#pragma unroll
-      for (int r = 0; r < RX; ++r) {
-        const int k = lane + 32 * r;
-        if ((NX % 32 == 0) || r < RX - 1 || k < NX) {
-          const double q = sQ[UC ? 0 : c][r];
-          const double w = v3[c][r] * inv_sigma + q * wx[r];
-          const double vnew_ = sigma * (w - a * w);
-          vb3[k] = vnew_;
-          const double dl = vnew_ - v3[c][r], ld = q * dx[r];
-          my_xi2 = fmax(my_xi2, fabs(ld - dl * inv_sigma));
-          my_pn += dl * (dl - sigma * ld);
-          ltx[r] += q * dl;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < RU; ++r) {
-        const int k = lane + 32 * r;
-        if ((NU % 32 == 0) || r < RU - 1 || k < NU) {
-          const double q = sR[UC ? 0 : c][r];
-          const double w = v4[c][r] * inv_sigma + q * wu[r];
-          const double vnew_ = sigma * (w - a * w);
-          vb4[k] = vnew_;
-          const double dl = vnew_ - v4[c][r], ld = q * du[r];
-          my_xi2 = fmax(my_xi2, fabs(ld - dl * inv_sigma));
-          my_pn += dl * (dl - sigma * ld);
-          ltu[r] += q * dl;
-        }
-      }
-      if (LEAVES) {
-        const long l = lfirst + c;
-        const double al = __shfl_sync(0xffffffffu, my_al, c);
-        double *vb11 = vb + D.vo[7] + l * NX, *vb14 = vb + D.vo[10] + l * NX;
-#pragma unroll
-        for (int r = 0; r < RX; ++r) {
-          const int k = lane + 32 * r;
-          if ((NX % 32 == 0) || r < RX - 1 || k < NX) {
-            const double q = sQN[UC ? 0 : c][r];
-            const double w = v11[c][r] * inv_sigma + q * wxc[c][r];  // L! :288-294
-            const double vnew_ = sigma * (w - al * w);
-            vb11[k] = vnew_;
-            const double dl = vnew_ - v11[c][r], ld = q * dxc[c][r];
-            my_xi2 = fmax(my_xi2, fabs(ld - dl * inv_sigma));
-            my_pn += dl * (dl - sigma * ld);
-            const double wb = v14[c][r] * inv_sigma + wxc[c][r];  // v14 box :804-809, L! :311-317
-            const double vn14 = sigma * (wb - spk_clip(wb, x_min, x_max));
-            vb14[k] = vn14;
-            const double d14 = vn14 - v14[c][r];
-            my_xi2 = fmax(my_xi2, fabs(dxc[c][r] - d14 * inv_sigma));
-            my_pn += d14 * (d14 - sigma * dxc[c][r]);
-            SPK_Z3(dxc[c][r], d14 + q * dl);  // x_leaf :376-396
-          }
-        }
-      }
-    }
-    if (lane < DD) {  // v5, v6 (t) of child `lane`, tau entry of xi1 (L_transpose! :432-437); leaf: v12, v13, s_leaf (:445-448)
-      const long jm = cfirst - 1 + lane;
-      const double v5new = sigma * (w5 - my_a * w5), v6new = sigma * (tt - my_pt);
-      const double d5 = v5new - v5o, d6 = v6new - v6o, ld = 0.5 * dtau;
-      vb[D.vo[4] + jm] = v5new;
-      vb[D.vo[5] + jm] = v6new;
-      my_xi2 = fmax(my_xi2, fmax(fabs(ld - d5 * inv_sigma), fabs(ld - d6 * inv_sigma)));
-      my_pn += d5 * (d5 - sigma * ld) + d6 * (d6 - sigma * ld);
-      SPK_Z3(dtau, 0.5 * d5 + 0.5 * d6);
-      if (LEAVES) {
-        const long l = lfirst + lane;
-        const double v12new = sigma * (w12 - my_al * w12), v13new = sigma * (tl - my_ptl);
-        const double d12 = v12new - v12o, d13 = v13new - v13o, lds = 0.5 * dsl;
-        vb[D.vo[8] + l] = v12new;
-        vb[D.vo[9] + l] = v13new;
-        my_xi2 = fmax(my_xi2, fmax(fabs(lds - d12 * inv_sigma), fabs(lds - d13 * inv_sigma)));
-        my_pn += d12 * (d12 - sigma * lds) + d13 * (d13 - sigma * lds);
-        SPK_Z3(dsl, 0.5 * d12 + 0.5 * d13);
-      }
-    }
-    // ---------------------------------------------------------------- xi1 and the z-part of <r, P r> for x_i, u_i, y_i, s_i
-#pragma unroll
-    for (int r = 0; r < RX; ++r)
-      if ((NX % 32 == 0) || r < RX - 1 || lane + 32 * r < NX) SPK_Z3(dx[r], ltx[r]);  // :351-373
-#pragma unroll
-    for (int r = 0; r < RU; ++r)
-      if ((NU % 32 == 0) || r < RU - 1 || lane + 32 * r < NU) SPK_Z3(du[r], ltu[r]);  // :399-420
-    if (lane < ny) SPK_Z3(dy, dv1 - b_k * dv2);                                       // :423-429
-    if (lane == 0) SPK_Z3(ds_i, dv2);                                                 // :440-442
   }
+  // ---------------------------------------------------------------- v7_i box (:903-908); starts the L'dv accumulators
+  double ltx[RX], ltu[RU];
+  {
+    double *vb7 = vb + D.vo[6] + i0 * (NX + NU);
+#pragma unroll
+    for (int r = 0; r < RX; ++r) {
+      ltx[r] = 0.0;
+      if (SPK_XON(r)) {
+        const double w = v7x[r] * inv_sigma + wx[r];  // L! :275-282
+        SPK_FIN3(vb7 + lane + G * r, w, v7x[r], dx[r], spk_clip(w, x_min, x_max), ltx[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      ltu[r] = 0.0;
+      if (SPK_UON(r)) {
+        const double w = v7u[r] * inv_sigma + wu[r];
+        SPK_FIN3(vb7 + NX + lane + G * r, w, v7u[r], du[r], spk_clip(w, u_min, u_max), ltu[r]);
+      }
+    }
+  }
+  // ---------------------------------------------------------------- children: SOC(nx+nu+2) on (t = v6; v3, v4, v5) (:854-900)
+#pragma unroll
+  for (int c = 0; c < DD; ++c) {
+    const long jm = cfirst - 1 + c;
+    const double a = __shfl_sync(0xffffffffu, my_a, c, G);
+    double *vb3 = vb + D.vo[2] + jm * NX, *vb4 = vb + D.vo[3] + jm * NU;
+#pragma unroll
+    for (int r = 0; r < RX; ++r) {
+      if (SPK_XON(r)) {
+        const double q = sQ[UC ? 0 : c][r], w = v3[c][r] * inv_sigma + q * wx[r];
+        double dl;
+        SPK_FIN3(vb3 + lane + G * r, w, v3[c][r], q * dx[r], a * w, dl);
+        ltx[r] += q * dl;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      if (SPK_UON(r)) {
+        const double q = sR[UC ? 0 : c][r], w = v4[c][r] * inv_sigma + q * wu[r];
+        double dl;
+        SPK_FIN3(vb4 + lane + G * r, w, v4[c][r], q * du[r], a * w, dl);
+        ltu[r] += q * dl;
+      }
+    }
+    if (LEAVES) {  // leaf children: SOC(nx+2) on (v13; v11, v12) (:768-800), v14 box (:804-809)
+      const long l = lfirst + c;
+      const double al = __shfl_sync(0xffffffffu, my_al, c, G);
+      double *vb11 = vb + D.vo[7] + l * NX, *vb14 = vb + D.vo[10] + l * NX;
+#pragma unroll
+      for (int r = 0; r < RX; ++r) {
+        if (SPK_XON(r)) {
+          const double q = sQN[UC ? 0 : c][r], w = v11[c][r] * inv_sigma + q * wxc[c][r];  // L! :288-294
+          double dl, d14;
+          SPK_FIN3(vb11 + lane + G * r, w, v11[c][r], q * dxc[c][r], al * w, dl);
+          const double wb = v14[c][r] * inv_sigma + wxc[c][r];  // L! :311-317
+          SPK_FIN3(vb14 + lane + G * r, wb, v14[c][r], dxc[c][r], spk_clip(wb, x_min, x_max), d14);
+          SPK_Z3(dxc[c][r], d14 + q * dl);  // x_leaf :376-396
+        }
+      }
+    }
+  }
+  if (lane < DD) {  // v5, v6 (t) of child `lane`, tau entry of xi1 (L_transpose! :432-437); leaf: v12, v13, s_leaf (:445-448)
+    const long jm = cfirst - 1 + lane;
+    const double ld = 0.5 * dtau;
+    double d5, d6;
+    SPK_FIN3(vb + D.vo[4] + jm, w5, v5o, ld, my_a * w5, d5);
+    SPK_FIN3(vb + D.vo[5] + jm, tt, v6o, ld, my_pt, d6);
+    SPK_Z3(dtau, 0.5 * d5 + 0.5 * d6);
+    if (LEAVES) {
+      const long l = lfirst + lane;
+      const double lds = 0.5 * dsl;
+      double d12, d13;
+      SPK_FIN3(vb + D.vo[8] + l, w12, v12o, lds, my_al * w12, d12);
+      SPK_FIN3(vb + D.vo[9] + l, tl, v13o, lds, my_ptl, d13);
+      SPK_Z3(dsl, 0.5 * d12 + 0.5 * d13);
+    }
+  }
+  // ---------------------------------------------------------------- xi1 and the z-part of <r, P r> for x_i, u_i, y_i, s_i
+#pragma unroll
+  for (int r = 0; r < RX; ++r)
+    if (SPK_XON(r)) SPK_Z3(dx[r], ltx[r]);  // :351-373
+#pragma unroll
+  for (int r = 0; r < RU; ++r)
+    if (SPK_UON(r)) SPK_Z3(du[r], ltu[r]);  // :399-420
+  if (lane < ny) SPK_Z3(dy, dv1 - b_k * dv2);  // :423-429
+  if (lane == 0) SPK_Z3(ds_i, dv2);            // :440-442
 #undef SPK_FIN3
 #undef SPK_Z3
-  // ---- folds: maxima by atomicMax; <r, P r> as one deterministic partial per CTA
-  const double m1 = spk_warp_max(my_xi1), m2 = spk_warp_max(my_xi2), ps = spk_warp_sum(my_pn);
-  if (lane == 0) {
-    spk_atomic_max_nonneg(A.xi + 0, m1);
-    spk_atomic_max_nonneg(A.xi + 1, m2);
-    s_red[warp] = ps;
+#undef SPK_XON
+#undef SPK_UON
+  // ---- folds: maxima by (lazy) atomicMax; <r, P r> as one deterministic partial per CTA
+  if (!valid) my_pn = 0.0;
+  const double m1 = spk_warp_max(my_xi1), m2 = spk_warp_max(my_xi2);
+  if (wlane == 0) {
+    spk_atomic_max_lazy(A.xi + 0, m1);
+    spk_atomic_max_lazy(A.xi + 1, m2);
   }
   if (A.pnorm) {
+    const double ps = spk_warp_sum(my_pn);
+    if (wlane == 0) s_red[warp] = ps;
     __syncthreads();
     if (threadIdx.x == 0) {
       double a3 = 0.0;

@@ -1,0 +1,265 @@
+// spk_mm.cuh -- per-stage ("factor table") S1 sweeps on the fp64 tensor pipe (DMMA, mma.sync.m8n8k4.f64).
+//
+// With SPK_FACTORS_PER_STAGE all families of a level share their Riccati factors, so a level of the backward / forward
+// sweep of projection_S1! (implicit_l.jl:584-637, :667-681) is a chain of small mat-mats over the families of the level
+// (tools/microbench/dmma_bench.cu: DMMA reaches the same 37 TFLOP/s as DFMA on B200, but takes its weight operand from a
+// single conflict-free 8-byte shared-memory read per lane and needs no per-thread index arithmetic).  One warp owns a
+// tile of 8 consecutive families:
+//   * the vectors of the tile (children's q, x_i, d_i) are read from HBM DIRECTLY in A-fragment order (lane (m, kk)
+//     reads entry 4s+kk of family m: 32 contiguous bytes per family and k-step), the right-hand sides / outputs in
+//     C-fragment order (two consecutive entries per lane) -- there is no shared-memory staging of vectors;
+//   * the level's weights sit in shared memory in B-fragment order (spk_mm_layout.h), fetched once per CTA with TMA bulk
+//     copies from the (L2-resident) per-level table;
+//   * intermediate results (rhs -> d_i -> G d_i) are fed back from accumulator registers as the next A operand through
+//     the permuted inner ordering, without shuffles.
+// Arithmetic per family is that of spk_k_bwd / spk_k_fwd_s1 (same folded factors), summed in DMMA order.
+#pragma once
+#include "spk_fused.cuh"
+#include "spk_mm_layout.h"
+
+#if !SPK_EMU
+SPK_D void spk_dmma(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+SPK_CONSTEXPR_HD int spk_mm_minb(int frags) { return frags * 256 > 110 * 1024 ? 1 : 2; }
+SPK_CONSTEXPR_HD size_t spk_mm_smem_bytes(int frags) { return 16 + (size_t)frags * 256; }
+
+// thread 0: fetch `frags` fragments of the level's table into shared memory (completion on `bar`)
+SPK_D void spk_mm_fetch(double *smem, const double *frag_g, int frags, int tid) {
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  if (tid == 0) {
+    spk_mbar_init(bar, 1);
+    const uint32_t total = (uint32_t)frags * 256u;
+    spk_mbar_expect_tx(bar, total);
+    for (uint32_t off = 0; off < total; off += 32768u) {
+      const uint32_t sz = total - off < 32768u ? total - off : 32768u;
+      spk_bulk_g2s(reinterpret_cast<char *>(smem + 2) + off, reinterpret_cast<const char *>(frag_g) + off, sz, bar);
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ backward level
+template <int NX, int NU, int DD, bool LEAVES>
+__launch_bounds__(256, spk_mm_minb(spk_mm_layout(NX, NU, DD).bwd_frags))
+__global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_g) {
+  constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
+  constexpr int KX = L.KX, NBX = L.NBX, NBU = L.NBU, NBS = L.NBU + L.NBX;
+  SPK_SMEM_DECL(double, smem);
+  const double *fr = smem + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
+  const int m = lane >> 2, kk = lane & 3;
+  const long count = A.p_cnt, first0 = spk_level_first0(DD, A.t) + A.p_lo, ntiles = (count + 7) / 8;
+  if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
+    A.xi[0] = 0.0;
+    A.xi[1] = 0.0;
+  }
+  spk_mm_fetch(smem, frag_g, L.bwd_frags, tid);
+  bool waited = false;
+  const double gamma = A.gamma;
+  const double *__restrict__ z = A.z, *__restrict__ v = A.v;
+  const bool ucq = D.n_sqrtQ == 1, ucn = D.n_sqrtQN == 1;
+  for (long tile = (long)blockIdx.x * wpb + warp; tile < ntiles; tile += (long)gridDim.x * wpb) {
+    long fm = tile * 8 + m;
+    const bool valid = fm < count;
+    if (!valid) fm = count - 1;  // trailing rows of the last tile recompute the last family; their stores are dropped
+    const long i0 = first0 + fm, cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
+    // ---- tu = (z - gamma L'v) on u_i (L_transpose! :399-420) in C-fragment order: entries 8 nb + 2 kk + {0, 1}
+    double tu[NBU][2];
+#pragma unroll
+    for (int nb = 0; nb < NBU; ++nb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = 8 * nb + 2 * kk + i;
+        double val = 0.0;
+        if (n < NU) {
+          double lt = v[D.vo[6] + i0 * (NX + NU) + NX + n];
+#pragma unroll
+          for (int c = 0; c < DD; ++c)
+            lt += P.sqrtR[(ucq ? 0 : (cfirst - 1 + c) * NU) + n] * v[D.vo[3] + (cfirst - 1 + c) * NU + n];
+          val = z[D.zo[1] + i0 * NU + n] - gamma * lt;
+        }
+        tu[nb][i] = val;
+      }
+    // ---- sweep over the children's q (A fragments straight from HBM): acc1 = sum_c B_c' q_c (:590-596),
+    //      acc3 = sum_c ABK_c' q_c (:610-632)
+    double acc1[NBU][2], acc3[NBX][2];
+#pragma unroll
+    for (int nb = 0; nb < NBU; ++nb) acc1[nb][0] = acc1[nb][1] = 0.0;
+#pragma unroll
+    for (int nb = 0; nb < NBX; ++nb) acc3[nb][0] = acc3[nb][1] = 0.0;
+#pragma unroll
+    for (int c = 0; c < DD; ++c) {
+      double qa[KX];
+#pragma unroll
+      for (int s = 0; s < KX; ++s) {
+        const int k = 4 * s + kk;
+        double a = 0.0;
+        if (k < NX) {
+          if (LEAVES) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
+            const long l = lfirst + c;
+            a = -(z[(cfirst + c) * NX + k] -
+                  gamma * (v[D.vo[10] + l * NX + k] + P.sqrtQN[(ucn ? 0 : l * NX) + k] * v[D.vo[7] + l * NX + k]));
+          } else {
+            a = A.q[(cfirst + c) * NX + k];
+          }
+        }
+        qa[s] = a;
+      }
+      if (!waited) {
+        spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);
+        waited = true;
+      }
+#pragma unroll
+      for (int s = 0; s < KX; ++s) {
+        const double *base = fr + (size_t)((c * KX + s) * NBS) * 32 + lane;
+#pragma unroll
+        for (int nb = 0; nb < NBU; ++nb) spk_dmma(acc1[nb][0], acc1[nb][1], qa[s], base[nb * 32]);
+#pragma unroll
+        for (int nb = 0; nb < NBX; ++nb) spk_dmma(acc3[nb][0], acc3[nb][1], qa[s], base[(NBU + nb) * 32]);
+      }
+    }
+    // ---- d_i = Rtilde^{-1} (tu - sum_c B_c' q_c) (:598-601): the accumulators are the next A operand (permuted k)
+    double dv[NBU][2];
+#pragma unroll
+    for (int nb = 0; nb < NBU; ++nb) dv[nb][0] = dv[nb][1] = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < NBU; ++kb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double a = tu[kb][i] - acc1[kb][i];
+        const double *base = fr + (size_t)(L.bwd_s2 + (2 * kb + i) * NBU) * 32 + lane;
+#pragma unroll
+        for (int nb = 0; nb < NBU; ++nb) spk_dmma(dv[nb][0], dv[nb][1], a, base[nb * 32]);
+      }
+    if (valid) {
+#pragma unroll
+      for (int nb = 0; nb < NBU; ++nb)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (8 * nb + 2 * kk + i < NU) A.dd[i0 * NU + 8 * nb + 2 * kk + i] = dv[nb][i];
+    }
+    // ---- + G d + K'(d - ubar) (:610-632)
+#pragma unroll
+    for (int kb = 0; kb < NBU; ++kb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double a1 = dv[kb][i], a2 = dv[kb][i] - tu[kb][i];
+        const double *bg = fr + (size_t)(L.bwd_s3b + (2 * kb + i) * NBX) * 32 + lane;
+        const double *bk = fr + (size_t)(L.bwd_s3c + (2 * kb + i) * NBX) * 32 + lane;
+#pragma unroll
+        for (int nb = 0; nb < NBX; ++nb) {
+          spk_dmma(acc3[nb][0], acc3[nb][1], a1, bg[nb * 32]);
+          spk_dmma(acc3[nb][0], acc3[nb][1], a2, bk[nb * 32]);
+        }
+      }
+    // ---- q_i = ... - (z - gamma L'v) on x_i (:634-636 with L_transpose! :351-373)
+#pragma unroll
+    for (int nb = 0; nb < NBX; ++nb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = 8 * nb + 2 * kk + i;
+        if (n < NX) {
+          double lt = v[D.vo[6] + i0 * (NX + NU) + n];
+#pragma unroll
+          for (int c = 0; c < DD; ++c)
+            lt += P.sqrtQ[(ucq ? 0 : (cfirst - 1 + c) * NX) + n] * v[D.vo[2] + (cfirst - 1 + c) * NX + n];
+          const double tx = z[i0 * NX + n] - gamma * lt;
+          if (valid) A.q[i0 * NX + n] = acc3[nb][i] - tx;
+        }
+      }
+  }
+  if (!waited) spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);  // never exit with a bulk copy in flight
+}
+
+// ------------------------------------------------------------------------------------------------ forward level
+template <int NX, int NU, int DD>
+__launch_bounds__(256, spk_mm_minb(spk_mm_layout(NX, NU, DD).fwd_frags))
+__global__ void spk_k_fwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_g) {
+  constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
+  constexpr int KX = L.KX, KU = L.KU, NBX = L.NBX, NBU = L.NBU;
+  SPK_SMEM_DECL(double, smem);
+  const double *fr = smem + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
+  const int m = lane >> 2, kk = lane & 3;
+  const long count = A.p_cnt, first0 = spk_level_first0(DD, A.t) + A.p_lo, ntiles = (count + 7) / 8;
+  spk_mm_fetch(smem, frag_g, L.fwd_frags, tid);
+  bool waited = false;
+  const bool root = A.t == 0;
+  for (long tile = (long)blockIdx.x * wpb + warp; tile < ntiles; tile += (long)gridDim.x * wpb) {
+    long fm = tile * 8 + m;
+    const bool valid = fm < count;
+    if (!valid) fm = count - 1;
+    const long i0 = first0 + fm, cfirst = (long)DD * i0 + 1;
+    // ---- x_i (:667: x0 at the root) and d_i as A fragments; d_i again in C-fragment order as the start value of u_i
+    double xa[KX], da[KU], accu[NBU][2];
+#pragma unroll
+    for (int s = 0; s < KX; ++s) {
+      const int k = 4 * s + kk;
+      xa[s] = k < NX ? (root ? P.x0[k] : A.zbar[i0 * NX + k]) : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < KU; ++s) {
+      const int k = 4 * s + kk;
+      da[s] = k < NU ? A.dd[i0 * NU + k] : 0.0;
+    }
+#pragma unroll
+    for (int nb = 0; nb < NBU; ++nb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = 8 * nb + 2 * kk + i;
+        accu[nb][i] = n < NU ? A.dd[i0 * NU + n] : 0.0;
+      }
+    if (root && valid) {
+#pragma unroll
+      for (int s = 0; s < KX; ++s)
+        if (4 * s + kk < NX) A.zbar[4 * s + kk] = xa[s];
+    }
+    if (!waited) {
+      spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);
+      waited = true;
+    }
+    // ---- u_i = K x_i + d_i (:670-673)
+#pragma unroll
+    for (int s = 0; s < KX; ++s) {
+      const double *base = fr + (size_t)(L.fwd_k + s * NBU) * 32 + lane;
+#pragma unroll
+      for (int nb = 0; nb < NBU; ++nb) spk_dmma(accu[nb][0], accu[nb][1], xa[s], base[nb * 32]);
+    }
+    if (valid) {
+#pragma unroll
+      for (int nb = 0; nb < NBU; ++nb)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (8 * nb + 2 * kk + i < NU) A.zbar[D.zo[1] + i0 * NU + 8 * nb + 2 * kk + i] = accu[nb][i];
+    }
+    // ---- x_c = ABK_c x_i + B_c d_i (:675-679)
+#pragma unroll
+    for (int c = 0; c < DD; ++c) {
+      double accx[NBX][2];
+#pragma unroll
+      for (int nb = 0; nb < NBX; ++nb) accx[nb][0] = accx[nb][1] = 0.0;
+#pragma unroll
+      for (int s = 0; s < KX; ++s) {
+        const double *base = fr + (size_t)(L.fwd_abk + (c * KX + s) * NBX) * 32 + lane;
+#pragma unroll
+        for (int nb = 0; nb < NBX; ++nb) spk_dmma(accx[nb][0], accx[nb][1], xa[s], base[nb * 32]);
+      }
+#pragma unroll
+      for (int s = 0; s < KU; ++s) {
+        const double *base = fr + (size_t)(L.fwd_b + (c * KU + s) * NBX) * 32 + lane;
+#pragma unroll
+        for (int nb = 0; nb < NBX; ++nb) spk_dmma(accx[nb][0], accx[nb][1], da[s], base[nb * 32]);
+      }
+      if (valid) {
+#pragma unroll
+        for (int nb = 0; nb < NBX; ++nb)
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (8 * nb + 2 * kk + i < NX) A.zbar[(cfirst + c) * NX + 8 * nb + 2 * kk + i] = accx[nb][i];
+      }
+    }
+  }
+  if (!waited) spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);
+}
+#endif

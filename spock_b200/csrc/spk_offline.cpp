@@ -230,3 +230,64 @@ bool spk_kernel_projector(int ny, int d, const double *E, const double *F, std::
       for (int i = 0; i < nls; ++i) ls[i + (size_t)j * nls] -= q[i] * q[j];
   return true;
 }
+
+// ------------------------------------------------------------------------------------------------ tensor-pipe fragment tables
+#include "spk_mm_layout.h"
+
+namespace {
+// W(n, k) accessor of a column-major rows x cols matrix; zero outside
+struct WView {
+  const double *p;
+  int rows, cols, ld;
+  bool transposed;  // W(n, k) = p[k + n * ld] instead of p[n + k * ld]
+  double at(int n, int k) const {
+    if (n >= rows || k >= cols) return 0.0;
+    return transposed ? p[k + (long)n * ld] : p[n + (long)k * ld];
+  }
+};
+void put_natural(double *frag, const WView &W, int s, int nb) {
+  for (int T = 0; T < 32; ++T) frag[T] = W.at(8 * nb + T / 4, 4 * s + T % 4);
+}
+void put_permuted(double *frag, const WView &W, int ks, int nb) {
+  for (int T = 0; T < 32; ++T) frag[T] = W.at(8 * nb + T / 4, 8 * (ks / 2) + 2 * (T % 4) + (ks % 2));
+}
+}  // namespace
+
+void spk_mm_fragment_tables(const SpkFactorTable &T, const double *B, std::vector<double> &bwd, std::vector<double> &fwd) {
+  const int N = T.N, d = T.d, nx = T.nx, nu = T.nu;
+  const SpkMmLayout L = spk_mm_layout(nx, nu, d);
+  bwd.assign((size_t)(N - 1) * L.bwd_frags * 32, 0.0);
+  fwd.assign((size_t)(N - 1) * L.fwd_frags * 32, 0.0);
+  for (int t = 0; t < N - 1; ++t) {
+    double *fb = bwd.data() + (size_t)t * L.bwd_frags * 32, *ff = fwd.data() + (size_t)t * L.fwd_frags * 32;
+    const WView Rinv{T.Rinv.data() + (size_t)t * T.r_stride, nu, nu, nu, false};
+    const WView G{T.G.data() + (size_t)t * T.k_stride, nx, nu, nx, false};
+    const WView Kt{T.Kt.data() + (size_t)t * T.k_stride, nx, nu, nx, false};
+    const WView K{T.K.data() + (size_t)t * T.k_stride, nu, nx, nu, false};
+    for (int c = 0; c < d; ++c) {
+      const int w = spk_child_mode(d, c);
+      const double *Bw = B + (size_t)w * nx * nu;                       // nx x nu column-major
+      const WView Bt{Bw, nu, nx, nx, true};                             // Bt(n, k) = B(k, n)
+      const WView Bn{Bw, nx, nu, nx, false};
+      const WView ABKt{T.ABKt.data() + (size_t)(t * d + c) * T.abk_stride, nx, nx, nx, false};
+      const WView ABK{T.ABK.data() + (size_t)(t * d + c) * T.abk_stride, nx, nx, nx, false};
+      for (int s = 0; s < L.KX; ++s) {
+        double *base = fb + (size_t)(L.bwd_sweep + (c * L.KX + s) * (L.NBU + L.NBX)) * 32;
+        for (int nb = 0; nb < L.NBU; ++nb) put_natural(base + (size_t)nb * 32, Bt, s, nb);
+        for (int nb = 0; nb < L.NBX; ++nb) put_natural(base + (size_t)(L.NBU + nb) * 32, ABKt, s, nb);
+        for (int nb = 0; nb < L.NBX; ++nb) put_natural(ff + (size_t)(L.fwd_abk + (c * L.KX + s) * L.NBX + nb) * 32, ABK, s, nb);
+      }
+      for (int s = 0; s < L.KU; ++s)
+        for (int nb = 0; nb < L.NBX; ++nb) put_natural(ff + (size_t)(L.fwd_b + (c * L.KU + s) * L.NBX + nb) * 32, Bn, s, nb);
+    }
+    for (int ks = 0; ks < L.KUP; ++ks) {
+      for (int nb = 0; nb < L.NBU; ++nb) put_permuted(fb + (size_t)(L.bwd_s2 + ks * L.NBU + nb) * 32, Rinv, ks, nb);
+      for (int nb = 0; nb < L.NBX; ++nb) {
+        put_permuted(fb + (size_t)(L.bwd_s3b + ks * L.NBX + nb) * 32, G, ks, nb);
+        put_permuted(fb + (size_t)(L.bwd_s3c + ks * L.NBX + nb) * 32, Kt, ks, nb);
+      }
+    }
+    for (int s = 0; s < L.KX; ++s)
+      for (int nb = 0; nb < L.NBU; ++nb) put_natural(ff + (size_t)(L.fwd_k + s * L.NBU + nb) * 32, K, s, nb);
+  }
+}

@@ -28,3 +28,7 @@ bool spk_offline_factors(int N, int d, int nx, int nu, const double *A, const do
 
 // Orthogonal projector on ker [E' -I -I; F' 0 0], (ny+2d)^2 column-major
 bool spk_kernel_projector(int ny, int d, const double *E, const double *F, std::vector<double> &ls, std::string &err);
+
+// Fragment-ordered weight tables of the tensor-pipe S1 kernels (spk_mm_layout.h): level t occupies
+// bwd[t * bwd_frags * 32 ...] and fwd[t * fwd_frags * 32 ...].
+void spk_mm_fragment_tables(const SpkFactorTable &T, const double *B, std::vector<double> &bwd, std::vector<double> &fwd);

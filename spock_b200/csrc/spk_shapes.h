@@ -1,13 +1,16 @@
 // spk_shapes.h -- table entry of one shape-specialised set of fused kernels (see spk_shapes.def)
 #pragma once
 #include "spk_fused.cuh"
+#include "spk_mm.cuh"
 
 typedef void (*spk_fused_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs);
 typedef void (*spk_dual2_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long);
 typedef void (*spk_dual3_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs, long, long);
+typedef void (*spk_mm_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs, const double *);
 struct SpkShapeEntry {
   int nx, nu, d, Tb, Tf;
   spk_fused_kernel_t bwd, fwd, dual;
   spk_dual2_kernel_t dual2;
   spk_dual3_kernel_t dual3[2][2];  // [children are leaves][uniform cost diagonals]
+  spk_mm_kernel_t bwd_mm[2], fwd_mm;  // per-stage factors on the fp64 tensor pipe; bwd_mm[children are leaves]
 };

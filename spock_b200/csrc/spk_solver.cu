@@ -144,6 +144,14 @@ struct spk_handle {
   void (*k_dual2)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long) = nullptr;
   void (*k_dual3[2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {nullptr, nullptr};  // [children are leaves]
   int occ_dual3 = 4;
+  // per-stage factors on the fp64 tensor pipe (spk_mm.cuh)
+  bool use_mm = false;
+  void (*k_bwd_mm[2])(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = {nullptr, nullptr};
+  void (*k_fwd_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = nullptr;
+  double *d_frag_bwd = nullptr, *d_frag_fwd = nullptr;
+  long mm_bwd_frags = 0, mm_fwd_frags = 0;
+  int occ_bwd_mm = 1, occ_fwd_mm = 1;
+  std::vector<double> B_host;
   int dual2_F = 1;          // families per batch of the batched dual kernel
   size_t dual2_smem = 0;
   bool use_dual2 = true;
@@ -480,9 +488,14 @@ static int fused_setup(spk_handle *h) {
         // register-resident dual kernel: Diagonal sqrt-costs, risk cone and branching within one warp
         const char *e3 = getenv("SPK_NO_DUAL3");
         const bool uc = D.n_sqrtQ == 1 && D.n_sqrtQN == 1;
-        if (!D.cost_dense && D.ny <= 32 && D.d <= 32 && !(e3 && e3[0] == '1') && (uc || (D.n_sqrtQ > 1 && D.n_sqrtQN > 1))) {
+        if (!D.cost_dense && D.ny <= spk_dual3_group(D.nx, D.nu, D.d) && D.d <= 32 && !(e3 && e3[0] == '1') && (uc || (D.n_sqrtQ > 1 && D.n_sqrtQN > 1))) {
           h->k_dual3[0] = e.dual3[0][uc ? 1 : 0];
           h->k_dual3[1] = e.dual3[1][uc ? 1 : 0];
+        }
+        const char *emm = getenv("SPK_NO_MM");
+        if (!D.per_node && !D.cost_dense && !(emm && emm[0] == '1')) {
+          h->k_bwd_mm[0] = e.bwd_mm[0]; h->k_bwd_mm[1] = e.bwd_mm[1]; h->k_fwd_mm = e.fwd_mm;
+          h->use_mm = true;
         }
       }
     }
@@ -521,6 +534,26 @@ static int fused_setup(spk_handle *h) {
   if (h->k_dual3[1]) {
     RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_dual3, (const void *)h->k_dual3[1], 128, 0));
     h->occ_dual3 = std::max(1, h->occ_dual3);
+  }
+  if (h->use_mm) {  // fragment-ordered per-level weight tables (spk_mm_layout.h)
+    const SpkMmLayout L = spk_mm_layout(D.nx, D.nu, D.d);
+    h->mm_bwd_frags = L.bwd_frags; h->mm_fwd_frags = L.fwd_frags;
+    const size_t sb = spk_mm_smem_bytes(L.bwd_frags), sf = spk_mm_smem_bytes(L.fwd_frags);
+    if (std::max(sb, sf) > 227 * 1024) {
+      h->use_mm = false;
+    } else {
+      std::vector<double> fb, ff;
+      spk_mm_fragment_tables(h->table, h->B_host.data(), fb, ff);
+      SPK_TRY(upload(h, &h->d_frag_bwd, fb.data(), (long)fb.size()));
+      SPK_TRY(upload(h, &h->d_frag_fwd, ff.data(), (long)ff.size()));
+      for (int k = 0; k < 2; ++k)
+        RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd_mm[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+      RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
+      RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd_mm, (const void *)h->k_bwd_mm[1], 256, sb));
+      RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd_mm, (const void *)h->k_fwd_mm, 256, sf));
+      h->occ_bwd_mm = std::max(1, h->occ_bwd_mm);
+      h->occ_fwd_mm = std::max(1, h->occ_fwd_mm);
+    }
   }
   h->occ_fwd = std::max(1, h->occ_fwd);
 #endif
@@ -561,8 +594,18 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
       ProfScope ps(h, PC_FUSED_BWD);
       A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
       level_range(h, t, A.p_lo, A.p_cnt);
-      spk_fused_kernel_t kfn = h->k_bwd;
-      SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, h->stream, D, h->P, A);
+#ifndef SPK_HOST_EMU
+      if (h->use_mm) {  // per-stage factors: the level is a chain of mat-mats on the fp64 tensor pipe
+        const long ctas = std::min(((A.p_cnt + 7) / 8 + 7) / 8, (long)h->num_sms * h->occ_bwd_mm);
+        spk_mm_kernel_t kmm = h->k_bwd_mm[A.children_are_leaves ? 1 : 0];
+        kmm<<<(unsigned)std::max(1L, ctas), 256, spk_mm_smem_bytes((int)h->mm_bwd_frags), h->stream>>>(
+            D, h->P, A, h->d_frag_bwd + (size_t)t * h->mm_bwd_frags * 32);
+      } else
+#endif
+      {
+        spk_fused_kernel_t kfn = h->k_bwd;
+        SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, h->stream, D, h->P, A);
+      }
       COUNT_LAUNCH(h, PC_FUSED_BWD);
     }
     if (h->world > 1 && t == h->t_cut) {  // the replicated levels above the cut need every subtree root's q
@@ -576,8 +619,17 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     ProfScope ps(h, PC_FUSED_FWD);
     A.t = t; A.children_are_leaves = (t == D.N - 2);
     level_range(h, t, A.p_lo, A.p_cnt);
-    spk_fused_kernel_t kfn = h->k_fwd;
-    SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D, h->P, A);
+#ifndef SPK_HOST_EMU
+    if (h->use_mm) {
+      const long ctas = std::min(((A.p_cnt + 7) / 8 + 7) / 8, (long)h->num_sms * h->occ_fwd_mm);
+      h->k_fwd_mm<<<(unsigned)std::max(1L, ctas), 256, spk_mm_smem_bytes((int)h->mm_fwd_frags), h->stream>>>(
+          D, h->P, A, h->d_frag_fwd + (size_t)t * h->mm_fwd_frags * 32);
+    } else
+#endif
+    {
+      spk_fused_kernel_t kfn = h->k_fwd;
+      SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D, h->P, A);
+    }
     COUNT_LAUNCH(h, PC_FUSED_FWD);
   }
   long pn_parts = owned;  // number of <r,Pr> partials in d_pnorm
@@ -597,7 +649,8 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
         long g;
 #ifndef SPK_HOST_EMU
         if (h->k_dual3[part]) {  // 4c. one warp per family, everything in registers
-          g = std::min((b - a + 3) / 4, (long)h->num_sms * h->occ_dual3);
+          const long fpc = 4L * (32 / spk_dual3_group(D.nx, D.nu, D.d));  // families per CTA (4 warps)
+          g = (b - a + fpc - 1) / fpc;
           spk_dual3_kernel_t k3 = h->k_dual3[part];
           k3<<<(unsigned)g, 128, 0, h->stream>>>(D, h->P, A2, a, b - a);
         } else
@@ -945,6 +998,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   double *tmp;
   SPK_TRY(upload(h, &tmp, p->A, (long)d * nx * nx)); h->P.A = tmp;
   SPK_TRY(upload(h, &tmp, p->B, (long)d * nx * nu)); h->P.B = tmp;
+  h->B_host.assign(p->B, p->B + (size_t)d * nx * nu);
   std::vector<double> Bt((size_t)d * nx * nu);
   for (int w = 0; w < d; ++w)
     for (int r = 0; r < nx; ++r)
@@ -1005,7 +1059,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   h->red_blocks = SPK_EMU ? 8 : 148 * 8;
   SPK_TRY(dev_alloc(h, &h->d_partial, h->red_blocks));
   SPK_TRY(dev_alloc(h, &h->d_scal, 32));
-  SPK_TRY(dev_alloc(h, &h->d_pnorm, std::max(nnl, 1L)));
+  SPK_TRY(dev_alloc(h, &h->d_pnorm, nnl + 64));
   SPK_TRY(fused_setup(h));
   h->rank = p->rank; h->world = p->world_size > 1 ? p->world_size : 1;
   if (h->world > 1) {
@@ -1237,6 +1291,86 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   h->last_xi2 = h->h_scal[1];
   const float t = timer.stop();
   if (ms) *ms = t;
+  return SPK_OK;
+}
+
+// ---- persistent solver memory (checkpoint / resume), layout documented in include/spock_b200.h
+int spk_state_size(const spk_handle *h, int64_t *doubles) {
+  if (!h || !doubles) return fail(SPK_ERR_INVALID, "NULL argument");
+  const int64_t nr = h->D.nz + h->D.nv;
+  *doubles = h->alg == SPK_SP ? 12 * nr + AA_M * AA_M : nr;
+  return SPK_OK;
+}
+static void state_blocks(spk_handle *h, std::vector<double *> &blocks) {
+  blocks.push_back(h->zv_old);
+  if (h->alg == SPK_SP) {
+    blocks.push_back(h->rzv_old);
+    blocks.push_back(h->dzv);
+    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->MP[j]);
+    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->MR[j]);
+    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->AQ[j]);
+  }
+}
+int spk_get_state(spk_handle *h, double *state) {
+  if (!h || !state) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->world > 1) return fail(SPK_ERR_INVALID, "spk_get_state is single-GPU");
+  const long nr = h->D.nz + h->D.nv;
+  std::vector<double *> blocks;
+  state_blocks(h, blocks);
+  for (size_t k = 0; k < blocks.size(); ++k) SPK_TRY(rt_d2h(state + k * nr, blocks[k], sizeof(double) * nr, h->stream));
+  if (h->alg == SPK_SP)
+    for (int k = 0; k < AA_M * AA_M; ++k) state[blocks.size() * nr + k] = h->aaR[k];
+  return SPK_OK;
+}
+int spk_set_state(spk_handle *h, const double *state) {
+  if (!h || !state) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->world > 1) return fail(SPK_ERR_INVALID, "spk_set_state is single-GPU");
+  const long nr = h->D.nz + h->D.nv;
+  std::vector<double *> blocks;
+  state_blocks(h, blocks);
+  for (size_t k = 0; k < blocks.size(); ++k) SPK_TRY(rt_h2d(blocks[k], state + k * nr, sizeof(double) * nr, h->stream));
+  if (h->alg == SPK_SP)
+    for (int k = 0; k < AA_M * AA_M; ++k) h->aaR[k] = state[blocks.size() * nr + k];
+  return SPK_OK;
+}
+
+// ---- ||L||^2: power iteration on L'L (largest eigenvalue) with the modular L / L' kernels
+int spk_estimate_L_norm(spk_handle *h, int32_t iters, double *L_norm) {
+  if (!h || !L_norm) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->world > 1) return fail(SPK_ERR_INVALID, "spk_estimate_L_norm is single-GPU");
+  const long nz = h->D.nz;
+  if (iters <= 0) iters = 50;
+  // scratch that carries nothing across passes or solves
+  double *w = h->zw, *Lw = h->ws_L + nz, *LtLw = h->xi;
+  {  // deterministic start vector with a component along every coordinate
+    std::vector<double> init((size_t)nz);
+    for (long k = 0; k < nz; ++k) init[(size_t)k] = 1.0 + 0.5 * std::sin(0.7 * (double)k + 0.3);
+    SPK_TRY(rt_h2d(w, init.data(), sizeof(double) * nz, h->stream));
+  }
+  double lam = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    SPK_TRY(op_reduce(h, nz, 0, w, w, 8, 0));
+    SPK_TRY(fetch_scalars(h, 9));
+    const double nrm = std::sqrt(h->h_scal[8]);
+    if (!(nrm > 0)) return fail(SPK_ERR_INVALID, "power iteration collapsed to zero");
+    SPK_TRY(op_axpby(h, nz, 1.0 / nrm, w, 0.0, nullptr, w));
+    SPK_TRY(op_L(h, w, 1.0, 0.0, nullptr, Lw));
+    SPK_TRY(op_Lt(h, Lw, 1.0, 0.0, nullptr, LtLw));
+    SPK_TRY(op_reduce(h, nz, 0, w, LtLw, 8, 0));  // Rayleigh quotient w'L'Lw with ||w|| = 1
+    SPK_TRY(fetch_scalars(h, 9));
+    const double next = h->h_scal[8];
+    SPK_TRY(rt_d2d(w, LtLw, sizeof(double) * nz, h->stream));
+    const bool done = it > 3 && std::fabs(next - lam) <= 1e-10 * next;
+    lam = next;
+    if (done) break;
+  }
+  SPK_TRY(rt_sync(h->stream));
+  *L_norm = lam;
+  return SPK_OK;
+}
+int spk_set_L_norm(spk_handle *h, double L_norm) {
+  if (!h || !(L_norm > 0)) return fail(SPK_ERR_INVALID, "L_norm must be positive");
+  h->L_norm = L_norm;
   return SPK_OK;
 }
 

@@ -246,3 +246,54 @@ def test_cuda_graph_replay_equals_stream_launches(cuda_lib, monkeypatch):
             out.append(h.get_iterate() + (h.residuals(),))
             h.close()
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+
+
+def _per_node_diagonal_cost_flat(N, d, nx, nu, uniform_terminal=False):
+    """Random system with a different Diagonal cost at every node (Vector{Diagonal} in the reference, cost.jl:3-7)."""
+    from spock_b200.problem import Cost, Diagonal
+
+    scen_tree, _, dynamics, rms, constraints = get_random_system_specs(N, d, nx, nu)
+    rng = np.random.default_rng(21)
+    Q = [Diagonal(0.05 + rng.random(nx)) for _ in range(scen_tree.n - 1)]
+    R = [Diagonal(0.5 + rng.random(nu)) for _ in range(scen_tree.n - 1)]
+    QN = Diagonal(0.1 * np.ones(nx)) if uniform_terminal else [Diagonal(0.05 + rng.random(nx)) for _ in range(scen_tree.n_leaf_nodes)]
+    return flatten_problem(scen_tree, Cost(Q, R, QN), dynamics, rms, constraints)
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(50, 20, 2, 5), (10, 10, 4, 4), (5, 5, 2, 7), (20, 20, 3, 4)])
+@pytest.mark.parametrize("uniform_terminal", [False, True])
+def test_register_dual_kernel_per_node_diagonal_costs(cuda_lib, nx, nu, d, N, uniform_terminal):
+    """spk_k_dual3 with per-node Diagonal sqrt-costs (UC = false instantiation) and the mixed per-node / uniform case
+    (falls back to the batched kernel) against the oracle, both factor modes (per-stage: tensor-pipe S1 sweeps)."""
+    flat = _per_node_diagonal_cost_flat(N, d, nx, nu, uniform_terminal)
+    for fm in (0, 1):
+        check_k_steps(cuda_lib, flat, CP, 20, factor_mode=fm)
+    check_k_steps(cuda_lib, flat, SP, 8, factor_mode=1)
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(50, 20, 2, 8), (50, 50, 2, 6), (20, 20, 2, 9), (10, 10, 4, 6), (10, 10, 2, 10),
+                                       (5, 5, 2, 11), (20, 20, 3, 6), (10, 10, 3, 7)])
+def test_tensor_pipe_sweeps_equal_family_kernels(cuda_lib, nx, nu, d, N, monkeypatch):
+    """Per-stage factors: the DMMA level kernels (spk_mm.cuh; tiles of 8 families, ragged last tiles on every level of a
+    d = 3 tree) against the CTA-per-family kernels on random iterates, and both against the oracle's projection_S1."""
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    rng = np.random.default_rng(17)
+    out = []
+    for no_mm in ("1", "0"):
+        monkeypatch.setenv("SPK_NO_MM", no_mm)
+        h = Handle(flat, CP, factor_mode=1, lib=cuda_lib)
+        if not out:
+            z0, v0, x0 = rng.standard_normal(h.nz), rng.standard_normal(h.nv), rng.standard_normal(nx)
+        h.set_x0(x0)
+        h.set_iterate(z0, v0)
+        h.step(4)
+        out.append(h.get_iterate() + (h.residuals(),))
+        h.close()
+    (zf, vf, xf), (zm, vm, xm) = out
+    assert relerr(zm, zf) < 1e-12 and relerr(vm, vf) < 1e-12
+    assert abs(xm[0] - xf[0]) < 1e-10 * xf[0] and abs(xm[1] - xf[1]) < 1e-10 * xf[1]
+    o = Oracle(flat, CP)
+    o.set_x0(x0)
+    o.z[:], o.v[:] = z0, v0
+    o.step(4)
+    assert relerr(zm, o.z) < 1e-11 and relerr(vm, o.v) < 1e-11
