@@ -40,6 +40,9 @@ CPU_SAMPLE_N = {"config3": 14, "config3_half": 14, "heat15": 12, "config5_slice"
 NCU_TRAFFIC = {("config3", "per_node"): (16.767805e9 + 0.150771712e9) * 524287 / 262144}
 
 
+DMMA_PEAK_TFLOPS = 37.1  # mma.sync.m8n8k4.f64, measured (tools/microbench/dmma_bench.cu)
+
+
 def make_spec(name, N_override=None):
     from spock_b200.examples import get_random_system_specs, get_server_heat_specs
 
@@ -357,9 +360,27 @@ def main():
                 h2.set_x0(x0)
                 h2.step(args.warmup)
                 ms2 = h2.step(args.steps) / args.steps
+                h2.profile(True)
+                h2.step(args.steps)
+                prof2 = {k: v["ms"] / args.steps for k, v in h2.profile_report().items() if v["launches"]}
+                h2.profile(False)
                 bv, bf, _ = algorithmic_bytes(flat, 1)
-                line["per_stage_factors"] = {"value": 1000.0 / ms2, "unit": "iterations/s", "ms_per_step": ms2,
-                                             "algorithmic_bytes": bv + bf, "achieved_GBs": (bv + bf) / 1e9 / (ms2 / 1e3)}
+                # S1 sweeps on the fp64 tensor pipe (spk_mm.cuh): useful flops of SURVEY 8(d) against the measured DMMA peak
+                fl_bwd = 2.0 * ((nx * nx + nx * nu) * (flat.n - 1) + (nu * nu + 2 * nx * nu) * flat.n_non_leaf)
+                fl_fwd = 2.0 * ((nx * nx + nx * nu) * (flat.n - 1) + nx * nu * flat.n_non_leaf)
+                r2, _ = h2.solve(x0, tol=1e-3, max_iter=1500, z0=np.zeros(h2.nz), v0=np.zeros(h2.nv))
+                line["per_stage_factors"] = {
+                    "value": 1000.0 / ms2, "unit": "iterations/s", "ms_per_step": ms2,
+                    "algorithmic_bytes": bv + bf, "achieved_GBs": (bv + bf) / 1e9 / (ms2 / 1e3),
+                    "frac_of_hbm_peak": (bv + bf) / 1e9 / (ms2 / 1e3) / peak,
+                    "per_kernel_ms_per_pass": prof2,
+                    "tensor_pipe": {"bound": "fp64 DMMA", "peak_TFLOPs": DMMA_PEAK_TFLOPS,
+                                    "peak_source": "tools/microbench/dmma_bench.cu on this pool (profiles/r01d_dmma_microbench.txt)",
+                                    "backward_TFLOPs": fl_bwd / 1e12 / (prof2["fused_backward"] / 1e3),
+                                    "forward_TFLOPs": fl_fwd / 1e12 / (prof2["fused_forward"] / 1e3)},
+                    "time_to_tol": {"tol": 1e-3, "seconds": r2["solve_ms"] / 1e3, "iterations": r2["passes"],
+                                    "converged": bool(r2["converged"])},
+                }
                 h2.close()
             line["cpu_baseline"] = cpu_baseline(args.workload, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)

@@ -23,7 +23,8 @@ EXPORTS = [
     "spk_last_error", "spk_version", "spk_create", "spk_destroy", "spk_sizes", "spk_offsets", "spk_tree_maps",
     "spk_set_x0", "spk_set_iterate", "spk_get_iterate", "spk_apply", "spk_dot", "spk_get_factors", "spk_step",
     "spk_solve", "spk_get_residuals", "spk_profile", "spk_profile_get", "spk_launch_count", "spk_device_bytes",
-    "spk_comm_unique_id", "spk_owned_ranges",
+    "spk_comm_unique_id", "spk_owned_ranges", "spk_state_size", "spk_get_state", "spk_set_state",
+    "spk_estimate_L_norm", "spk_set_L_norm",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -85,6 +86,11 @@ def bind(path: str) -> C.CDLL:
     lib.spk_device_bytes.argtypes = [vp, _i64p]
     lib.spk_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.spk_owned_ranges.argtypes = [vp, _i32p, _i64p, _i64p]
+    lib.spk_state_size.argtypes = [vp, _i64p]
+    lib.spk_get_state.argtypes = [vp, _dp]
+    lib.spk_set_state.argtypes = [vp, _dp]
+    lib.spk_estimate_L_norm.argtypes = [vp, C.c_int32, _dp]
+    lib.spk_set_L_norm.argtypes = [vp, C.c_double]
     for name in EXPORTS:
         if name not in ("spk_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -74,7 +74,13 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra_flags=()) -> str:
+    """variant/extra_flags: development builds with extra nvcc flags into csrc/_variants/<variant>.so (tuning sweeps)."""
+    global OBJ, LIB, NVCC_FLAGS
+    if variant:
+        OBJ = os.path.join(CSRC, "_variants", variant + "_obj")
+        LIB = os.path.join(CSRC, "_variants", variant + ".so")
+        NVCC_FLAGS = NVCC_FLAGS + list(extra_flags)
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -110,4 +116,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    flags = sys.argv[sys.argv.index("--flags") + 1].split() if "--flags" in sys.argv else []
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, extra_flags=flags))

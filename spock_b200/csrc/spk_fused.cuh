@@ -116,6 +116,7 @@ struct SpkFusedArgs {
   int t;                   // level of the parents handled by this launch (kernels 1, 2)
   int children_are_leaves; // t == N-2
   double gamma, sigma;
+  double inv_gamma, inv_sigma;  // reciprocals, computed once on the host
   const double *z, *v;     // input iterate (reference layout)
   double *zbar, *vbar;     // output iterate
   double *q, *dd;          // sweep scratch: q (n*nx), d (nnl*nu)
@@ -1070,6 +1071,9 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
 // grid-stride loop: address registers die as soon as the loads are issued, so more warps are resident.
 // UC: the sqrt-cost diagonals are uniform over the nodes instead of per node.
 #if !SPK_EMU
+#ifndef SPK_DUAL3_MINB
+#define SPK_DUAL3_MINB 3
+#endif
 SPK_CONSTEXPR_HD int spk_dual3_group(int nx, int nu, int d) {
   int m = nx > nu ? nx : nu;
   if (m > 32) return 32;
@@ -1083,8 +1087,18 @@ SPK_D void spk_atomic_max_lazy(double *addr, double val) {
   if (val > __ldcg(addr)) spk_atomic_max_nonneg(addr, val);
 }
 
-template <int NX, int NU, int DD, bool LEAVES, bool UC>
-__launch_bounds__(128, 4)
+// exact maximum of non-negative doubles over the warp with two integer REDUX operations (high words, then the low
+// words of the lanes that hold the maximal high word)
+SPK_D double spk_warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
+// PN: also accumulate <r, P r> (SuperMann only; Chambolle-Pock needs just the residual maxima)
+template <int NX, int NU, int DD, bool LEAVES, bool UC, bool PN>
+__launch_bounds__(128, SPK_DUAL3_MINB)
 __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, long fam_cnt) {
   constexpr int G = spk_dual3_group(NX, NU, DD), FPW = 32 / G;  // lanes per family, families per warp
   constexpr int RX = (NX + G - 1) / G, RU = (NU + G - 1) / G, CD = UC ? 1 : DD, LD = LEAVES ? DD : 1;
@@ -1092,7 +1106,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   const int wlane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int lane = wlane & (G - 1);  // lane within the family's group
   const int ny = D.ny;
-  const double gamma = A.gamma, sigma = A.sigma, inv_sigma = 1.0 / sigma, inv_gamma = 1.0 / gamma;
+  const double gamma = A.gamma, sigma = A.sigma, inv_sigma = A.inv_sigma, inv_gamma = A.inv_gamma;
   const double *__restrict__ z = A.z, *__restrict__ zb = A.zbar, *__restrict__ v = A.v;
   double *__restrict__ vb = A.vbar;
   const double x_min = D.x_min, x_max = D.x_max, u_min = D.u_min, u_max = D.u_max;
@@ -1109,7 +1123,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   {                                                            \
     const double dzv_ = (dz_), ltv_ = (lt_);                   \
     my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
-    my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
+    if (PN) my_pn += dzv_ * (dzv_ - gamma * ltv_);             \
   }
   // vbar = sigma (W - Proj W), delta v, xi2 and the v-part of <r, P r> of one dual entry
 #define SPK_FIN3(ptr_, w_, vold_, Ld_, pr_, dl_)                        \
@@ -1118,7 +1132,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     *(ptr_) = vnew_;                                                    \
     dl_ = vnew_ - (vold_);                                              \
     my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
-    my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
+    if (PN) my_pn += dl_ * (dl_ - sigma * (Ld_));                       \
   }
   // ---------------------------------------------------------------- loads (all independent)
   double wx[RX], dx[RX], v7x[RX], v3[DD][RX], sQ[CD][RX], sQN[CD][RX];
@@ -1322,7 +1336,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
       vb[D.vo[1] + i0] = v2new;
       const double l2 = ds_i - bdy;
       my_xi2 = fmax(my_xi2, fabs(l2 - dv2 * inv_sigma));
-      my_pn += dv2 * (dv2 - sigma * l2);
+      if (PN) my_pn += dv2 * (dv2 - sigma * l2);
     }
   }
   // ---------------------------------------------------------------- v7_i box (:903-908); starts the L'dv accumulators
@@ -1418,12 +1432,12 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
 #undef SPK_UON
   // ---- folds: maxima by (lazy) atomicMax; <r, P r> as one deterministic partial per CTA
   if (!valid) my_pn = 0.0;
-  const double m1 = spk_warp_max(my_xi1), m2 = spk_warp_max(my_xi2);
+  const double m1 = spk_warp_max_nonneg(my_xi1), m2 = spk_warp_max_nonneg(my_xi2);
   if (wlane == 0) {
     spk_atomic_max_lazy(A.xi + 0, m1);
     spk_atomic_max_lazy(A.xi + 1, m2);
   }
-  if (A.pnorm) {
+  if (PN) {
     const double ps = spk_warp_sum(my_pn);
     if (wlane == 0) s_red[warp] = ps;
     __syncthreads();

@@ -11,6 +11,6 @@ struct SpkShapeEntry {
   int nx, nu, d, Tb, Tf;
   spk_fused_kernel_t bwd, fwd, dual;
   spk_dual2_kernel_t dual2;
-  spk_dual3_kernel_t dual3[2][2];  // [children are leaves][uniform cost diagonals]
+  spk_dual3_kernel_t dual3[2][2][2];  // [children are leaves][uniform cost diagonals][with <r,Pr>]
   spk_mm_kernel_t bwd_mm[2], fwd_mm;  // per-stage factors on the fp64 tensor pipe; bwd_mm[children are leaves]
 };

@@ -142,7 +142,7 @@ struct spk_handle {
   void (*k_fwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_dual)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_dual2)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long) = nullptr;
-  void (*k_dual3[2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {nullptr, nullptr};  // [children are leaves]
+  void (*k_dual3[2][2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {{nullptr, nullptr}, {nullptr, nullptr}};  // [children are leaves][with <r,Pr>]
   int occ_dual3 = 4;
   // per-stage factors on the fp64 tensor pipe (spk_mm.cuh)
   bool use_mm = false;
@@ -489,8 +489,8 @@ static int fused_setup(spk_handle *h) {
         const char *e3 = getenv("SPK_NO_DUAL3");
         const bool uc = D.n_sqrtQ == 1 && D.n_sqrtQN == 1;
         if (!D.cost_dense && D.ny <= spk_dual3_group(D.nx, D.nu, D.d) && D.d <= 32 && !(e3 && e3[0] == '1') && (uc || (D.n_sqrtQ > 1 && D.n_sqrtQN > 1))) {
-          h->k_dual3[0] = e.dual3[0][uc ? 1 : 0];
-          h->k_dual3[1] = e.dual3[1][uc ? 1 : 0];
+          for (int lv = 0; lv < 2; ++lv)
+            for (int pn = 0; pn < 2; ++pn) h->k_dual3[lv][pn] = e.dual3[lv][uc ? 1 : 0][pn];
         }
         const char *emm = getenv("SPK_NO_MM");
         if (!D.per_node && !D.cost_dense && !(emm && emm[0] == '1')) {
@@ -531,8 +531,8 @@ static int fused_setup(spk_handle *h) {
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, (const void *)h->k_bwd, Tb, h->fused_smem_bwd));
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, (const void *)h->k_fwd, Tf, h->fused_smem_fwd));
   h->occ_bwd = std::max(1, h->occ_bwd);
-  if (h->k_dual3[1]) {
-    RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_dual3, (const void *)h->k_dual3[1], 128, 0));
+  if (h->k_dual3[1][0]) {
+    RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_dual3, (const void *)h->k_dual3[1][0], 128, 0));
     h->occ_dual3 = std::max(1, h->occ_dual3);
   }
   if (h->use_mm) {  // fragment-ordered per-level weight tables (spk_mm_layout.h)
@@ -576,7 +576,7 @@ static unsigned fused_grid(const spk_handle *h, long count, int occ) {
 static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
   const SpkDims &D = h->D;
   SpkFusedArgs A;
-  A.gamma = gamma; A.sigma = sigma;
+  A.gamma = gamma; A.sigma = sigma; A.inv_gamma = 1.0 / gamma; A.inv_sigma = 1.0 / sigma;
   A.z = zv_in; A.v = zv_in + D.nz; A.zbar = zv_out; A.vbar = zv_out + D.nz;
   A.q = h->ric_q; A.dd = h->ric_d; A.xi = h->d_scal; A.pnorm = pnorm_slot >= 0 ? h->d_pnorm : nullptr;
   A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0; A.p_lo = 0; A.p_cnt = 0;
@@ -648,10 +648,10 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
         A2.pnorm = A.pnorm ? A.pnorm + pn_off : nullptr;
         long g;
 #ifndef SPK_HOST_EMU
-        if (h->k_dual3[part]) {  // 4c. one warp per family, everything in registers
+        if (h->k_dual3[part][0]) {  // 4c. one group of lanes per family, everything in registers
           const long fpc = 4L * (32 / spk_dual3_group(D.nx, D.nu, D.d));  // families per CTA (4 warps)
           g = (b - a + fpc - 1) / fpc;
-          spk_dual3_kernel_t k3 = h->k_dual3[part];
+          spk_dual3_kernel_t k3 = h->k_dual3[part][A.pnorm ? 1 : 0];
           k3<<<(unsigned)g, 128, 0, h->stream>>>(D, h->P, A2, a, b - a);
         } else
 #endif

@@ -65,6 +65,31 @@ class Handle:
         check(self.lib, self.lib.spk_get_iterate(self._h, dptr(z), dptr(v)))
         return z, v
 
+    def get_state(self):
+        """Solver memory that persists across solves besides (z, v) (checkpoint / resume; layout: include/spock_b200.h)."""
+        n = C.c_int64()
+        check(self.lib, self.lib.spk_state_size(self._h, C.byref(n)))
+        st = np.empty(int(n.value))
+        check(self.lib, self.lib.spk_get_state(self._h, dptr(st)))
+        return st
+
+    def set_state(self, state):
+        n = C.c_int64()
+        check(self.lib, self.lib.spk_state_size(self._h, C.byref(n)))
+        state = _f64(state)
+        if state.shape != (int(n.value),):
+            raise ValueError("state has the wrong length")
+        check(self.lib, self.lib.spk_set_state(self._h, dptr(state)))
+
+    def estimate_L_norm(self, iters: int = 0, apply: bool = False) -> float:
+        """||L||^2 by power iteration on the device; apply=True makes it the value behind the default step sizes."""
+        out = C.c_double()
+        check(self.lib, self.lib.spk_estimate_L_norm(self._h, int(iters), C.byref(out)))
+        if apply:
+            check(self.lib, self.lib.spk_set_L_norm(self._h, out.value))
+            self.L_norm = out.value
+        return out.value
+
     # ------------------------------------------------------------------ operators
     _IN_LEN = {OP_L: "nz", OP_LT: "nv", OP_PROX_F: "nz", OP_PROX_HCONJ: "nv"}
     _OUT_LEN = {OP_L: "nv", OP_LT: "nz", OP_PROX_F: "nz", OP_PROX_HCONJ: "nv"}

@@ -22,7 +22,7 @@ def lib():
 
 def test_exports_match_header(lib):
     header = open(os.path.join(ROOT, "include", "spock_b200.h")).read()
-    declared = set(re.findall(r"\b(spk_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(spk_[A-Za-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     assert declared == set(_lib.EXPORTS)
     for name in declared:

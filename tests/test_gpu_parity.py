@@ -297,3 +297,46 @@ def test_tensor_pipe_sweeps_equal_family_kernels(cuda_lib, nx, nu, d, N, monkeyp
     o.z[:], o.v[:] = z0, v0
     o.step(4)
     assert relerr(zm, o.z) < 1e-11 and relerr(vm, o.v) < 1e-11
+
+
+def test_state_checkpoint_resume_is_bit_exact(cuda_lib):
+    """spk_get_state / spk_set_state + the iterate = everything the next pass reads: a SuperMann run interrupted after
+    9 passes and resumed in a FRESH handle reproduces the uninterrupted run bit for bit (Anderson memory included)."""
+    flat = flat_of("heat_N7_d2_nx5")
+    for alg, k1, k2 in ((SP, 9, 11), (CP, 20, 15)):
+        ref = Handle(flat, alg, factor_mode=1, lib=cuda_lib)
+        ref.set_x0(0.1 * np.ones(5))
+        ref.step(k1)
+        z1, v1 = ref.get_iterate()
+        st = ref.get_state()
+        ref.step(k2)
+        z_ref, v_ref = ref.get_iterate()
+        ref.close()
+        h = Handle(flat, alg, factor_mode=1, lib=cuda_lib)
+        h.set_x0(0.1 * np.ones(5))
+        assert h.get_state().shape == st.shape == ((12 * (h.nz + h.nv) + 9,) if alg == SP else (h.nz + h.nv,))
+        h.set_iterate(z1, v1)
+        h.set_state(st)
+        h.step(k2)
+        z, v = h.get_iterate()
+        h.close()
+        # (r_safe and the iteration counters are per-solve locals, sp.jl:366-386: both runs restart them at the split)
+        assert np.array_equal(z, z_ref) and np.array_equal(v, v_ref)
+
+
+def test_power_iteration_L_norm(cuda_lib):
+    """||L||^2 from the device power iteration == the largest eigenvalue of L'L assembled column by column from the oracle's L;
+    the reference's hard-coded values (10 / 3.28) are upper bounds of it for server_heat (cpock.jl:62, spock.jl:63)."""
+    flat = flat_of("fixture_N3_d2")
+    h, o = Handle(flat, CP, lib=cuda_lib), Oracle(flat, CP)
+    Lmat = np.stack([o.L(e) for e in np.eye(h.nz)], axis=1)
+    lam = float(np.linalg.eigvalsh(Lmat.T @ Lmat)[-1])
+    est = h.estimate_L_norm(400)
+    assert abs(est - lam) < 1e-6 * lam
+    h.close()
+    hh = Handle(flat_of("heat_N7_d2_nx5"), CP, lib=cuda_lib)
+    est = hh.estimate_L_norm(200, apply=True)
+    assert 1.0 < est < 3.28
+    res, _ = hh.solve(0.1 * np.ones(5), tol=1e-3)  # converges with the estimated (larger) step sizes
+    assert res["converged"] == 1
+    hh.close()
