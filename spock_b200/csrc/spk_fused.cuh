@@ -123,6 +123,7 @@ struct SpkFusedArgs {
   double *xi;              // xi[0] = xi1, xi[1] = xi2 (atomic max; reset by the first backward launch of the pass)
   double *pnorm;           // per-family partial of <r, P r> (nnl doubles), or NULL
   int reset_xi;            // this launch zeroes xi[0..1] (block 0)
+  const int *gate;         // device-side "done" flag of the loop (spk_sp.cuh): every kernel returns at once when it is set
   // ownership (multi-GPU subtree partition; a single GPU owns everything):
   long p_lo, p_cnt;        // kernels 1, 2: positions [p_lo, p_lo + p_cnt) of level t are processed by this rank
   int n_ranges;            // kernels 3, 4: the owned families are n_ranges contiguous node ranges
@@ -222,6 +223,7 @@ SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
 template <int NX_, int NU_, int D_, int T_>
 SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
   const int tid = threadIdx.x, t = A.t;
   const int WL = T < 32 ? T : 32, warp = tid / WL, lane = tid % WL;
@@ -375,6 +377,7 @@ SPK_HD long spk_fwd_smem_doubles(const SpkDims &D, int T) {
 template <int NX_, int NU_, int D_, int T_>
 SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
   const int tid = threadIdx.x, t = A.t;
   const int R = nu + d * nx, S = spk_slices(T, R);
@@ -464,6 +467,7 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
 // s_1 -= gamma (:741), the only s entry outside every S2 group.
 #ifndef SPK_SHAPE_TU  // not a template: defined in the solver's translation unit only
 SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  if (A.gate && *A.gate) return;
   const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= A.r_prefix[A.n_ranges]) return;
   const long i0 = spk_owned_family(A, f);
@@ -513,6 +517,7 @@ __launch_bounds__(128, SPK_DUAL_MINB)
 #endif
 SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, ny = D.ny;
   const int T = blockDim.x, tid = threadIdx.x;
   const int WL = T < 32 ? T : 32;  // lanes per warp (1 in the host-emulation test build)
@@ -786,6 +791,7 @@ __launch_bounds__(256, 4)
 #endif
 SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fam_lo, long fam_cnt) {
   SPK_SMEM_DECL(double, S);
+  if (A.gate && *A.gate) return;
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, ny = D.ny;
   const int T = blockDim.x, tid = threadIdx.x;
   const int WL = T < 32 ? T : 32, nwarps = (T + WL - 1) / WL, warp = tid / WL, lane = tid % WL;
@@ -1100,6 +1106,7 @@ SPK_D double spk_warp_max_nonneg(double v) {
 template <int NX, int NU, int DD, bool LEAVES, bool UC, bool PN>
 __launch_bounds__(128, SPK_DUAL3_MINB)
 __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, long fam_cnt) {
+  if (A.gate && *A.gate) return;
   constexpr int G = spk_dual3_group(NX, NU, DD), FPW = 32 / G;  // lanes per family, families per warp
   constexpr int RX = (NX + G - 1) / G, RU = (NU + G - 1) / G, CD = UC ? 1 : DD, LD = LEAVES ? DD : 1;
   __shared__ double s_red[3 * 4];

@@ -41,10 +41,7 @@ SPK_HD void spk_project_soc_serial(double *vec, int len) {
 // ------------------------------------------------------------------------------------------------ L and L'
 
 // out[e] = alpha * (L' v)[e] + beta * in[e]     L_transpose! implicit_l.jl:320-449 fused with spock_mul! :451-481
-SPK_KERNEL void spk_k_Lt(SpkDims D, SpkPtrs P, const double *__restrict__ v, double alpha, double beta,
-                         const double *__restrict__ in, double *__restrict__ out) {
-  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= D.nz) return;
+SPK_D double spk_Lt_entry(const SpkDims &D, const SpkPtrs &P, const double *__restrict__ v, long e) {
   const int nx = D.nx, nu = D.nu, d = D.d;
   double val;
   if (e < D.zo[1]) {  // x
@@ -87,14 +84,18 @@ SPK_KERNEL void spk_k_Lt(SpkDims D, SpkPtrs P, const double *__restrict__ v, dou
     const int k = (int)(idx - i0 * D.ny);
     val = v[idx] - P.b[k] * v[D.vo[1] + i0];
   }
+  return val;
+}
+SPK_KERNEL void spk_k_Lt(SpkDims D, SpkPtrs P, const double *__restrict__ v, double alpha, double beta,
+                         const double *__restrict__ in, double *__restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.nz) return;
+  const double val = spk_Lt_entry(D, P, v, e);
   out[e] = (beta == 0.0) ? alpha * val : alpha * val + beta * in[e];
 }
 
 // out[e] = alpha * (L z)[e] + beta * in[e]      L! implicit_l.jl:177-318 fused with spock_mul!
-SPK_KERNEL void spk_k_L(SpkDims D, SpkPtrs P, const double *__restrict__ z, double alpha, double beta,
-                        const double *__restrict__ in, double *__restrict__ out) {
-  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= D.nv) return;
+SPK_D double spk_L_entry(const SpkDims &D, const SpkPtrs &P, const double *__restrict__ z, long e) {
   const int nx = D.nx, nu = D.nu, d = D.d;
   double val;
   if (e < D.vo[1]) {  // v1 :207-210
@@ -135,6 +136,13 @@ SPK_KERNEL void spk_k_L(SpkDims D, SpkPtrs P, const double *__restrict__ z, doub
   } else {  // v14 :311-317
     val = z[D.nnl * nx + (e - D.vo[10])];
   }
+  return val;
+}
+SPK_KERNEL void spk_k_L(SpkDims D, SpkPtrs P, const double *__restrict__ z, double alpha, double beta,
+                        const double *__restrict__ in, double *__restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.nv) return;
+  const double val = spk_L_entry(D, P, z, e);
   out[e] = (beta == 0.0) ? alpha * val : alpha * val + beta * in[e];
 }
 

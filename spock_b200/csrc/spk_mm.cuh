@@ -46,6 +46,7 @@ __global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
   constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
   constexpr int KX = L.KX, NBX = L.NBX, NBU = L.NBU, NBS = L.NBU + L.NBX;
   SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
   const double *fr = smem + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
   const int m = lane >> 2, kk = lane & 3;
@@ -86,8 +87,23 @@ __global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
     double acc1[NBU][2], acc3[NBX][2];
 #pragma unroll
     for (int nb = 0; nb < NBU; ++nb) acc1[nb][0] = acc1[nb][1] = 0.0;
+    // acc3 starts at -(z - gamma L'v) on x_i (:634-636 with L_transpose! :351-373): these loads are issued with the tile's
+    // first loads instead of sitting exposed behind the DMMA chain
 #pragma unroll
-    for (int nb = 0; nb < NBX; ++nb) acc3[nb][0] = acc3[nb][1] = 0.0;
+    for (int nb = 0; nb < NBX; ++nb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = 8 * nb + 2 * kk + i;
+        double val = 0.0;
+        if (n < NX) {
+          double lt = v[D.vo[6] + i0 * (NX + NU) + n];
+#pragma unroll
+          for (int c = 0; c < DD; ++c)
+            lt += P.sqrtQ[(ucq ? 0 : (cfirst - 1 + c) * NX) + n] * v[D.vo[2] + (cfirst - 1 + c) * NX + n];
+          val = gamma * lt - z[i0 * NX + n];
+        }
+        acc3[nb][i] = val;
+      }
 #pragma unroll
     for (int c = 0; c < DD; ++c) {
       double qa[KX];
@@ -153,21 +169,14 @@ __global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
           spk_dmma(acc3[nb][0], acc3[nb][1], a2, bk[nb * 32]);
         }
       }
-    // ---- q_i = ... - (z - gamma L'v) on x_i (:634-636 with L_transpose! :351-373)
+    // ---- q_i (:634-636)
+    if (valid) {
 #pragma unroll
-    for (int nb = 0; nb < NBX; ++nb)
+      for (int nb = 0; nb < NBX; ++nb)
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int n = 8 * nb + 2 * kk + i;
-        if (n < NX) {
-          double lt = v[D.vo[6] + i0 * (NX + NU) + n];
-#pragma unroll
-          for (int c = 0; c < DD; ++c)
-            lt += P.sqrtQ[(ucq ? 0 : (cfirst - 1 + c) * NX) + n] * v[D.vo[2] + (cfirst - 1 + c) * NX + n];
-          const double tx = z[i0 * NX + n] - gamma * lt;
-          if (valid) A.q[i0 * NX + n] = acc3[nb][i] - tx;
-        }
-      }
+        for (int i = 0; i < 2; ++i)
+          if (8 * nb + 2 * kk + i < NX) A.q[i0 * NX + 8 * nb + 2 * kk + i] = acc3[nb][i];
+    }
   }
   if (!waited) spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);  // never exit with a bulk copy in flight
 }
@@ -179,6 +188,7 @@ __global__ void spk_k_fwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
   constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
   constexpr int KX = L.KX, KU = L.KU, NBX = L.NBX, NBU = L.NBU;
   SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
   const double *fr = smem + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
   const int m = lane >> 2, kk = lane & 3;

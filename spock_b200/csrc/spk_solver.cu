@@ -13,6 +13,7 @@
 #include "spk_fused.cuh"
 #include "spk_kernels.cuh"
 #include "spk_offline.h"
+#include "spk_sp.cuh"
 
 #ifdef SPK_HOST_EMU
 thread_local spk_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -163,6 +164,19 @@ struct spk_handle {
 #ifndef SPK_HOST_EMU
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
   std::map<std::tuple<const void *, void *, double, double, int>, GraphEntry> graphs;
+#endif
+  // device-resident loop control (spk_sp.cuh): termination test, SuperMann / Anderson scalars, per-pass log
+  SpkCtl *d_ctl = nullptr;
+  SpkCtl h_ctl;
+  bool dev_loop = false;         // CP and SP loops run without a host synchronisation per pass
+  int sp_rot = 0;                // rotations of the Anderson column slots so far (logical column j = slot (j + 2 rot) % 3)
+  double *d_log = nullptr, *d_sp_partial = nullptr;
+  unsigned *d_ticket = nullptr;
+  int log_cap = 0;
+#ifndef SPK_HOST_EMU
+  cudaGraphExec_t sp_graph = nullptr;
+  double sp_graph_gamma = 0, sp_graph_sigma = 0;
+  int64_t sp_graph_kernels = 0;
 #endif
   // reductions
   double *d_partial = nullptr, *d_scal = nullptr;
@@ -580,6 +594,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   A.z = zv_in; A.v = zv_in + D.nz; A.zbar = zv_out; A.vbar = zv_out + D.nz;
   A.q = h->ric_q; A.dd = h->ric_d; A.xi = h->d_scal; A.pnorm = pnorm_slot >= 0 ? h->d_pnorm : nullptr;
   A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0; A.p_lo = 0; A.p_cnt = 0;
+  A.gate = h->d_ctl ? &h->d_ctl->done : nullptr;
   fill_ranges(h, A);
   const long owned = A.r_prefix[A.n_ranges];
   std::string cerr;
@@ -895,6 +910,123 @@ static void default_steps(const spk_handle *h, double &gamma, double &sigma) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ device-resident loops
+// (spk_sp.cuh) The loop scalars live in SpkCtl on the device; the host launches passes in batches and polls `done`.
+
+static int ctl_begin(spk_handle *h, double tol, int verbose_log, int ignore_done) {
+  SpkCtl &c = h->h_ctl;
+  memset(&c, 0, sizeof(c));
+  c.tol = tol;
+  c.res0[0] = h->res_0[0]; c.res0[1] = h->res_0[1];
+  c.xi1 = c.xi2 = NAN;
+  c.ignore_done = ignore_done; c.verbose_log = verbose_log; c.log_cap = h->log_cap;
+  for (int k = 0; k < AA_M * AA_M; ++k) c.R[k] = h->aaR[k];
+  c.r_safe = INFINITY;  // sp.jl:373
+  c.rot = h->sp_rot;
+  return rt_h2d(h->d_ctl, &c, sizeof(SpkCtl), h->stream);
+}
+static int ctl_poll(spk_handle *h) { return rt_d2h(&h->h_ctl, h->d_ctl, sizeof(SpkCtl), h->stream); }
+static void ctl_end(spk_handle *h) {
+  const SpkCtl &c = h->h_ctl;
+  for (int k = 0; k < AA_M * AA_M; ++k) h->aaR[k] = c.R[k];
+  h->sp_rot = c.rot % 3;
+  h->res_0[0] = c.res0[0]; h->res_0[1] = c.res0[1];
+  h->last_xi1 = c.xi1; h->last_xi2 = c.xi2;
+}
+
+#ifndef SPK_HOST_EMU
+static unsigned vec_grid(const spk_handle *h, long n) {
+  long g = (n + SPK_SP_THREADS - 1) / SPK_SP_THREADS;
+  return (unsigned)std::max(1L, std::min(g, (long)h->red_blocks));
+}
+// should_terminate! on the device for one finished pass (CP: xi1, xi2 come out of the dual kernel in d_scal[0..1])
+static int launch_terminate(spk_handle *h, int xi_slot, int is_sp) {
+  if (h->world > 1) {
+    std::string cerr;
+    if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+  }
+  spk_k_terminate<<<1, 1, 0, h->stream>>>(h->d_ctl, h->d_scal, xi_slot, is_sp, h->d_log);
+  COUNT_LAUNCH(h, PC_VEC);
+  return rt_launch_check();
+}
+
+// one pass of run_sp! (sp.jl:388-463) as a fixed launch sequence without any host decision
+static int sp_pass_device_launch(spk_handle *h, double gamma, double sigma) {
+  const SpkDims &D = h->D;
+  const long nz = D.nz, nv = D.nv, nr = nz + nv;
+  SpkSpVecs V;
+  V.zv = h->zv; V.zvbar = h->zvbar; V.zv_old = h->zv_old; V.dzv = h->dzv; V.rzv = h->rzv; V.rzv_old = h->rzv_old;
+  V.dir = h->dir; V.wu = h->wu; V.wubar = h->wubar; V.rwu = h->rwu; V.ws_rho = h->ws_rho;
+  for (int j = 0; j < AA_M; ++j) { V.MP[j] = h->MP[j]; V.MR[j] = h->MR[j]; V.AQ[j] = h->AQ[j]; }
+  SpkCtl *c = h->d_ctl;
+  double *scal = h->d_scal, *part = h->d_sp_partial;
+  unsigned *tick = h->d_ticket;
+  const unsigned g = vec_grid(h, nr), gz = vec_grid(h, nz), gv = vec_grid(h, nv);
+  const int T = SPK_SP_THREADS;
+  SPK_TRY(op_T_fused_launch(h, h->zv, h->zvbar, gamma, sigma, 4));                       // :389-390 and <r, P r>
+  {
+    ProfScope ps(h, PC_VEC);
+    spk_k_sp_a<<<g, T, 0, h->stream>>>(nr, V, c, scal, part, tick);
+    spk_k_sp_b<<<g, T, 0, h->stream>>>(nr, V, c, part, tick);
+    spk_k_sp_c<<<g, T, 0, h->stream>>>(nr, V, c, part, tick);
+    spk_k_sp_d<<<g, T, 0, h->stream>>>(nr, V, c, part, tick);
+    spk_k_sp_e<<<g, T, 0, h->stream>>>(nr, V, c);
+    for (int k = 0; k < 5; ++k) COUNT_LAUNCH(h, PC_VEC);
+  }
+  SPK_TRY(op_T_fused_launch(h, h->wu, h->wubar, gamma, sigma, 5));                       // :133-164
+  {
+    ProfScope ps(h, PC_VEC);
+    spk_k_sp_f_decide<<<1, 1, 0, h->stream>>>(c, scal);
+    spk_k_sp_f<<<g, T, 0, h->stream>>>(nr, V, c);
+    // K2: rho = <r~, P (r~ - d)> (spock_dot :485-516), only when K1 failed
+    spk_k_Lop_ctl<true><<<gz, T, 0, h->stream>>>(D, h->P, h->ws_rho + nz, -gamma, 1.0, h->ws_rho, nullptr, h->rwu, scal + 6, 0, nullptr,
+                                                  c, &c->need_k2, part, tick);
+    spk_k_Lop_ctl<false><<<gv, T, 0, h->stream>>>(D, h->P, h->ws_rho, -sigma, 1.0, h->ws_rho + nz, nullptr, h->rwu + nz, scal + 6, 1,
+                                                   nullptr, c, &c->need_k2, part, tick);
+    spk_k_sp_g_decide<<<1, 1, 0, h->stream>>>(c, scal);
+    spk_k_sp_g<<<g, T, 0, h->stream>>>(nr, V, c);
+    // should_terminate! (sp.jl:270-344): xi1 = ||L'dv - dz/gamma||_inf, xi2 = ||L dz - dv/sigma||_inf
+    spk_k_Lop_ctl<true><<<gz, T, 0, h->stream>>>(D, h->P, h->dzv + nz, 1.0, -1.0 / gamma, h->dzv, nullptr, nullptr, nullptr, 0, scal + 10,
+                                                  c, nullptr, part, tick);
+    spk_k_Lop_ctl<false><<<gv, T, 0, h->stream>>>(D, h->P, h->dzv, 1.0, -1.0 / sigma, h->dzv + nz, nullptr, nullptr, nullptr, 0, scal + 11,
+                                                   c, nullptr, part, tick);
+    for (int k = 0; k < 8; ++k) COUNT_LAUNCH(h, PC_VEC);
+  }
+  return launch_terminate(h, 10, 1);
+}
+static int sp_pass_device(spk_handle *h, double gamma, double sigma) {
+  if (h->use_graphs && !h->prof_on) {
+    if (h->sp_graph && (h->sp_graph_gamma != gamma || h->sp_graph_sigma != sigma)) {
+      cudaGraphExecDestroy(h->sp_graph);
+      h->sp_graph = nullptr;
+    }
+    if (!h->sp_graph) {
+      const int64_t l0 = h->launches;
+      RT_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = sp_pass_device_launch(h, gamma, sigma);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (rc != SPK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+      h->sp_graph_kernels = h->launches - l0;
+      h->launches = l0;
+      const cudaError_t ie = cudaGraphInstantiate(&h->sp_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+      h->sp_graph_gamma = gamma; h->sp_graph_sigma = sigma;
+    }
+    RT_CHECK(cudaGraphLaunch(h->sp_graph, h->stream));
+    h->launches += h->sp_graph_kernels;
+    return SPK_OK;
+  }
+  return sp_pass_device_launch(h, gamma, sigma);
+}
+#endif
+
+// passes per host poll: large problems are polled every pass (a pass is milliseconds), small ones every 8 passes
+static int poll_batch(const spk_handle *h) { return (h->D.nz + h->D.nv) > (1L << 21) ? 1 : 8; }
+
 // ------------------------------------------------------------------------------------------------ C ABI
 
 static int check_problem(const spk_problem *p) {
@@ -951,6 +1083,7 @@ int spk_destroy(spk_handle *h) {
   for (void *p : h->allocs) rt_free(p);
 #ifndef SPK_HOST_EMU
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->sp_graph) cudaGraphExecDestroy(h->sp_graph);
   for (auto &s : h->prof_open) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -1060,6 +1193,16 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(dev_alloc(h, &h->d_partial, h->red_blocks));
   SPK_TRY(dev_alloc(h, &h->d_scal, 32));
   SPK_TRY(dev_alloc(h, &h->d_pnorm, nnl + 64));
+  {
+    double *ctl_mem = nullptr, *tick = nullptr;
+    SPK_TRY(dev_alloc(h, &ctl_mem, (long)(sizeof(SpkCtl) / sizeof(double)) + 2));
+    h->d_ctl = reinterpret_cast<SpkCtl *>(ctl_mem);
+    SPK_TRY(dev_alloc(h, &tick, 2));
+    h->d_ticket = reinterpret_cast<unsigned *>(tick);
+    SPK_TRY(dev_alloc(h, &h->d_sp_partial, (long)h->red_blocks * 4));
+    h->log_cap = 5000;
+    SPK_TRY(dev_alloc(h, &h->d_log, 3L * h->log_cap));
+  }
   SPK_TRY(fused_setup(h));
   h->rank = p->rank; h->world = p->world_size > 1 ? p->world_size : 1;
   if (h->world > 1) {
@@ -1074,6 +1217,10 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
     if (!h->comm.init(h->rank, h->world, p->comm_id, cerr)) return fail(SPK_ERR_COMM, cerr);
   }
   h->res_0[0] = h->res_0[1] = -INFINITY;
+  {
+    const char *nd = getenv("SPK_HOST_LOOP");
+    h->dev_loop = !SPK_EMU && h->fused_ok && !(nd && nd[0] == '1') && (h->alg == SPK_CP || h->world == 1);
+  }
   if (h->alg == SPK_SP) {  // spock.jl:160-202
     SPK_TRY(dev_alloc(h, &h->rzv, nr));
     SPK_TRY(dev_alloc(h, &h->rzv_old, nr));
@@ -1278,7 +1425,23 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   LoopState S;
   default_steps(h, gamma, sigma);
   S.gamma = gamma; S.sigma = sigma; S.tol = 0.0; S.verbose_log = 0;
+  SPK_TRY(ctl_begin(h, 0.0, 0, 1));  // also clears the device-side `done` flag that gates the fused kernels
   LoopTimer timer(h);
+#ifndef SPK_HOST_EMU
+  if (h->dev_loop && h->alg == SPK_SP) {  // SuperMann without host decisions (spk_sp.cuh)
+    for (int k = 0; k < K; ++k) {
+      SPK_TRY(sp_pass_device(h, gamma, sigma));
+      if (h->prof_on && h->prof_open.size() > 8192) prof_harvest(h);
+    }
+    SPK_TRY(ctl_poll(h));
+    const double r0a = h->res_0[0], r0b = h->res_0[1];
+    ctl_end(h);
+    h->res_0[0] = r0a; h->res_0[1] = r0b;  // spk_step leaves solve_model!'s res_0 alone
+    const float t = timer.stop();
+    if (ms) *ms = t;
+    return SPK_OK;
+  }
+#endif
   for (int k = 0; k < K; ++k) {
     S.iter = k;
     int bc = 0;
@@ -1306,9 +1469,10 @@ static void state_blocks(spk_handle *h, std::vector<double *> &blocks) {
   if (h->alg == SPK_SP) {
     blocks.push_back(h->rzv_old);
     blocks.push_back(h->dzv);
-    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->MP[j]);
-    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->MR[j]);
-    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->AQ[j]);
+    // logical column j lives in slot (j + 2 rot) % 3 (device loop); the host-driven loop rotates the pointers, rot = 0
+    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->MP[(j + 2 * h->sp_rot) % 3]);
+    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->MR[(j + 2 * h->sp_rot) % 3]);
+    for (int j = 0; j < AA_M; ++j) blocks.push_back(h->AQ[(j + 2 * h->sp_rot) % 3]);
   }
 }
 int spk_get_state(spk_handle *h, double *state) {
@@ -1398,7 +1562,57 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
   if (max_iter <= 0) max_iter = (h->alg == SPK_SP) ? 1000 : 5000;  // sp.jl:360 / cp.jl:190
   int iter = 0, passes = 0, converged = 0;
   double xi = NAN, xi1 = NAN, xi2 = NAN;
+  SPK_TRY(ctl_begin(h, tol, verbose_log, 0));
   LoopTimer timer(h);
+#ifndef SPK_HOST_EMU
+  // Device-resident loop: CP (SILENT; LOG needs the xi vector, cp.jl:82-86) and SP (both modes, sp.jl:304)
+  if (h->dev_loop && (h->alg == SPK_SP || !verbose_log)) {
+    const int batch = poll_batch(h);
+    int launched = 0;
+    while (launched < max_iter) {
+      const int nb = std::min(batch, max_iter - launched);
+      for (int b = 0; b < nb; ++b, ++launched) {
+        if (h->alg == SPK_SP) {
+          SPK_TRY(sp_pass_device(h, gamma, sigma));
+        } else {
+          SPK_TRY(cp_pass_launch(h, S));
+          SPK_TRY(launch_terminate(h, 0, 0));
+        }
+        if (h->prof_on && h->prof_open.size() > 8192) prof_harvest(h);
+      }
+      SPK_TRY(ctl_poll(h));
+      if (h->h_ctl.done) break;
+    }
+    const SpkCtl &c = h->h_ctl;
+    passes = c.passes;
+    converged = c.done ? 1 : 0;
+    iter = converged ? passes - 1 : passes;
+    if (h->alg == SPK_CP && ((launched - passes) & 1)) std::swap(h->zv, h->zvbar);  // gated passes did not move the iterate
+    ctl_end(h);
+    xi1 = c.xi1; xi2 = c.xi2;
+    xi = verbose_log ? std::max(xi1, xi2) : NAN;
+    S.k1 = c.k1; S.k2 = c.k2; S.fb = c.fb;
+    const float ms = timer.stop();
+    if ((log_xi || log_xi1 || log_xi2 || log_bc) && passes > 0) {
+      const int cnt = std::min(std::min(passes, (int)log_cap), h->log_cap);
+      std::vector<double> lg((size_t)3 * cnt);
+      if (cnt > 0) SPK_TRY(rt_d2h(lg.data(), h->d_log, sizeof(double) * 3 * cnt, h->stream));
+      for (int k = 0; k < cnt; ++k) {
+        if (log_xi) log_xi[k] = verbose_log ? std::max(lg[3 * k], lg[3 * k + 1]) : NAN;
+        if (log_xi1) log_xi1[k] = lg[3 * k];
+        if (log_xi2) log_xi2[k] = lg[3 * k + 1];
+        if (log_bc) log_bc[k] = (int32_t)lg[3 * k + 2];
+      }
+    }
+    if (result) {
+      result->passes = passes; result->printed_iter = iter; result->converged = converged;
+      result->xi1 = xi1; result->xi2 = xi2; result->xi = xi;
+      result->k1_count = S.k1; result->k2_count = S.k2; result->fallback_count = S.fb;
+      result->solve_ms = ms;
+    }
+    return SPK_OK;
+  }
+#endif
   while (iter < max_iter) {
     int bc = 0;
     S.iter = iter;
@@ -1453,6 +1667,7 @@ int spk_comm_unique_id(uint8_t id[128]) {
 int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int64_t *count) {
   if (!h || !n_ranges) return fail(SPK_ERR_INVALID, "NULL argument");
   SpkFusedArgs A;
+  A.gate = nullptr;
   fill_ranges(h, A);
   *n_ranges = A.n_ranges;
   for (int k = 0; k < A.n_ranges; ++k) {

@@ -340,3 +340,44 @@ def test_power_iteration_L_norm(cuda_lib):
     res, _ = hh.solve(0.1 * np.ones(5), tol=1e-3)  # converges with the estimated (larger) step sizes
     assert res["converged"] == 1
     hh.close()
+
+
+@pytest.mark.parametrize("alg,verbose_log", [(CP, False), (SP, False), (SP, True)])
+@pytest.mark.parametrize("name", ["heat_N7_d2_nx5", "l2ball_N4_d3_nx3", "random_N5_d2_nx6_nu3"])
+def test_device_resident_loop_equals_host_driven_loop(cuda_lib, alg, verbose_log, name, monkeypatch):
+    """solve_model! with the loop scalars on the device (termination test, Anderson / SuperMann decisions, polled every
+    8 passes) against the host-driven loop (one synchronisation per decision): same stopping pass, same per-pass log,
+    same branch counts, iterate within rounding; and a warm-started second solve from the persisted state."""
+    flat = flat_of(name)
+    x0 = 0.1 * np.ones(flat.nx)
+    out = []
+    for host_loop in ("1", "0"):
+        monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
+        h = Handle(flat, alg, factor_mode=1, lib=cuda_lib)
+        r1, log1 = h.solve(x0, tol=1e-4, verbose_log=verbose_log)
+        z1, v1 = h.get_iterate()
+        r2, log2 = h.solve(0.9 * x0, tol=1e-4, verbose_log=verbose_log)  # warm start (cpock.jl:180-186)
+        z2, v2 = h.get_iterate()
+        out.append((r1, log1, z1, v1, r2, log2, z2, v2))
+        h.close()
+    (a1, la1, za1, va1, a2, la2, za2, va2), (b1, lb1, zb1, vb1, b2, lb2, zb2, vb2) = out
+    if alg == CP:  # deterministic contraction: identical stopping pass, log and iterate
+        for ra, rb in ((a1, b1), (a2, b2)):
+            assert ra["passes"] == rb["passes"] and ra["converged"] == rb["converged"] == 1 and ra["printed_iter"] == rb["printed_iter"]
+            assert abs(ra["xi1"] - rb["xi1"]) <= 1e-9 * abs(ra["xi1"])
+        for la, lb in ((la1, lb1), (la2, lb2)):
+            assert np.allclose(la["xi1"], lb["xi1"], rtol=1e-9, atol=0) and np.allclose(la["xi2"], lb["xi2"], rtol=1e-9, atol=0)
+        assert relerr(zb1, za1) < 1e-11 and relerr(vb1, va1) < 1e-11 and relerr(zb2, za2) < 1e-11 and relerr(vb2, va2) < 1e-11
+    else:
+        # SuperMann + Anderson amplify rounding differences of the reductions chaotically (DESIGN.md section 5): the two loops
+        # are compared pass by pass over the first 25 passes; both must converge to the solver tolerance
+        for ra, rb in ((a1, b1), (a2, b2)):
+            assert ra["converged"] == rb["converged"] == 1
+            assert ra["k1_count"] + ra["k2_count"] + ra["fallback_count"] == ra["passes"]
+            assert rb["k1_count"] + rb["k2_count"] + rb["fallback_count"] == rb["passes"]
+        k = min(25, len(la1["xi1"]), len(lb1["xi1"]))
+        assert np.array_equal(la1["backtrack_count"][:k], lb1["backtrack_count"][:k])
+        assert np.allclose(la1["xi1"][:k], lb1["xi1"][:k], rtol=1e-7, atol=0) and np.allclose(la1["xi2"][:k], lb1["xi2"][:k], rtol=1e-7, atol=0)
+        if verbose_log:
+            assert np.allclose(la1["xi"][:k], lb1["xi"][:k], rtol=1e-7, atol=0)
+            assert la1["xi"][-1] <= 1e-4 and lb1["xi"][-1] <= 1e-4 and la2["xi"][-1] <= 1e-4 and lb2["xi"][-1] <= 1e-4
