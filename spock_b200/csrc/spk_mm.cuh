@@ -40,27 +40,19 @@ SPK_D void spk_mm_fetch(double *smem, const double *frag_g, int frags, int tid) 
 }
 
 // ------------------------------------------------------------------------------------------------ backward level
+// One tile (8 consecutive families starting at position 8*tile of the level whose first node is first0) of the
+// backward step.  fr: the level's fragments in shared memory, complete once `bar` has flipped past `phase`.
 template <int NX, int NU, int DD, bool LEAVES>
-__launch_bounds__(256, spk_mm_minb(spk_mm_layout(NX, NU, DD).bwd_frags))
-__global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_g) {
+__device__ __forceinline__ void spk_bwd_mm_tile(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &A, const double *fr,
+                                                uint64_t *bar, uint32_t phase, bool &waited, long first0, long count, long tile,
+                                                int lane) {
   constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
   constexpr int KX = L.KX, NBX = L.NBX, NBU = L.NBU, NBS = L.NBU + L.NBX;
-  SPK_SMEM_DECL(double, smem);
-  if (A.gate && *A.gate) return;
-  const double *fr = smem + 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
   const int m = lane >> 2, kk = lane & 3;
-  const long count = A.p_cnt, first0 = spk_level_first0(DD, A.t) + A.p_lo, ntiles = (count + 7) / 8;
-  if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
-    A.xi[0] = 0.0;
-    A.xi[1] = 0.0;
-  }
-  spk_mm_fetch(smem, frag_g, L.bwd_frags, tid);
-  bool waited = false;
   const double gamma = A.gamma;
   const double *__restrict__ z = A.z, *__restrict__ v = A.v;
   const bool ucq = D.n_sqrtQ == 1, ucn = D.n_sqrtQN == 1;
-  for (long tile = (long)blockIdx.x * wpb + warp; tile < ntiles; tile += (long)gridDim.x * wpb) {
+  {
     long fm = tile * 8 + m;
     const bool valid = fm < count;
     if (!valid) fm = count - 1;  // trailing rows of the last tile recompute the last family; their stores are dropped
@@ -123,7 +115,7 @@ __global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
         qa[s] = a;
       }
       if (!waited) {
-        spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);
+        spk_mbar_wait(bar, phase);
         waited = true;
       }
 #pragma unroll
@@ -178,25 +170,37 @@ __global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
           if (8 * nb + 2 * kk + i < NX) A.q[i0 * NX + 8 * nb + 2 * kk + i] = acc3[nb][i];
     }
   }
-  if (!waited) spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);  // never exit with a bulk copy in flight
+}
+
+template <int NX, int NU, int DD, bool LEAVES>
+__launch_bounds__(256, spk_mm_minb(spk_mm_layout(NX, NU, DD).bwd_frags))
+__global__ void spk_k_bwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_g) {
+  constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
+  const long count = A.p_cnt, first0 = spk_level_first0(DD, A.t) + A.p_lo, ntiles = (count + 7) / 8;
+  if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
+    A.xi[0] = 0.0;
+    A.xi[1] = 0.0;
+  }
+  spk_mm_fetch(smem, frag_g, L.bwd_frags, tid);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  bool waited = false;
+  for (long tile = (long)blockIdx.x * wpb + warp; tile < ntiles; tile += (long)gridDim.x * wpb)
+    spk_bwd_mm_tile<NX, NU, DD, LEAVES>(D, P, A, smem + 2, bar, 0, waited, first0, count, tile, lane);
+  if (!waited) spk_mbar_wait(bar, 0);  // never exit with a bulk copy in flight
 }
 
 // ------------------------------------------------------------------------------------------------ forward level
 template <int NX, int NU, int DD>
-__launch_bounds__(256, spk_mm_minb(spk_mm_layout(NX, NU, DD).fwd_frags))
-__global__ void spk_k_fwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_g) {
+__device__ __forceinline__ void spk_fwd_mm_tile(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &A, const double *fr,
+                                                uint64_t *bar, uint32_t phase, bool &waited, long first0, long count, long tile,
+                                                int lane, bool root) {
   constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
   constexpr int KX = L.KX, KU = L.KU, NBX = L.NBX, NBU = L.NBU;
-  SPK_SMEM_DECL(double, smem);
-  if (A.gate && *A.gate) return;
-  const double *fr = smem + 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
   const int m = lane >> 2, kk = lane & 3;
-  const long count = A.p_cnt, first0 = spk_level_first0(DD, A.t) + A.p_lo, ntiles = (count + 7) / 8;
-  spk_mm_fetch(smem, frag_g, L.fwd_frags, tid);
-  bool waited = false;
-  const bool root = A.t == 0;
-  for (long tile = (long)blockIdx.x * wpb + warp; tile < ntiles; tile += (long)gridDim.x * wpb) {
+  {
     long fm = tile * 8 + m;
     const bool valid = fm < count;
     if (!valid) fm = count - 1;
@@ -226,7 +230,7 @@ __global__ void spk_k_fwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
         if (4 * s + kk < NX) A.zbar[4 * s + kk] = xa[s];
     }
     if (!waited) {
-      spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);
+      spk_mbar_wait(bar, phase);
       waited = true;
     }
     // ---- u_i = K x_i + d_i (:670-673)
@@ -270,6 +274,69 @@ __global__ void spk_k_fwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double 
       }
     }
   }
-  if (!waited) spk_mbar_wait(reinterpret_cast<uint64_t *>(smem), 0);
+}
+
+template <int NX, int NU, int DD>
+__launch_bounds__(256, spk_mm_minb(spk_mm_layout(NX, NU, DD).fwd_frags))
+__global__ void spk_k_fwd_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_g) {
+  constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = blockDim.x >> 5;
+  const long count = A.p_cnt, first0 = spk_level_first0(DD, A.t) + A.p_lo, ntiles = (count + 7) / 8;
+  spk_mm_fetch(smem, frag_g, L.fwd_frags, tid);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  bool waited = false;
+  for (long tile = (long)blockIdx.x * wpb + warp; tile < ntiles; tile += (long)gridDim.x * wpb)
+    spk_fwd_mm_tile<NX, NU, DD>(D, P, A, smem + 2, bar, 0, waited, first0, count, tile, lane, A.t == 0);
+  if (!waited) spk_mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ top of the tree
+// Levels t_top .. 0 of the backward sweep and 0 .. t_top of the forward sweep (at most 64 families each, one tile per
+// warp) in ONE launch of a single CTA: a level of a small tree is far below the fixed cost of a kernel (launch, cold
+// instruction cache of the unrolled DMMA chain, fragment fetch), which is what bounds every latency-bound configuration
+// (MPC, scaling sweep).  Between levels: __syncthreads (the level's q / x are visible to the CTA) and a TMA
+// refill of the fragment buffer with the next level's weights.
+SPK_CONSTEXPR_HD int spk_mm_top_frags(int nx, int nu, int d) {
+  return spk_mm_layout(nx, nu, d).bwd_frags > spk_mm_layout(nx, nu, d).fwd_frags ? spk_mm_layout(nx, nu, d).bwd_frags
+                                                                                 : spk_mm_layout(nx, nu, d).fwd_frags;
+}
+template <int NX, int NU, int DD>
+__launch_bounds__(256, 1)
+__global__ void spk_k_top_mm(SpkDims D, SpkPtrs P, SpkFusedArgs A, const double *__restrict__ frag_bwd, const double *__restrict__ frag_fwd,
+                             int t_top) {
+  constexpr SpkMmLayout L = spk_mm_layout(NX, NU, DD);
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  if (tid == 0) spk_mbar_init(bar, 1);
+  uint32_t phase = 0;
+  for (int pass = 0; pass < 2; ++pass) {  // 0: backward levels t_top .. 0, 1: forward levels 0 .. t_top
+    for (int step = 0; step <= t_top; ++step) {
+      const int t = pass == 0 ? t_top - step : step;
+      const int frags = pass == 0 ? L.bwd_frags : L.fwd_frags;
+      const double *src = (pass == 0 ? frag_bwd : frag_fwd) + (size_t)t * frags * 32;
+      __syncthreads();  // the previous level's results are visible; nobody reads the fragment buffer any more
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t total = (uint32_t)frags * 256u;
+        spk_mbar_expect_tx(bar, total);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+          const uint32_t sz = total - off < 32768u ? total - off : 32768u;
+          spk_bulk_g2s(reinterpret_cast<char *>(smem + 2) + off, reinterpret_cast<const char *>(src) + off, sz, bar);
+        }
+      }
+      const long count = spk_level_count(DD, t), first0 = spk_level_first0(DD, t);
+      bool waited = false;
+      if ((long)warp * 8 < count) {
+        if (pass == 0) spk_bwd_mm_tile<NX, NU, DD, false>(D, P, A, smem + 2, bar, phase, waited, first0, count, warp, lane);
+        else spk_fwd_mm_tile<NX, NU, DD>(D, P, A, smem + 2, bar, phase, waited, first0, count, warp, lane, t == 0);
+      }
+      if (!waited) spk_mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+  }
 }
 #endif

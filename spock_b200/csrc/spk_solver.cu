@@ -149,6 +149,8 @@ struct spk_handle {
   bool use_mm = false;
   void (*k_bwd_mm[2])(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = {nullptr, nullptr};
   void (*k_fwd_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = nullptr;
+  void (*k_top_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *, const double *, int) = nullptr;
+  int t_top = -1;  // levels 0 .. t_top of both sweeps run in the single-CTA top-of-tree kernel (-1: none)
   double *d_frag_bwd = nullptr, *d_frag_fwd = nullptr;
   long mm_bwd_frags = 0, mm_fwd_frags = 0;
   int occ_bwd_mm = 1, occ_fwd_mm = 1;
@@ -508,7 +510,7 @@ static int fused_setup(spk_handle *h) {
         }
         const char *emm = getenv("SPK_NO_MM");
         if (!D.per_node && !D.cost_dense && !(emm && emm[0] == '1')) {
-          h->k_bwd_mm[0] = e.bwd_mm[0]; h->k_bwd_mm[1] = e.bwd_mm[1]; h->k_fwd_mm = e.fwd_mm;
+          h->k_bwd_mm[0] = e.bwd_mm[0]; h->k_bwd_mm[1] = e.bwd_mm[1]; h->k_fwd_mm = e.fwd_mm; h->k_top_mm = e.top_mm;
           h->use_mm = true;
         }
       }
@@ -567,6 +569,11 @@ static int fused_setup(spk_handle *h) {
       RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd_mm, (const void *)h->k_fwd_mm, 256, sf));
       h->occ_bwd_mm = std::max(1, h->occ_bwd_mm);
       h->occ_fwd_mm = std::max(1, h->occ_fwd_mm);
+      RT_CHECK(cudaFuncSetAttribute((const void *)h->k_top_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sb, sf)));
+      const char *nt = getenv("SPK_NO_TOP");
+      h->t_top = -1;
+      if (!(nt && nt[0] == '1'))
+        for (int t = 0; t <= D.N - 3 && spk_level_count(D.d, t) <= 64; ++t) h->t_top = t;  // never the leaf-parent level
     }
   }
   h->occ_fwd = std::max(1, h->occ_fwd);
@@ -604,16 +611,22 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     SPK_LAUNCH(spk_k_s2t, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_S2);
   }
-  for (int t = D.N - 2; t >= 0; --t) {  // 1. backward sweep
+  // levels 0 .. t_top of both sweeps run in one single-CTA launch (single GPU, tensor-pipe kernels)
+  const int t_top = (h->use_mm && h->world == 1) ? h->t_top : -1;
+  for (int t = D.N - 2; t > t_top; --t) {  // 1. backward sweep
     {
       ProfScope ps(h, PC_FUSED_BWD);
       A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
       level_range(h, t, A.p_lo, A.p_cnt);
 #ifndef SPK_HOST_EMU
       if (h->use_mm) {  // per-stage factors: the level is a chain of mat-mats on the fp64 tensor pipe
-        const long ctas = std::min(((A.p_cnt + 7) / 8 + 7) / 8, (long)h->num_sms * h->occ_bwd_mm);
+        // small levels: fewer warps (tiles) per CTA so that the tiles spread over the SMs (a DMMA chain is bound by
+        // the tensor pipe of its SM sub-partition)
+        const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_bwd_mm;
+        const long wpb = std::min(8L, std::max(1L, (tiles + cap - 1) / cap));
+        const long ctas = std::min((tiles + wpb - 1) / wpb, cap);
         spk_mm_kernel_t kmm = h->k_bwd_mm[A.children_are_leaves ? 1 : 0];
-        kmm<<<(unsigned)std::max(1L, ctas), 256, spk_mm_smem_bytes((int)h->mm_bwd_frags), h->stream>>>(
+        kmm<<<(unsigned)std::max(1L, ctas), (unsigned)(32 * wpb), spk_mm_smem_bytes((int)h->mm_bwd_frags), h->stream>>>(
             D, h->P, A, h->d_frag_bwd + (size_t)t * h->mm_bwd_frags * 32);
       } else
 #endif
@@ -630,14 +643,25 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     }
   }
   A.reset_xi = 0;
-  for (int t = 0; t <= D.N - 2; ++t) {  // 2. forward sweep
+#ifndef SPK_HOST_EMU
+  if (t_top >= 0) {
+    ProfScope ps(h, PC_FUSED_BWD);
+    A.t = 0; A.children_are_leaves = 0; A.p_lo = 0; A.p_cnt = 1;
+    h->k_top_mm<<<1, 256, spk_mm_smem_bytes((int)std::max(h->mm_bwd_frags, h->mm_fwd_frags)), h->stream>>>(
+        D, h->P, A, h->d_frag_bwd, h->d_frag_fwd, t_top);
+    COUNT_LAUNCH(h, PC_FUSED_BWD);
+  }
+#endif
+  for (int t = t_top + 1; t <= D.N - 2; ++t) {  // 2. forward sweep
     ProfScope ps(h, PC_FUSED_FWD);
     A.t = t; A.children_are_leaves = (t == D.N - 2);
     level_range(h, t, A.p_lo, A.p_cnt);
 #ifndef SPK_HOST_EMU
     if (h->use_mm) {
-      const long ctas = std::min(((A.p_cnt + 7) / 8 + 7) / 8, (long)h->num_sms * h->occ_fwd_mm);
-      h->k_fwd_mm<<<(unsigned)std::max(1L, ctas), 256, spk_mm_smem_bytes((int)h->mm_fwd_frags), h->stream>>>(
+      const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_fwd_mm;
+      const long wpb = std::min(8L, std::max(1L, (tiles + cap - 1) / cap));
+      const long ctas = std::min((tiles + wpb - 1) / wpb, cap);
+      h->k_fwd_mm<<<(unsigned)std::max(1L, ctas), (unsigned)(32 * wpb), spk_mm_smem_bytes((int)h->mm_fwd_frags), h->stream>>>(
           D, h->P, A, h->d_frag_fwd + (size_t)t * h->mm_fwd_frags * 32);
     } else
 #endif

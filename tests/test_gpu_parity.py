@@ -279,8 +279,9 @@ def test_tensor_pipe_sweeps_equal_family_kernels(cuda_lib, nx, nu, d, N, monkeyp
     flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
     rng = np.random.default_rng(17)
     out = []
-    for no_mm in ("1", "0"):
+    for no_mm, no_top in (("1", "0"), ("0", "0"), ("0", "1")):
         monkeypatch.setenv("SPK_NO_MM", no_mm)
+        monkeypatch.setenv("SPK_NO_TOP", no_top)
         h = Handle(flat, CP, factor_mode=1, lib=cuda_lib)
         if not out:
             z0, v0, x0 = rng.standard_normal(h.nz), rng.standard_normal(h.nv), rng.standard_normal(nx)
@@ -289,7 +290,9 @@ def test_tensor_pipe_sweeps_equal_family_kernels(cuda_lib, nx, nu, d, N, monkeyp
         h.step(4)
         out.append(h.get_iterate() + (h.residuals(),))
         h.close()
-    (zf, vf, xf), (zm, vm, xm) = out
+    (zf, vf, xf), (zm, vm, xm), (zl, vl, xl) = out
+    # the single-CTA top-of-tree kernel does the same arithmetic per tile as the per-level launches
+    assert np.array_equal(zm, zl) and np.array_equal(vm, vl) and xm == xl
     assert relerr(zm, zf) < 1e-12 and relerr(vm, vf) < 1e-12
     assert abs(xm[0] - xf[0]) < 1e-10 * xf[0] and abs(xm[1] - xf[1]) < 1e-10 * xf[1]
     o = Oracle(flat, CP)
