@@ -123,6 +123,7 @@ struct SpkFusedArgs {
   double *xi;              // xi[0] = xi1, xi[1] = xi2 (atomic max; reset by the first backward launch of the pass)
   double *pnorm;           // per-family partial of <r, P r> (nnl doubles), or NULL
   int reset_xi;            // this launch zeroes xi[0..1] (block 0)
+  int vec2;                // tensor-pipe kernels: every pair of consecutive entries they touch is 16-byte aligned
   const int *gate;         // device-side "done" flag of the loop (spk_sp.cuh): every kernel returns at once when it is set
   // ownership (multi-GPU subtree partition; a single GPU owns everything):
   long p_lo, p_cnt;        // kernels 1, 2: positions [p_lo, p_lo + p_cnt) of level t are processed by this rank

@@ -24,6 +24,42 @@ SPK_D void spk_dmma(double &c0, double &c1, double a, double b) {
 SPK_CONSTEXPR_HD int spk_mm_minb(int frags) { return frags * 256 > 110 * 1024 ? 1 : 2; }
 SPK_CONSTEXPR_HD size_t spk_mm_smem_bytes(int frags) { return 16 + (size_t)frags * 256; }
 
+// Two consecutive entries p[n0], p[n0 + 1] (zero beyond nlim).  vec2: every such pair of this launch is 16-byte aligned
+// (host-checked: even sizes and segment offsets), so it is ONE 16-byte load -- half the L1 wavefronts of the 8-byte form.
+SPK_D void spk_ld2(const double *__restrict__ p, int n0, int nlim, bool vec2, double &a, double &b) {
+  if (vec2) {
+    if (n0 < nlim) {
+      const double2 t = *reinterpret_cast<const double2 *>(p + n0);
+      a = t.x;
+      b = t.y;
+    } else {
+      a = 0.0;
+      b = 0.0;
+    }
+  } else {
+    a = n0 < nlim ? p[n0] : 0.0;
+    b = n0 + 1 < nlim ? p[n0 + 1] : 0.0;
+  }
+}
+SPK_D void spk_st2(double *p, int n0, int nlim, bool vec2, double a, double b) {
+  if (vec2) {
+    if (n0 < nlim) *reinterpret_cast<double2 *>(p + n0) = make_double2(a, b);
+  } else {
+    if (n0 < nlim) p[n0] = a;
+    if (n0 + 1 < nlim) p[n0 + 1] = b;
+  }
+}
+// A operands of all k-steps of an `n`-vector at p (inner order spk_mm_kidx): steps in pairs, an odd last step alone
+template <int STEPS>
+SPK_D void spk_ld_afrag(const double *__restrict__ p, int n, int kk, bool vec2, double (&a)[STEPS]) {
+#pragma unroll
+  for (int S = 0; S < STEPS / 2; ++S) spk_ld2(p, 8 * S + 2 * kk, n, vec2, a[2 * S], a[2 * S + 1]);
+  if (STEPS & 1) {
+    const int k = 4 * (STEPS - 1) + kk;
+    a[STEPS - 1] = k < n ? p[k] : 0.0;
+  }
+}
+
 // thread 0: fetch `frags` fragments of the level's table into shared memory (completion on `bar`)
 SPK_D void spk_mm_fetch(double *smem, const double *frag_g, int frags, int tid) {
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -58,22 +94,28 @@ __device__ __forceinline__ void spk_bwd_mm_tile(const SpkDims &D, const SpkPtrs 
     if (!valid) fm = count - 1;  // trailing rows of the last tile recompute the last family; their stores are dropped
     const long i0 = first0 + fm, cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
     // ---- tu = (z - gamma L'v) on u_i (L_transpose! :399-420) in C-fragment order: entries 8 nb + 2 kk + {0, 1}
+    const bool vec2 = A.vec2 != 0;
     double tu[NBU][2];
+    {
+      const double *v7u = v + D.vo[6] + i0 * (NX + NU) + NX, *zu = z + D.zo[1] + i0 * NU;
 #pragma unroll
-    for (int nb = 0; nb < NBU; ++nb)
+      for (int nb = 0; nb < NBU; ++nb) {
+        const int n0 = 8 * nb + 2 * kk;
+        double l0, l1, z0, z1;
+        spk_ld2(v7u, n0, NU, vec2, l0, l1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int n = 8 * nb + 2 * kk + i;
-        double val = 0.0;
-        if (n < NU) {
-          double lt = v[D.vo[6] + i0 * (NX + NU) + NX + n];
-#pragma unroll
-          for (int c = 0; c < DD; ++c)
-            lt += P.sqrtR[(ucq ? 0 : (cfirst - 1 + c) * NU) + n] * v[D.vo[3] + (cfirst - 1 + c) * NU + n];
-          val = z[D.zo[1] + i0 * NU + n] - gamma * lt;
+        for (int c = 0; c < DD; ++c) {
+          double s0, s1, w0, w1;
+          spk_ld2(P.sqrtR + (ucq ? 0 : (cfirst - 1 + c) * NU), n0, NU, vec2, s0, s1);
+          spk_ld2(v + D.vo[3] + (cfirst - 1 + c) * NU, n0, NU, vec2, w0, w1);
+          l0 += s0 * w0;
+          l1 += s1 * w1;
         }
-        tu[nb][i] = val;
+        spk_ld2(zu, n0, NU, vec2, z0, z1);
+        tu[nb][0] = z0 - gamma * l0;
+        tu[nb][1] = z1 - gamma * l1;
       }
+    }
     // ---- sweep over the children's q (A fragments straight from HBM): acc1 = sum_c B_c' q_c (:590-596),
     //      acc3 = sum_c ABK_c' q_c (:610-632)
     double acc1[NBU][2], acc3[NBX][2];
@@ -81,38 +123,50 @@ __device__ __forceinline__ void spk_bwd_mm_tile(const SpkDims &D, const SpkPtrs 
     for (int nb = 0; nb < NBU; ++nb) acc1[nb][0] = acc1[nb][1] = 0.0;
     // acc3 starts at -(z - gamma L'v) on x_i (:634-636 with L_transpose! :351-373): these loads are issued with the tile's
     // first loads instead of sitting exposed behind the DMMA chain
+    {
+      const double *v7x = v + D.vo[6] + i0 * (NX + NU), *zx = z + i0 * NX;
 #pragma unroll
-    for (int nb = 0; nb < NBX; ++nb)
+      for (int nb = 0; nb < NBX; ++nb) {
+        const int n0 = 8 * nb + 2 * kk;
+        double l0, l1, z0, z1;
+        spk_ld2(v7x, n0, NX, vec2, l0, l1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int n = 8 * nb + 2 * kk + i;
-        double val = 0.0;
-        if (n < NX) {
-          double lt = v[D.vo[6] + i0 * (NX + NU) + n];
-#pragma unroll
-          for (int c = 0; c < DD; ++c)
-            lt += P.sqrtQ[(ucq ? 0 : (cfirst - 1 + c) * NX) + n] * v[D.vo[2] + (cfirst - 1 + c) * NX + n];
-          val = gamma * lt - z[i0 * NX + n];
+        for (int c = 0; c < DD; ++c) {
+          double s0, s1, w0, w1;
+          spk_ld2(P.sqrtQ + (ucq ? 0 : (cfirst - 1 + c) * NX), n0, NX, vec2, s0, s1);
+          spk_ld2(v + D.vo[2] + (cfirst - 1 + c) * NX, n0, NX, vec2, w0, w1);
+          l0 += s0 * w0;
+          l1 += s1 * w1;
         }
-        acc3[nb][i] = val;
+        spk_ld2(zx, n0, NX, vec2, z0, z1);
+        acc3[nb][0] = gamma * l0 - z0;
+        acc3[nb][1] = gamma * l1 - z1;
       }
+    }
 #pragma unroll
     for (int c = 0; c < DD; ++c) {
       double qa[KX];
+      if (LEAVES) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
+        const long l = lfirst + c;
+        const double *pz = z + (cfirst + c) * NX, *p14 = v + D.vo[10] + l * NX, *psq = P.sqrtQN + (ucn ? 0 : l * NX),
+                     *p11 = v + D.vo[7] + l * NX;
 #pragma unroll
-      for (int s = 0; s < KX; ++s) {
-        const int k = 4 * s + kk;
-        double a = 0.0;
-        if (k < NX) {
-          if (LEAVES) {  // q_leaf = -(x - gamma L'v)_leaf, implicit_l.jl:578-582 with :376-396
-            const long l = lfirst + c;
-            a = -(z[(cfirst + c) * NX + k] -
-                  gamma * (v[D.vo[10] + l * NX + k] + P.sqrtQN[(ucn ? 0 : l * NX) + k] * v[D.vo[7] + l * NX + k]));
-          } else {
-            a = A.q[(cfirst + c) * NX + k];
-          }
+        for (int S = 0; S < KX / 2; ++S) {
+          const int n0 = 8 * S + 2 * kk;
+          double z0, z1, a0, a1, q0, q1, b0, b1;
+          spk_ld2(pz, n0, NX, vec2, z0, z1);
+          spk_ld2(p14, n0, NX, vec2, a0, a1);
+          spk_ld2(psq, n0, NX, vec2, q0, q1);
+          spk_ld2(p11, n0, NX, vec2, b0, b1);
+          qa[2 * S] = -(z0 - gamma * (a0 + q0 * b0));
+          qa[2 * S + 1] = -(z1 - gamma * (a1 + q1 * b1));
         }
-        qa[s] = a;
+        if (KX & 1) {
+          const int k = 4 * (KX - 1) + kk;
+          qa[KX - 1] = k < NX ? -(pz[k] - gamma * (p14[k] + psq[k] * p11[k])) : 0.0;
+        }
+      } else {
+        spk_ld_afrag<KX>(A.q + (cfirst + c) * NX, NX, kk, vec2, qa);
       }
       if (!waited) {
         spk_mbar_wait(bar, phase);
@@ -142,10 +196,7 @@ __device__ __forceinline__ void spk_bwd_mm_tile(const SpkDims &D, const SpkPtrs 
       }
     if (valid) {
 #pragma unroll
-      for (int nb = 0; nb < NBU; ++nb)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          if (8 * nb + 2 * kk + i < NU) A.dd[i0 * NU + 8 * nb + 2 * kk + i] = dv[nb][i];
+      for (int nb = 0; nb < NBU; ++nb) spk_st2(A.dd + i0 * NU, 8 * nb + 2 * kk, NU, vec2, dv[nb][0], dv[nb][1]);
     }
     // ---- + G d + K'(d - ubar) (:610-632)
 #pragma unroll
@@ -164,10 +215,7 @@ __device__ __forceinline__ void spk_bwd_mm_tile(const SpkDims &D, const SpkPtrs 
     // ---- q_i (:634-636)
     if (valid) {
 #pragma unroll
-      for (int nb = 0; nb < NBX; ++nb)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          if (8 * nb + 2 * kk + i < NX) A.q[i0 * NX + 8 * nb + 2 * kk + i] = acc3[nb][i];
+      for (int nb = 0; nb < NBX; ++nb) spk_st2(A.q + i0 * NX, 8 * nb + 2 * kk, NX, vec2, acc3[nb][0], acc3[nb][1]);
     }
   }
 }
@@ -206,28 +254,18 @@ __device__ __forceinline__ void spk_fwd_mm_tile(const SpkDims &D, const SpkPtrs 
     if (!valid) fm = count - 1;
     const long i0 = first0 + fm, cfirst = (long)DD * i0 + 1;
     // ---- x_i (:667: x0 at the root) and d_i as A fragments; d_i again in C-fragment order as the start value of u_i
+    const bool vec2 = A.vec2 != 0;
     double xa[KX], da[KU], accu[NBU][2];
+    spk_ld_afrag<KX>(root ? P.x0 : A.zbar + i0 * NX, NX, kk, vec2, xa);
+    spk_ld_afrag<KU>(A.dd + i0 * NU, NU, kk, vec2, da);
 #pragma unroll
-    for (int s = 0; s < KX; ++s) {
-      const int k = 4 * s + kk;
-      xa[s] = k < NX ? (root ? P.x0[k] : A.zbar[i0 * NX + k]) : 0.0;
-    }
-#pragma unroll
-    for (int s = 0; s < KU; ++s) {
-      const int k = 4 * s + kk;
-      da[s] = k < NU ? A.dd[i0 * NU + k] : 0.0;
-    }
-#pragma unroll
-    for (int nb = 0; nb < NBU; ++nb)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int n = 8 * nb + 2 * kk + i;
-        accu[nb][i] = n < NU ? A.dd[i0 * NU + n] : 0.0;
-      }
+    for (int nb = 0; nb < NBU; ++nb) spk_ld2(A.dd + i0 * NU, 8 * nb + 2 * kk, NU, vec2, accu[nb][0], accu[nb][1]);
     if (root && valid) {
 #pragma unroll
-      for (int s = 0; s < KX; ++s)
-        if (4 * s + kk < NX) A.zbar[4 * s + kk] = xa[s];
+      for (int s = 0; s < KX; ++s) {
+        const int k = spk_mm_kidx(s, kk, KX);
+        if (k < NX) A.zbar[k] = xa[s];
+      }
     }
     if (!waited) {
       spk_mbar_wait(bar, phase);
@@ -242,10 +280,7 @@ __device__ __forceinline__ void spk_fwd_mm_tile(const SpkDims &D, const SpkPtrs 
     }
     if (valid) {
 #pragma unroll
-      for (int nb = 0; nb < NBU; ++nb)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          if (8 * nb + 2 * kk + i < NU) A.zbar[D.zo[1] + i0 * NU + 8 * nb + 2 * kk + i] = accu[nb][i];
+      for (int nb = 0; nb < NBU; ++nb) spk_st2(A.zbar + D.zo[1] + i0 * NU, 8 * nb + 2 * kk, NU, vec2, accu[nb][0], accu[nb][1]);
     }
     // ---- x_c = ABK_c x_i + B_c d_i (:675-679)
 #pragma unroll
@@ -267,10 +302,7 @@ __device__ __forceinline__ void spk_fwd_mm_tile(const SpkDims &D, const SpkPtrs 
       }
       if (valid) {
 #pragma unroll
-        for (int nb = 0; nb < NBX; ++nb)
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (8 * nb + 2 * kk + i < NX) A.zbar[(cfirst + c) * NX + 8 * nb + 2 * kk + i] = accx[nb][i];
+        for (int nb = 0; nb < NBX; ++nb) spk_st2(A.zbar + (cfirst + c) * NX, 8 * nb + 2 * kk, NX, vec2, accx[nb][0], accx[nb][1]);
       }
     }
   }

@@ -7,7 +7,10 @@
 // The weights are stored per level in FRAGMENT ORDER -- 32 consecutive doubles per (k-step, n-block), entry T being
 // the B-operand register of lane T -- so that a CTA fetches the whole level with one bulk copy and every operand read
 // is a conflict-free 256-byte shared-memory access.
-//   natural k-step s  : lane T holds W[8 nb + T/4][4 s + T%4]
+//   "natural" k-step s: lane T holds W[8 nb + T/4][spk_mm_kidx(s, T%4, steps)] -- steps are PAIRED: steps 2S and 2S+1
+//                       hold the inner entries 8S + 2(T%4) and 8S + 2(T%4) + 1, so that a lane fetches the A operands of
+//                       both steps with one 16-byte load of two consecutive vector entries (an odd last step holds
+//                       4 s + T%4)
 //   permuted k-step ks: lane T holds W[8 nb + T/4][8 (ks/2) + 2 (T%4) + (ks%2)]   -- the inner index order in which
 //                       the accumulator registers of a previous DMMA (rows 2(T%4), 2(T%4)+1 of n-block ks/2) can be fed
 //                       back as the A operand without any shuffle.
@@ -18,6 +21,11 @@
 #else
 #define SPK_MM_HD constexpr
 #endif
+
+// inner index held by lane position kk (= T%4) at k-step s of a matrix with `steps` k-steps
+SPK_MM_HD int spk_mm_kidx(int s, int kk, int steps) {
+  return ((steps & 1) && s == steps - 1) ? 4 * s + kk : 8 * (s >> 1) + 2 * kk + (s & 1);
+}
 
 struct SpkMmLayout {
   int KX, KU, KUP, NBX, NBU;          // k-steps over nx (natural), nu (natural), nu (permuted); n-blocks of nx / nu rows

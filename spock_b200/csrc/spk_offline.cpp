@@ -245,8 +245,8 @@ struct WView {
     return transposed ? p[k + (long)n * ld] : p[n + (long)k * ld];
   }
 };
-void put_natural(double *frag, const WView &W, int s, int nb) {
-  for (int T = 0; T < 32; ++T) frag[T] = W.at(8 * nb + T / 4, 4 * s + T % 4);
+void put_natural(double *frag, const WView &W, int s, int nb, int steps) {
+  for (int T = 0; T < 32; ++T) frag[T] = W.at(8 * nb + T / 4, spk_mm_kidx(s, T % 4, steps));
 }
 void put_permuted(double *frag, const WView &W, int ks, int nb) {
   for (int T = 0; T < 32; ++T) frag[T] = W.at(8 * nb + T / 4, 8 * (ks / 2) + 2 * (T % 4) + (ks % 2));
@@ -273,12 +273,12 @@ void spk_mm_fragment_tables(const SpkFactorTable &T, const double *B, std::vecto
       const WView ABK{T.ABK.data() + (size_t)(t * d + c) * T.abk_stride, nx, nx, nx, false};
       for (int s = 0; s < L.KX; ++s) {
         double *base = fb + (size_t)(L.bwd_sweep + (c * L.KX + s) * (L.NBU + L.NBX)) * 32;
-        for (int nb = 0; nb < L.NBU; ++nb) put_natural(base + (size_t)nb * 32, Bt, s, nb);
-        for (int nb = 0; nb < L.NBX; ++nb) put_natural(base + (size_t)(L.NBU + nb) * 32, ABKt, s, nb);
-        for (int nb = 0; nb < L.NBX; ++nb) put_natural(ff + (size_t)(L.fwd_abk + (c * L.KX + s) * L.NBX + nb) * 32, ABK, s, nb);
+        for (int nb = 0; nb < L.NBU; ++nb) put_natural(base + (size_t)nb * 32, Bt, s, nb, L.KX);
+        for (int nb = 0; nb < L.NBX; ++nb) put_natural(base + (size_t)(L.NBU + nb) * 32, ABKt, s, nb, L.KX);
+        for (int nb = 0; nb < L.NBX; ++nb) put_natural(ff + (size_t)(L.fwd_abk + (c * L.KX + s) * L.NBX + nb) * 32, ABK, s, nb, L.KX);
       }
       for (int s = 0; s < L.KU; ++s)
-        for (int nb = 0; nb < L.NBX; ++nb) put_natural(ff + (size_t)(L.fwd_b + (c * L.KU + s) * L.NBX + nb) * 32, Bn, s, nb);
+        for (int nb = 0; nb < L.NBX; ++nb) put_natural(ff + (size_t)(L.fwd_b + (c * L.KU + s) * L.NBX + nb) * 32, Bn, s, nb, L.KU);
     }
     for (int ks = 0; ks < L.KUP; ++ks) {
       for (int nb = 0; nb < L.NBU; ++nb) put_permuted(fb + (size_t)(L.bwd_s2 + ks * L.NBU + nb) * 32, Rinv, ks, nb);
@@ -288,6 +288,6 @@ void spk_mm_fragment_tables(const SpkFactorTable &T, const double *B, std::vecto
       }
     }
     for (int s = 0; s < L.KX; ++s)
-      for (int nb = 0; nb < L.NBU; ++nb) put_natural(ff + (size_t)(L.fwd_k + s * L.NBU + nb) * 32, K, s, nb);
+      for (int nb = 0; nb < L.NBU; ++nb) put_natural(ff + (size_t)(L.fwd_k + s * L.NBU + nb) * 32, K, s, nb, L.KX);
   }
 }

@@ -146,7 +146,7 @@ struct spk_handle {
   void (*k_dual3[2][2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {{nullptr, nullptr}, {nullptr, nullptr}};  // [children are leaves][with <r,Pr>]
   int occ_dual3 = 4;
   // per-stage factors on the fp64 tensor pipe (spk_mm.cuh)
-  bool use_mm = false;
+  bool use_mm = false, mm_vec2 = false;
   void (*k_bwd_mm[2])(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = {nullptr, nullptr};
   void (*k_fwd_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = nullptr;
   void (*k_top_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *, const double *, int) = nullptr;
@@ -554,6 +554,11 @@ static int fused_setup(spk_handle *h) {
   if (h->use_mm) {  // fragment-ordered per-level weight tables (spk_mm_layout.h)
     const SpkMmLayout L = spk_mm_layout(D.nx, D.nu, D.d);
     h->mm_bwd_frags = L.bwd_frags; h->mm_fwd_frags = L.fwd_frags;
+    {  // 16-byte loads of consecutive entry pairs need even sizes and even segment offsets (reference layout, 8-byte entries)
+      const char *nv2 = getenv("SPK_NO_VEC2");
+      h->mm_vec2 = !(nv2 && nv2[0] == '1') && D.nx % 2 == 0 && D.nu % 2 == 0 && D.nz % 2 == 0 && D.zo[1] % 2 == 0 &&
+                   D.vo[2] % 2 == 0 && D.vo[3] % 2 == 0 && D.vo[6] % 2 == 0 && D.vo[7] % 2 == 0 && D.vo[10] % 2 == 0;
+    }
     const size_t sb = spk_mm_smem_bytes(L.bwd_frags), sf = spk_mm_smem_bytes(L.fwd_frags);
     if (std::max(sb, sf) > 227 * 1024) {
       h->use_mm = false;
@@ -602,6 +607,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   A.q = h->ric_q; A.dd = h->ric_d; A.xi = h->d_scal; A.pnorm = pnorm_slot >= 0 ? h->d_pnorm : nullptr;
   A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0; A.p_lo = 0; A.p_cnt = 0;
   A.gate = h->d_ctl ? &h->d_ctl->done : nullptr;
+  A.vec2 = h->mm_vec2 ? 1 : 0;
   fill_ranges(h, A);
   const long owned = A.r_prefix[A.n_ranges];
   std::string cerr;
@@ -623,7 +629,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
         // small levels: fewer warps (tiles) per CTA so that the tiles spread over the SMs (a DMMA chain is bound by
         // the tensor pipe of its SM sub-partition)
         const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_bwd_mm;
-        const long wpb = std::min(8L, std::max(1L, (tiles + cap - 1) / cap));
+        const long wpb = std::min(8L, std::max(1L, (tiles + h->num_sms - 1) / h->num_sms));  // one tile per SM sub-partition first
         const long ctas = std::min((tiles + wpb - 1) / wpb, cap);
         spk_mm_kernel_t kmm = h->k_bwd_mm[A.children_are_leaves ? 1 : 0];
         kmm<<<(unsigned)std::max(1L, ctas), (unsigned)(32 * wpb), spk_mm_smem_bytes((int)h->mm_bwd_frags), h->stream>>>(
@@ -659,7 +665,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
 #ifndef SPK_HOST_EMU
     if (h->use_mm) {
       const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_fwd_mm;
-      const long wpb = std::min(8L, std::max(1L, (tiles + cap - 1) / cap));
+      const long wpb = std::min(8L, std::max(1L, (tiles + h->num_sms - 1) / h->num_sms));
       const long ctas = std::min((tiles + wpb - 1) / wpb, cap);
       h->k_fwd_mm<<<(unsigned)std::max(1L, ctas), (unsigned)(32 * wpb), spk_mm_smem_bytes((int)h->mm_fwd_frags), h->stream>>>(
           D, h->P, A, h->d_frag_fwd + (size_t)t * h->mm_fwd_frags * 32);
@@ -1691,7 +1697,7 @@ int spk_comm_unique_id(uint8_t id[128]) {
 int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int64_t *count) {
   if (!h || !n_ranges) return fail(SPK_ERR_INVALID, "NULL argument");
   SpkFusedArgs A;
-  A.gate = nullptr;
+  A.gate = nullptr; A.vec2 = 0;
   fill_ranges(h, A);
   *n_ranges = A.n_ranges;
   for (int k = 0; k < A.n_ranges; ++k) {
