@@ -114,4 +114,29 @@ function solve_model!(m::Model, x0::AbstractVector{Float64}; tol = 1e-3, verbose
   return nothing
 end
 
+"""
+    get_state(model) / set_state!(model, state)
+
+Everything besides (z, v) that `solve_model!` carries over from the previous solve (model.jl:80-226): checkpoint /
+resume of a warm-started MPC loop.  Layout: include/spock_b200.h.
+"""
+function get_state(m::Model)
+  n = Ref{Int64}(0); check(ccall((:spk_state_size, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), m.handle, n))
+  st = zeros(n[]); check(ccall((:spk_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), m.handle, st))
+  return st
+end
+set_state!(m::Model, st::Vector{Float64}) = check(ccall((:spk_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), m.handle, st))
+
+"""
+    estimate_L_norm!(model; iters = 50)
+
+Replaces the hard-coded `L_norm` of cpock.jl:62-63 / spock.jl:63-64 by a power-iteration estimate of ||L||^2.
+"""
+function estimate_L_norm!(m::Model; iters = 50)
+  out = Ref{Float64}(0.0)
+  check(ccall((:spk_estimate_L_norm, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), m.handle, iters, out))
+  check(ccall((:spk_set_L_norm, LIB), Cint, (Ptr{Cvoid}, Float64), m.handle, out[]))
+  return out[]
+end
+
 end # module

@@ -1108,6 +1108,9 @@ template <int NX, int NU, int DD, bool LEAVES, bool UC, bool PN>
 __launch_bounds__(128, SPK_DUAL3_MINB)
 __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, long fam_cnt) {
   if (A.gate && *A.gate) return;
+  // current residual maxima, read now so that the round trip overlaps the family's loads (a stale value only causes a
+  // redundant atomic at the end, never a missed one)
+  const double seen_xi1 = __ldcg(A.xi + 0), seen_xi2 = __ldcg(A.xi + 1);
   constexpr int G = spk_dual3_group(NX, NU, DD), FPW = 32 / G;  // lanes per family, families per warp
   constexpr int RX = (NX + G - 1) / G, RU = (NU + G - 1) / G, CD = UC ? 1 : DD, LD = LEAVES ? DD : 1;
   __shared__ double s_red[3 * 4];
@@ -1442,8 +1445,8 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   if (!valid) my_pn = 0.0;
   const double m1 = spk_warp_max_nonneg(my_xi1), m2 = spk_warp_max_nonneg(my_xi2);
   if (wlane == 0) {
-    spk_atomic_max_lazy(A.xi + 0, m1);
-    spk_atomic_max_lazy(A.xi + 1, m2);
+    if (m1 > seen_xi1) spk_atomic_max_nonneg(A.xi + 0, m1);
+    if (m2 > seen_xi2) spk_atomic_max_nonneg(A.xi + 1, m2);
   }
   if (PN) {
     const double ps = spk_warp_sum(my_pn);

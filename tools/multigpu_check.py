@@ -50,6 +50,19 @@ for name, spec, K in (("heat N=8 nx=5", get_server_heat_specs(8, 5, 2), 40), ("r
                 assert abs(w[3][0] - xr[0]) < 1e-10 * xr[0] and abs(w[3][1] - xr[1]) < 1e-10 * xr[1], (w[3], xr)
             worst_all = max(worst_all, ez, ev)
             ref.close()
+        # solve_model! to tolerance with the device-resident termination test (xi all-reduced over the ranks every pass):
+        # every rank stops on the same pass as the single-GPU solve
+        x0 = 0.1 * np.ones(flat.nx)
+        res, _ = h.solve(x0, tol=1e-3, z0=np.zeros(h.nz), v0=np.zeros(h.nv))
+        allres = [None] * world
+        dist.all_gather_object(allres, (res["passes"], res["converged"], res["xi1"], res["xi2"]))
+        if rank == 0:
+            ref = Handle(flat, 1, factor_mode=fm, device=local)
+            rr, _ = ref.solve(x0, tol=1e-3, z0=np.zeros(ref.nz), v0=np.zeros(ref.nv))
+            for a in allres:
+                assert a[0] == rr["passes"] and a[1] == rr["converged"] == 1, (name, fm, a, rr["passes"])
+                assert abs(a[2] - rr["xi1"]) < 1e-9 * rr["xi1"] and abs(a[3] - rr["xi2"]) < 1e-9 * rr["xi2"]
+            ref.close()
         h.close()
         dist.barrier()
 if rank == 0:
