@@ -19,8 +19,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libspock_b200.so")
-HEADERS = ["spk_kernels.cuh", "spk_types.h", "spk_runtime.h", "spk_offline.h", "spk_fused.cuh", "spk_shapes.h",
-           "spk_shapes.def", "spk_comm.h", os.path.join("..", "..", "include", "spock_b200.h")]
+def _headers():
+    """every header / table of csrc plus the public C header: any change rebuilds every translation unit"""
+    hs = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".def")))
+    return hs + [os.path.join("..", "..", "include", "spock_b200.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -56,7 +59,7 @@ def _units():
 
 def _dep_stamp(src: str, extra) -> str:
     h = hashlib.sha1()
-    for d in [src] + HEADERS:
+    for d in [src] + _headers():
         p = os.path.join(CSRC, d)
         if os.path.exists(p):
             h.update(open(p, "rb").read())

@@ -150,6 +150,7 @@ struct spk_handle {
   void (*k_bwd_mm[2])(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = {nullptr, nullptr};
   void (*k_fwd_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *) = nullptr;
   void (*k_top_mm)(SpkDims, SpkPtrs, SpkFusedArgs, const double *, const double *, int) = nullptr;
+  long mm_min_count = 512;  // levels with fewer families run the CTA-per-family kernels (lower fixed cost per launch)
   int t_top = -1;  // levels 0 .. t_top of both sweeps run in the single-CTA top-of-tree kernel (-1: none)
   double *d_frag_bwd = nullptr, *d_frag_fwd = nullptr;
   long mm_bwd_frags = 0, mm_fwd_frags = 0;
@@ -577,8 +578,12 @@ static int fused_setup(spk_handle *h) {
       RT_CHECK(cudaFuncSetAttribute((const void *)h->k_top_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sb, sf)));
       const char *nt = getenv("SPK_NO_TOP");
       h->t_top = -1;
-      if (!(nt && nt[0] == '1'))
+      // (measured: with large fragment tables -- nx = 50: 93-168 KB per level -- a level in the single-CTA kernel costs
+      // ~9 us against ~5 us for a CTA-per-family launch, so the top-of-tree kernel is used for the small shapes only)
+      if (!(nt && nt[0] == '1') && std::max(sb, sf) <= 64 * 1024)
         for (int t = 0; t <= D.N - 3 && spk_level_count(D.d, t) <= 64; ++t) h->t_top = t;  // never the leaf-parent level
+      const char *mc = getenv("SPK_MM_MIN_COUNT");
+      if (mc) h->mm_min_count = atol(mc);
     }
   }
   h->occ_fwd = std::max(1, h->occ_fwd);
@@ -625,7 +630,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
       A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
       level_range(h, t, A.p_lo, A.p_cnt);
 #ifndef SPK_HOST_EMU
-      if (h->use_mm) {  // per-stage factors: the level is a chain of mat-mats on the fp64 tensor pipe
+      if (h->use_mm && A.p_cnt >= h->mm_min_count) {  // per-stage factors: the level is a chain of mat-mats on the fp64 tensor pipe
         // small levels: fewer warps (tiles) per CTA so that the tiles spread over the SMs (a DMMA chain is bound by
         // the tensor pipe of its SM sub-partition)
         const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_bwd_mm;
@@ -663,7 +668,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     A.t = t; A.children_are_leaves = (t == D.N - 2);
     level_range(h, t, A.p_lo, A.p_cnt);
 #ifndef SPK_HOST_EMU
-    if (h->use_mm) {
+    if (h->use_mm && A.p_cnt >= h->mm_min_count) {
       const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_fwd_mm;
       const long wpb = std::min(8L, std::max(1L, (tiles + h->num_sms - 1) / h->num_sms));
       const long ctas = std::min((tiles + wpb - 1) / wpb, cap);

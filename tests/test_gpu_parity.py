@@ -279,6 +279,7 @@ def test_tensor_pipe_sweeps_equal_family_kernels(cuda_lib, nx, nu, d, N, monkeyp
     flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
     rng = np.random.default_rng(17)
     out = []
+    monkeypatch.setenv("SPK_MM_MIN_COUNT", "1")  # by default levels with < 512 families use the CTA-per-family kernels
     for no_mm, no_top in (("1", "0"), ("0", "0"), ("0", "1")):
         monkeypatch.setenv("SPK_NO_MM", no_mm)
         monkeypatch.setenv("SPK_NO_TOP", no_top)
@@ -300,6 +301,15 @@ def test_tensor_pipe_sweeps_equal_family_kernels(cuda_lib, nx, nu, d, N, monkeyp
     o.z[:], o.v[:] = z0, v0
     o.step(4)
     assert relerr(zm, o.z) < 1e-11 and relerr(vm, o.v) < 1e-11
+    # default policy: tensor-pipe kernels on the wide levels, CTA-per-family kernels on the narrow ones
+    monkeypatch.setenv("SPK_MM_MIN_COUNT", "16")
+    h = Handle(flat, CP, factor_mode=1, lib=cuda_lib)
+    h.set_x0(x0)
+    h.set_iterate(z0, v0)
+    h.step(4)
+    zh, vh = h.get_iterate()
+    h.close()
+    assert relerr(zh, o.z) < 1e-11 and relerr(vh, o.v) < 1e-11
 
 
 def test_state_checkpoint_resume_is_bit_exact(cuda_lib):
