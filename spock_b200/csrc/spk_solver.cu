@@ -166,7 +166,7 @@ struct spk_handle {
   bool use_graphs = false;
 #ifndef SPK_HOST_EMU
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
-  std::map<std::tuple<const void *, void *, double, double, int>, GraphEntry> graphs;
+  std::map<std::tuple<const void *, void *, double, double, int, int>, GraphEntry> graphs;
 #endif
   // device-resident loop control (spk_sp.cuh): termination test, SuperMann / Anderson scalars, per-pass log
   SpkCtl *d_ctl = nullptr;
@@ -604,7 +604,11 @@ static unsigned fused_grid(const spk_handle *h, long count, int occ) {
   return (unsigned)std::max(1L, g);
 }
 
-static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
+// `parts`: 1 = kernels up to the cut-level exchange, 2 = that exchange (all-gather of the subtree roots' q), 4 = the remaining
+// kernels, 8 = the exchange of the subtree roots' vbar2.  All (15) for a plain launch; the multi-GPU graph replay captures the
+// kernel segments 1 and 4 separately and issues the two NCCL exchanges between them on the stream.
+static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot,
+                             int parts = 15) {
   const SpkDims &D = h->D;
   SpkFusedArgs A;
   A.gamma = gamma; A.sigma = sigma; A.inv_gamma = 1.0 / gamma; A.inv_sigma = 1.0 / sigma;
@@ -616,7 +620,8 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   fill_ranges(h, A);
   const long owned = A.r_prefix[A.n_ranges];
   std::string cerr;
-  {  // 3. S2 (independent of the sweeps)
+  const bool seg_a = (parts & 1) != 0, seg_b = (parts & 4) != 0;
+  if (seg_a) {  // 3. S2 (independent of the sweeps)
     ProfScope ps(h, PC_S2);
     const int b = SPK_EMU ? 1 : 128;
     SPK_LAUNCH(spk_k_s2t, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
@@ -625,7 +630,8 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   // levels 0 .. t_top of both sweeps run in one single-CTA launch (single GPU, tensor-pipe kernels)
   const int t_top = (h->use_mm && h->world == 1) ? h->t_top : -1;
   for (int t = D.N - 2; t > t_top; --t) {  // 1. backward sweep
-    {
+    const bool in_a = h->world <= 1 || t >= h->t_cut;  // levels down to the cut belong to the first kernel segment
+    if (in_a ? seg_a : seg_b) {
       ProfScope ps(h, PC_FUSED_BWD);
       A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
       level_range(h, t, A.p_lo, A.p_cnt);
@@ -647,13 +653,21 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
       }
       COUNT_LAUNCH(h, PC_FUSED_BWD);
     }
-    if (h->world > 1 && t == h->t_cut) {  // the replicated levels above the cut need every subtree root's q
+    if (h->world > 1 && t == h->t_cut && (parts & 2)) {  // the replicated levels above the cut need every subtree root's q
       ProfScope ps(h, PC_VEC);
       if (!h->comm.allgather_inplace(h->ric_q + spk_level_first0(D.d, t) * D.nx, h->m_sub * D.nx, h->stream, cerr))
         return comm_fail(cerr);
     }
   }
   A.reset_xi = 0;
+  if (!seg_b) {
+    if (h->world > 1 && (parts & 8)) {  // the second exchange on its own (between graph segments)
+      ProfScope ps(h, PC_VEC);
+      if (!h->comm.allgather_inplace(A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub, h->stream, cerr))
+        return comm_fail(cerr);
+    }
+    return rt_launch_check();
+  }
 #ifndef SPK_HOST_EMU
   if (t_top >= 0) {
     ProfScope ps(h, PC_FUSED_BWD);
@@ -727,7 +741,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     SPK_LAUNCH(kfn, (unsigned)std::max(1L, g), T, h->fused_smem_dual, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_PROX_H);
   }
-  if (h->world > 1) {  // v2 of the subtree roots is read by the replicated family above the cut in the next evaluation
+  if (h->world > 1 && (parts & 8)) {  // v2 of the subtree roots is read by the replicated family above the cut in the next evaluation
     ProfScope ps(h, PC_VEC);
     if (!h->comm.allgather_inplace(A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub, h->stream, cerr))
       return comm_fail(cerr);
@@ -737,37 +751,49 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   return SPK_OK;
 }
 
-// One operator evaluation.  On a single GPU the whole launch sequence (2(N-1)+3 kernels, more with the P-norm) is
-// captured once per (input buffer, output buffer, step sizes) into a CUDA graph and replayed: for small and medium
-// trees a pass is launch-bound and a graph node costs a fraction of a stream launch.
+#ifndef SPK_HOST_EMU
+// replay (capturing it on first use) the kernel segment `parts` of one operator evaluation
+static int graph_segment(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot, int parts) {
+  const auto key = std::make_tuple((const void *)zv_in, (void *)zv_out, gamma, sigma, pnorm_slot, parts);
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    if (h->graphs.size() >= 96) {  // bounded cache
+      for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+      h->graphs.clear();
+    }
+    const int64_t l0 = h->launches;
+    RT_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot, parts);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != SPK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    spk_handle::GraphEntry ge;
+    ge.kernels = h->launches - l0;
+    h->launches = l0;
+    const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    it = h->graphs.emplace(key, ge).first;
+  }
+  RT_CHECK(cudaGraphLaunch(it->second.exec, h->stream));
+  h->launches += it->second.kernels;
+  return SPK_OK;
+}
+#endif
+
+// One operator evaluation.  The launch sequence (2(N-1)+3 kernels, more with the P-norm) is captured once per (input buffer,
+// output buffer, step sizes) into CUDA graphs and replayed: for small and medium trees a pass is launch-bound and a graph
+// node costs a fraction of a stream launch.  With several GPUs the two kernel segments around the cut-level exchange are
+// separate graphs and the NCCL all-gathers are issued on the stream between them (a collective inside a capture hung).
 static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
 #ifndef SPK_HOST_EMU
-  if (h->use_graphs && !h->prof_on && h->world == 1) {  // NCCL collectives inside a capture hung on this stack: 1 GPU only
-    const auto key = std::make_tuple((const void *)zv_in, (void *)zv_out, gamma, sigma, pnorm_slot);
-    auto it = h->graphs.find(key);
-    if (it == h->graphs.end()) {
-      if (h->graphs.size() >= 48) {  // bounded cache
-        for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
-        h->graphs.clear();
-      }
-      const int64_t l0 = h->launches;
-      RT_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot);
-      cudaGraph_t graph = nullptr;
-      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-      if (rc != SPK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (ce != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-      spk_handle::GraphEntry ge;
-      ge.kernels = h->launches - l0;
-      h->launches = l0;
-      const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ie != cudaSuccess) return fail(SPK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
-      it = h->graphs.emplace(key, ge).first;
-    }
-    RT_CHECK(cudaGraphLaunch(it->second.exec, h->stream));
-    h->launches += it->second.kernels;
-    return SPK_OK;
+  if (h->use_graphs && !h->prof_on) {
+    if (h->world == 1) return graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 15);
+    SPK_TRY(graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 1));
+    SPK_TRY(op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 2));
+    SPK_TRY(graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 4));
+    return op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 8);
   }
 #endif
   return op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot);
