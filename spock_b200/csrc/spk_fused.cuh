@@ -466,34 +466,37 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
 // One thread per non-leaf node: gathers (z - gamma L'v) for (y_i, s_children, tau_children) (L_transpose! :423-448),
 // multiplies by the kernel projector (projection_S2! :688-727) and writes zbar; thread 0 also does prox_f!'s
 // s_1 -= gamma (:741), the only s entry outside every S2 group.
-#ifndef SPK_SHAPE_TU  // not a template: defined in the solver's translation unit only
+// NY_, DD_ > 0: risk-vector length and branching fixed at compile time, so that the gathered vector stays in registers
+// (with runtime sizes it is a dynamically indexed local array: 1.4 ms per pass at config 5); 0: runtime sizes.
+template <int NY_, int DD_>
 SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   if (A.gate && *A.gate) return;
   const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= A.r_prefix[A.n_ranges]) return;
   const long i0 = spk_owned_family(A, f);
-  const int ny = D.ny, d = D.d, nls = D.nls;
+  const int ny = NY_ > 0 ? NY_ : D.ny, d = NY_ > 0 ? DD_ : D.d, nls = ny + 2 * d;
+  constexpr int CAP = NY_ > 0 ? NY_ + 2 * DD_ : SPK_MAX_LS;
   const double gamma = A.gamma;
   const long cfirst = (long)d * i0 + 1;
-  double in[SPK_MAX_LS];
+  double in[CAP];
   const double v2i = A.v[D.vo[1] + i0];
-  for (int k = 0; k < ny; ++k) in[k] = A.z[D.zo[4] + i0 * ny + k] - gamma * (A.v[i0 * ny + k] - P.b[k] * v2i);
-  for (int c = 0; c < d; ++c) {
+  _Pragma("unroll") for (int k = 0; k < (NY_ > 0 ? NY_ : ny); ++k)
+    in[k] = A.z[D.zo[4] + i0 * ny + k] - gamma * (A.v[i0 * ny + k] - P.b[k] * v2i);
+  _Pragma("unroll") for (int c = 0; c < (NY_ > 0 ? DD_ : d); ++c) {
     const long j0 = cfirst + c;
     const double lt = (j0 < D.nnl) ? A.v[D.vo[1] + j0] : 0.5 * A.v[D.vo[8] + (j0 - D.nnl)] + 0.5 * A.v[D.vo[9] + (j0 - D.nnl)];
     in[ny + c] = A.z[D.zo[2] + j0] - gamma * lt;
     in[ny + d + c] = A.z[D.zo[3] + j0 - 1] - gamma * (0.5 * A.v[D.vo[4] + j0 - 1] + 0.5 * A.v[D.vo[5] + j0 - 1]);
   }
-  for (int k = 0; k < nls; ++k) {
+  _Pragma("unroll") for (int k = 0; k < (NY_ > 0 ? CAP : nls); ++k) {
     double acc = 0.0;
-    for (int m = 0; m < nls; ++m) acc += P.ls[k + (long)m * nls] * in[m];
+    _Pragma("unroll") for (int m = 0; m < (NY_ > 0 ? CAP : nls); ++m) acc += P.ls[k + (long)m * nls] * in[m];
     if (k < ny) A.zbar[D.zo[4] + i0 * ny + k] = acc;
     else if (k < ny + d) A.zbar[D.zo[2] + cfirst + (k - ny)] = acc;
     else A.zbar[D.zo[3] + cfirst + (k - ny - d) - 1] = acc;
   }
   if (i0 == 0) A.zbar[D.zo[2]] = A.z[D.zo[2]] - gamma * v2i - gamma;
 }
-#endif
 
 // ------------------------------------------------------------------------------------------------ 4. dual blocks
 

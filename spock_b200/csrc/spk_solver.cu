@@ -624,7 +624,16 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   if (seg_a) {  // 3. S2 (independent of the sweeps)
     ProfScope ps(h, PC_S2);
     const int b = SPK_EMU ? 1 : 128;
-    SPK_LAUNCH(spk_k_s2t, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
+    void (*ks2)(SpkDims, SpkPtrs, SpkFusedArgs) = spk_k_s2t<0, 0>;
+    if (!SPK_EMU) {  // the common risk measures: AV@R (ny = 2d+1), l2-ball / TV style (ny = 2d+2)
+      if (D.ny == 5 && D.d == 2) ks2 = spk_k_s2t<5, 2>;
+      else if (D.ny == 7 && D.d == 3) ks2 = spk_k_s2t<7, 3>;
+      else if (D.ny == 9 && D.d == 4) ks2 = spk_k_s2t<9, 4>;
+      else if (D.ny == 6 && D.d == 2) ks2 = spk_k_s2t<6, 2>;
+      else if (D.ny == 8 && D.d == 3) ks2 = spk_k_s2t<8, 3>;
+      else if (D.ny == 10 && D.d == 4) ks2 = spk_k_s2t<10, 4>;
+    }
+    SPK_LAUNCH(ks2, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_S2);
   }
   // levels 0 .. t_top of both sweeps run in one single-CTA launch (single GPU, tensor-pipe kernels)
