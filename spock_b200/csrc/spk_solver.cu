@@ -1746,3 +1746,26 @@ int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int
   }
   return SPK_OK;
 }
+
+#ifdef SPK_HOST_EMU
+// Test hook of the host-emulation build only (tests/test_mm_fragments.py): the fragment-ordered weight tables that the
+// tensor-pipe S1 kernels of the CUDA build read (spk_mm_layout.h), so that the CPU test-suite can check the host-side
+// fragment / permutation logic by emulating the DMMA chain.  counts = {bwd fragments per level, fwd fragments per level,
+// and the layout offsets}.  Either table pointer may be NULL (size query).
+#include "spk_mm_layout.h"
+extern "C" int spk_emu_mm_tables(spk_handle *h, double *bwd, double *fwd, int64_t counts[16]) {
+  if (!h || !counts) return fail(SPK_ERR_INVALID, "NULL argument");
+  const SpkMmLayout L = spk_mm_layout(h->D.nx, h->D.nu, h->D.d);
+  const int vals[16] = {L.bwd_frags, L.fwd_frags, L.KX, L.KU, L.KUP, L.NBX, L.NBU, L.bwd_sweep, L.bwd_s2, L.bwd_s3b,
+                        L.bwd_s3c, L.fwd_k, L.fwd_abk, L.fwd_b, h->D.N, 0};
+  for (int k = 0; k < 16; ++k) counts[k] = vals[k];
+  if (bwd || fwd) {
+    std::vector<double> fb, ff;
+    spk_mm_fragment_tables(h->table, h->B_host.data(), fb, ff);
+    if (bwd) memcpy(bwd, fb.data(), fb.size() * sizeof(double));
+    if (fwd) memcpy(fwd, ff.data(), ff.size() * sizeof(double));
+  }
+  return SPK_OK;
+}
+#endif
+
