@@ -79,3 +79,41 @@ def test_silent_termination_and_warm_start(emu_lib):
             h.solve(x0, z0=np.zeros(h.nz))
         with pytest.raises(ValueError):
             h.L(np.zeros(h.nz + 1))  # implicit_l.jl:184-186
+
+
+def test_state_checkpoint_resume(emu_lib):
+    """spk_get_state / spk_set_state through the host-emulation build (host-driven loops): an interrupted SuperMann / CP run
+    resumed in a fresh handle reproduces the uninterrupted one bit for bit."""
+    import numpy as np
+
+    flat = flat_of("fixture_N3_d2")
+    for alg, k1, k2 in ((SP, 7, 6), (CP, 10, 8)):
+        ref = Handle(flat, alg, factor_mode=1, lib=emu_lib)
+        ref.set_x0(0.1 * np.ones(flat.nx))
+        ref.step(k1)
+        z1, v1 = ref.get_iterate()
+        st = ref.get_state()
+        ref.step(k2)
+        z_ref, v_ref = ref.get_iterate()
+        ref.close()
+        h = Handle(flat, alg, factor_mode=1, lib=emu_lib)
+        h.set_x0(0.1 * np.ones(flat.nx))
+        assert st.shape == ((12 * (h.nz + h.nv) + 9,) if alg == SP else (h.nz + h.nv,))
+        h.set_iterate(z1, v1)
+        h.set_state(st)
+        h.step(k2)
+        z, v = h.get_iterate()
+        h.close()
+        assert np.array_equal(z, z_ref) and np.array_equal(v, v_ref)
+
+
+def test_power_iteration_L_norm(emu_lib):
+    """spk_estimate_L_norm == largest eigenvalue of L'L assembled from the oracle's L, column by column."""
+    import numpy as np
+
+    flat = flat_of("fixture_N3_d2")
+    h, o = Handle(flat, CP, lib=emu_lib), Oracle(flat, CP)
+    Lmat = np.stack([o.L(e) for e in np.eye(h.nz)], axis=1)
+    lam = float(np.linalg.eigvalsh(Lmat.T @ Lmat)[-1])
+    assert abs(h.estimate_L_norm(400) - lam) < 1e-6 * lam
+    h.close()
