@@ -1397,8 +1397,9 @@ int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double s
   if (!h || !in || !out) return fail(SPK_ERR_INVALID, "NULL argument");
   const SpkDims &D = h->D;
   const long nz = D.nz, nv = D.nv;
-  // scratch: wu-sized temporaries carved from dzv / xi12 (not live outside the loops)
-  double *tz = h->dzv, *tv = h->dzv + nz, *oz = h->xi12, *ov = h->xi12 + nz;
+  // scratch that carries nothing across passes or solves: zvbar (rewritten by every operator evaluation) and xi12
+  // (dzv is NOT scratch: SuperMann's next Anderson step reads delta_z, delta_v of the previous pass)
+  double *tz = h->zvbar, *tv = h->zvbar + nz, *oz = h->xi12, *ov = h->xi12 + nz;
   switch (op) {
     case SPK_OP_L:
       SPK_TRY(rt_h2d(tz, in, sizeof(double) * nz, h->stream));
@@ -1434,11 +1435,11 @@ int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b
             double sigma, double *out) {
   if (!h || !a_z || !a_v || !b_z || !b_v || !out) return fail(SPK_ERR_INVALID, "NULL argument");
   const long nz = h->D.nz, nv = h->D.nv;
-  SPK_TRY(rt_h2d(h->dzv, a_z, sizeof(double) * nz, h->stream));
-  SPK_TRY(rt_h2d(h->dzv + nz, a_v, sizeof(double) * nv, h->stream));
+  SPK_TRY(rt_h2d(h->zvbar, a_z, sizeof(double) * nz, h->stream));
+  SPK_TRY(rt_h2d(h->zvbar + nz, a_v, sizeof(double) * nv, h->stream));
   SPK_TRY(rt_h2d(h->xi12, b_z, sizeof(double) * nz, h->stream));
   SPK_TRY(rt_h2d(h->xi12 + nz, b_v, sizeof(double) * nv, h->stream));
-  SPK_TRY(op_pdot(h, h->dzv, h->xi12, gamma, sigma, 4));
+  SPK_TRY(op_pdot(h, h->zvbar, h->xi12, gamma, sigma, 4));
   SPK_TRY(fetch_scalars(h, 5));
   *out = h->h_scal[4];
   return SPK_OK;

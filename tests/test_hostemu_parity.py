@@ -117,3 +117,26 @@ def test_power_iteration_L_norm(emu_lib):
     lam = float(np.linalg.eigvalsh(Lmat.T @ Lmat)[-1])
     assert abs(h.estimate_L_norm(400) - lam) < 1e-6 * lam
     h.close()
+
+
+def test_operator_calls_do_not_disturb_the_supermann_memory(emu_lib):
+    """Like the reference's spock_mul! / spock_dot, spk_apply / spk_dot between two solves leave the persistent SuperMann
+    state (delta_z, delta_v, Anderson columns) alone: the warm-started second solve is bit-identical with and without them."""
+    import numpy as np
+
+    flat = flat_of("heat_N4_d3_nx3")
+    x0 = 0.1 * np.ones(flat.nx)
+    rng = np.random.default_rng(4)
+    out = []
+    for poke in (False, True):
+        h = Handle(flat, SP, lib=emu_lib)
+        h.solve(x0, tol=1e-3)
+        if poke:
+            z, v = rng.standard_normal(h.nz), rng.standard_normal(h.nv)
+            h.L(z), h.Lt(v), h.prox_f(z, 0.2), h.prox_h_conj(v, 0.3), h.projection_S1(z[: h.z_off[2]])
+            h.dot(z, v, z, v, 0.3, 0.2)
+        r, log = h.solve(0.8 * x0, tol=1e-4)
+        out.append((r["passes"], log["xi1"], h.get_iterate()))
+        h.close()
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2][0], out[1][2][0]) and np.array_equal(out[0][2][1], out[1][2][1])
