@@ -280,6 +280,117 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
       }
     }
   };
+  // SPLIT (large specialised shapes): the factors arrive in D_+1 chunks on their own mbarriers -- ABK_c' per child, then
+  // (G, K', Rinv) -- and the ABK' mat-vec runs child by child, so that a child's matrix is re-fetched for the next family as
+  // soon as it is consumed instead of after the whole family (see spk_k_fwd_s1).
+  constexpr bool SPLIT = !SPK_EMU && NX_ > 0 && D_ <= 4 && NX_ * NX_ * 8 >= 16 * 1024 && NX_ * spk_cslices(T_, NX_) <= T_;
+  if constexpr (SPLIT) {
+    uint64_t *cbar = reinterpret_cast<uint64_t *>(rv11 + (long)d * nx);  // D_ barriers in the 4 spare doubles behind the staging
+    if (tid == 0)
+      for (int c = 0; c < D_; ++c) spk_mbar_init(cbar + c, 1);
+    SPK_SYNCTHREADS();
+    auto fetch_child = [&](long i0, int c) {
+      const long aslot = D.per_node ? (long)d * i0 : (long)t * d;
+      spk_mbar_expect_tx(cbar + c, (uint32_t)(D.abk_stride * sizeof(double)));
+      spk_bulk_g2s(mABKt + (long)c * D.abk_stride, P.ABKt + (aslot + c) * D.abk_stride, (uint32_t)(D.abk_stride * sizeof(double)), cbar + c);
+    };
+    auto fetch_rest = [&](long i0) {
+      const long kslot = D.per_node ? i0 : t;
+      spk_mbar_expect_tx(bar, 2 * bytes_k + bytes_r);
+      spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
+      spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
+      spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
+    };
+    if ((long)blockIdx.x < count) {
+      if (tid == 0) {
+        for (int c = 0; c < D_; ++c) fetch_child(first0 + blockIdx.x, c);
+        fetch_rest(first0 + blockIdx.x);
+      }
+      stage_raw(first0 + blockIdx.x);
+    }
+    uint32_t cph = 0;  // bit c: phase of child barrier c
+    const bool activeA = tid < NX_ * cSA;
+    for (long p = blockIdx.x; p < count; p += gridDim.x) {
+      const long i0 = first0 + p;
+      const long cfirst = (long)d * i0 + 1;
+      const bool fresh = D.per_node || p == (long)blockIdx.x, more = D.per_node && p + gridDim.x < count;
+      spk_cp_async_wait_all();
+      SPK_SYNCTHREADS();
+      // ---- P0 (as below)
+      for (int k = tid; k < nu; k += T) {
+        double val = rv7[nx + k];
+        for (int c = 0; c < d; ++c) val += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, rv4 + c * nu);
+        tu[k] = rzu[k] - gamma * val;
+      }
+      for (int k = tid; k < nx; k += T) {
+        double val = rv7[k];
+        for (int c = 0; c < d; ++c) val += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, rv3 + c * nx);
+        tx[k] = rzx[k] - gamma * val;
+      }
+      for (int idx = tid; idx < d * nx; idx += T) {
+        if (leaves) {
+          const int c = (idx == tid) ? qc_c : idx / nx, k = (idx == tid) ? qc_k : idx - (idx / nx) * nx;
+          const double val = rv14[idx] + spk_cost_row(spk_sqrtQN(D, P, cfirst + c - D.nnl), D.cost_dense, nx, k, rv11 + c * nx);
+          qc[idx] = -(rq[idx] - gamma * val);
+        } else {
+          qc[idx] = rq[idx];
+        }
+      }
+      SPK_SYNCTHREADS();
+      if (p + gridDim.x < count) stage_raw(i0 + gridDim.x);
+      // ---- P1: sum_c B_w' q_c from the L1-resident table, then sum_c ABK_c' q_c child by child
+      for (int o = tid; o < nu * SB; o += T) {
+        const SpkItem it = (o == tid) ? itB : spk_make_item(o, nu, SB, nx, nu);
+        double acc = 0.0;
+        for (int c = 0; c < d; ++c)
+          acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_child_mode_dev(d, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
+        partB[o] = acc;
+      }
+      double accA = 0.0;
+#pragma unroll
+      for (int c = 0; c < D_; ++c) {
+        if (fresh) {
+          spk_mbar_wait(cbar + c, (cph >> c) & 1u);
+          cph ^= 1u << c;
+        }
+        if (activeA) accA += spk_dot_fixed<PER_AX>(mABKt + (long)c * D.abk_stride + itA.r, NX_, qc + c * NX_, itA.m0, NX_);
+        if (c == D_ - 1 && activeA) partA[tid] = accA;
+        SPK_SYNCTHREADS();  // ABK_c' is consumed (after the last child: partA, partB complete)
+        if (more && tid == 0) fetch_child(i0 + gridDim.x, c);
+      }
+      if (fresh) {
+        spk_mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      // ---- P2+P3
+      for (int k = lane; k < nu; k += WL) {
+        double s2 = 0.0;
+        for (int sl = 0; sl < SB; ++sl) s2 += partB[sl * nu + k];
+        wrhs[k] = tu[k] - s2;
+      }
+      SPK_SYNCWARP();
+      for (int k = lane; k < nu; k += WL) {
+        const double acc = spk_dot_any<NU_>(mRinv + k, nu, wrhs, 0, nu, nu);
+        wdv[k] = acc;
+        wdmt[k] = acc - tu[k];
+        if (warp == 0) A.dd[i0 * nu + k] = acc;
+      }
+      SPK_SYNCWARP();
+      // ---- P4
+      if (activeA)
+        partA[tid] += spk_dot_any<PER_AU>(mG + itA.r, nx, wdv, itA.k0, itA.k1, nu) + spk_dot_any<PER_AU>(mKt + itA.r, nx, wdmt, itA.k0, itA.k1, nu);
+      SPK_SYNCTHREADS();
+      if (more && tid == 0) fetch_rest(i0 + gridDim.x);
+      // ---- P5
+      for (int r = tid; r < nx; r += T) {
+        double acc = 0.0;
+        for (int sl = 0; sl < SA; ++sl) acc += partA[sl * nx + r];
+        A.q[i0 * nx + r] = acc - tx[r];
+      }
+      SPK_SYNCTHREADS();
+    }
+    return;
+  }
   if ((long)blockIdx.x < count) {
     if (tid == 0) fetch(first0 + blockIdx.x);
     stage_raw(first0 + blockIdx.x);
@@ -392,6 +503,14 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   // family-independent work item of this thread: row r of [K; ABK_0; ..; ABK_{d-1}] and an inner-dimension slice
   const SpkItem it0 = spk_make_item(tid, R, S, nx, nu);
   const int c0 = it0.r < nu ? 0 : (it0.r - nu) / nx, rr0 = it0.r < nu ? it0.r : (it0.r - nu) - c0 * nx;
+  // SPLIT (specialised shapes with two inner slices): the factors arrive as two column halves on two mbarriers and the
+  // mat-vec runs half by half, so that a half is re-fetched for the next family while the other half is still being
+  // consumed -- ncu showed 57 % of the stall samples of the single-buffer version on the wait for the whole fetch.
+  constexpr int HC = spk_cper(NX_, 2);  // columns of the first half
+  constexpr bool SPLIT = !SPK_EMU && NX_ > 0 && cS == 2 && (HC * NX_) % 2 == 0 && (HC * NU_) % 2 == 0 &&
+                         ((NX_ - HC) * NX_) % 2 == 0 && ((NX_ - HC) * NU_) % 2 == 0 &&
+                         NX_ * NX_ * 8 >= 16 * 1024;  // measured: no gain (slightly slower) with a few KB per family
+  if (SPLIT && tid == 0) spk_mbar_init(bar + 1, 1);
   SPK_SYNCTHREADS();
   uint32_t phase = 0;
   auto fetch = [&](long i0) {
@@ -406,6 +525,66 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     for (int k = tid; k < nx; k += T) spk_cp_async8(dst + k, (t == 0) ? P.x0 + k : A.zbar + i0 * nx + k);
     for (int k = tid; k < nu; k += T) spk_cp_async8(dst + nx + k, A.dd + i0 * nu + k);
   };
+  if constexpr (SPLIT) {
+    auto fetch_half = [&](long i0, int hf) {  // columns [0, HC) or [HC, nx) of ABK_0..ABK_{d-1} and K
+      const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+      const int c0h = hf ? HC : 0, nc = hf ? NX_ - HC : HC;
+      uint64_t *br = bar + hf;
+      spk_mbar_expect_tx(br, (uint32_t)((D_ * NX_ + NU_) * nc * sizeof(double)));
+      for (int c = 0; c < D_; ++c)
+        spk_bulk_g2s(mABK + (long)c * D.abk_stride + c0h * NX_, P.ABK + (aslot + c) * D.abk_stride + c0h * NX_,
+                     (uint32_t)(nc * NX_ * sizeof(double)), br);
+      spk_bulk_g2s(mK + c0h * NU_, P.K + kslot * D.k_stride + c0h * NU_, (uint32_t)(nc * NU_ * sizeof(double)), br);
+    };
+    constexpr int PA = spk_cper(HC, 2), PB = spk_cper(NX_ - HC, 2);  // columns per sub-slice of each half
+    const int ss = tid / R, r = tid - ss * R;                       // this thread's item: row r, sub-slice ss of both halves
+    const bool active = tid < 2 * R;
+    const int c = r < NU_ ? 0 : (r - NU_) / NX_, rr = r < NU_ ? r : (r - NU_) - c * NX_;
+    const int k0 = ss * PER_U;
+    uint32_t ph0 = 0, ph1 = 0;
+    if ((long)blockIdx.x < count) {
+      if (tid == 0) { fetch_half(first0 + blockIdx.x, 0); fetch_half(first0 + blockIdx.x, 1); }
+      stage_raw(first0 + blockIdx.x, 0);
+    }
+    spk_cp_async_commit();
+    int buf = 0;
+    for (long p = blockIdx.x; p < count; p += gridDim.x, buf ^= 1) {
+      const long i0 = first0 + p;
+      const long cfirst = (long)d * i0 + 1;
+      const bool fresh = D.per_node || p == (long)blockIdx.x, more = D.per_node && p + gridDim.x < count;
+      if (p + gridDim.x < count) stage_raw(i0 + gridDim.x, buf ^ 1);  // one family ahead
+      spk_cp_async_commit();
+      spk_cp_async_wait_prev();  // this family's entries have landed
+      SPK_SYNCTHREADS();
+      const double *xb = raw0 + (long)buf * (nx + nu), *ds = xb + nx;
+      if (t == 0)
+        for (int k = tid; k < nx; k += T) A.zbar[k] = xb[k];
+      if (fresh) { spk_mbar_wait(bar, ph0); ph0 ^= 1; }
+      double acc = 0.0;
+      if (active) {  // first column half; rows 0..nu-1: K x_i (:670); rows nu + c*nx + rr: ABK_c x_i + B_w d_i (:675-679)
+        if (r < NU_) acc = spk_dot_fixed<PA>(mK + rr, NU_, xb, ss * PA, HC);
+        else acc = spk_dot_fixed<PA>(mABK + (long)c * D.abk_stride + rr, NX_, xb, ss * PA, HC) +
+                   spk_dot_fixed<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, NX_, ds, k0, NU_);
+      }
+      SPK_SYNCTHREADS();  // the first half is consumed: refill it while the second half is processed
+      if (more && tid == 0) fetch_half(i0 + gridDim.x, 0);
+      if (fresh) { spk_mbar_wait(bar + 1, ph1); ph1 ^= 1; }
+      if (active) {
+        if (r < NU_) acc += spk_dot_fixed<PB>(mK + rr, NU_, xb, HC + ss * PB, NX_);
+        else acc += spk_dot_fixed<PB>(mABK + (long)c * D.abk_stride + rr, NX_, xb, HC + ss * PB, NX_);
+        part[tid] = acc;
+      }
+      SPK_SYNCTHREADS();
+      if (more && tid == 0) fetch_half(i0 + gridDim.x, 1);
+      for (int r2 = tid; r2 < R; r2 += T) {
+        const double sum = part[r2] + part[R + r2];
+        if (r2 < nu) A.zbar[D.zo[1] + i0 * nu + r2] = sum + ds[r2];  // :671-673
+        else A.zbar[cfirst * nx + (r2 - nu)] = sum;
+      }
+      SPK_SYNCTHREADS();
+    }
+    return;
+  }
   if ((long)blockIdx.x < count) {
     if (tid == 0) fetch(first0 + blockIdx.x);
     stage_raw(first0 + blockIdx.x, 0);
