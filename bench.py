@@ -35,9 +35,9 @@ WORKLOADS = {
     "small": ("random", 12, 2, 50, 20, "development size: random N=12 d=2 nx=50 nu=20, 4095 nodes"),
 }
 CPU_SAMPLE_N = {"config3": 14, "config3_half": 14, "heat15": 12, "config5_slice": 8, "config5": 8, "config5_n12": 8, "small": 10}
-# DRAM traffic of the dominant kernel from `ncu --set full` (profiles/r01e_bwd_config3_ncu.txt): deepest-level launch
-# (262144 of the 524287 families) read 16.770 GB + wrote 0.152 GB; scaled to all level launches of one pass
-NCU_TRAFFIC = {("config3", "per_node"): (16.769877e9 + 0.152440832e9) * 524287 / 262144}
+# DRAM traffic of the dominant kernel from `ncu --set full` (profiles/r01f_bwd_config3_ncu.txt): deepest-level launch
+# (262144 of the 524287 families) read 16.749 GB + wrote 0.152 GB; scaled to all level launches of one pass
+NCU_TRAFFIC = {("config3", "per_node"): (16.749308e9 + 0.152153344e9) * 524287 / 262144}
 
 
 DMMA_PEAK_TFLOPS = 37.1  # mma.sync.m8n8k4.f64, measured (tools/microbench/dmma_bench.cu)
@@ -315,7 +315,7 @@ def main():
             "bound": "hbm", "kernel": "spk_k_bwd (backward S1 sweep: all N-1 level launches of one pass)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "traffic": (NCU_TRAFFIC.get((args.workload, args.factor_mode)) / world) if NCU_TRAFFIC.get((args.workload, args.factor_mode)) else None,
-            "traffic_source": "ncu --set full, deepest-level launch scaled to one pass (profiles/r01e_bwd_config3_ncu.txt)"
+            "traffic_source": "ncu --set full, deepest-level launch scaled to one pass (profiles/r01f_bwd_config3_ncu.txt)"
             if NCU_TRAFFIC.get((args.workload, args.factor_mode)) else None,
             "peak_source": peak_src,
             "algorithmic_bytes_per_pass": b_bwd / world, "avg_launch_ms": bwd["ms"] / max(bwd["launches"], 1),
