@@ -82,6 +82,12 @@ struct SpkComm {
     if (rc != 0) { err = std::string("ncclAllReduce: ") + (errstr ? errstr(rc) : "?"); return false; }
     return true;
   }
+  bool allreduce_sum(double *buf, int n, spk_stream_t s, std::string &err) {
+    if (world <= 1) return true;
+    const int rc = allreduce(buf, buf, (size_t)n, 8, 0 /*ncclSum*/, comm, s);
+    if (rc != 0) { err = std::string("ncclAllReduce: ") + (errstr ? errstr(rc) : "?"); return false; }
+    return true;
+  }
   void destroy() {
     if (comm && destroy_fn) destroy_fn(comm);
     comm = nullptr;
@@ -161,6 +167,18 @@ struct SpkComm {
       double mx = seg->data[k];
       for (int g = 1; g < world; ++g) mx = seg->data[(long)g * n + k] > mx ? seg->data[(long)g * n + k] : mx;
       buf[k] = mx;
+    }
+    barrier();
+    return true;
+  }
+  bool allreduce_sum(double *buf, int n, spk_stream_t, std::string &) {  // fixed rank order: deterministic
+    if (world <= 1) return true;
+    memcpy(seg->data + (long)rank * n, buf, sizeof(double) * n);
+    barrier();
+    for (int k = 0; k < n; ++k) {
+      double sm = 0.0;
+      for (int g = 0; g < world; ++g) sm += seg->data[(long)g * n + k];
+      buf[k] = sm;
     }
     barrier();
     return true;

@@ -428,12 +428,14 @@ SPK_KERNEL void spk_k_add_scalar(double *x, long idx, double a) {
 // Deterministic two-stage reductions: stage 1 writes one partial per block (fixed grid, fixed tree),
 // stage 2 (one block) folds the partials in a fixed order.
 // mode 0: sum x[i]*y[i]; mode 1: max |x[i]|; mode 2: sum x[i]
+// mask (may be NULL): only entries with mask[i] != 0 take part -- the entries this rank counts under the subtree partition
 SPK_KERNEL void spk_k_reduce_partial(long n, int mode, const double *__restrict__ x, const double *__restrict__ y,
-                                     double *__restrict__ partial) {
+                                     double *__restrict__ partial, const unsigned char *__restrict__ mask) {
   SPK_SMEM_DECL(double, sm);
   const long stride = (long)gridDim.x * blockDim.x;
   double acc = 0.0;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (mask && !mask[i]) continue;
     if (mode == 0) acc += x[i] * y[i];
     else if (mode == 2) acc += x[i];
     else { const double a = fabs(x[i]); acc = a > acc ? a : acc; }

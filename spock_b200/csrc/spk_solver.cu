@@ -181,6 +181,10 @@ struct spk_handle {
   double sp_graph_gamma = 0, sp_graph_sigma = 0;
   int64_t sp_graph_kernels = 0;
 #endif
+  // SuperMann over the subtree partition: entries this rank counts in the global sums / maxima (1 byte per entry of (z|v)),
+  // and which scalar slots hold a rank-local value that the next fetch must all-reduce (1 = sum, 2 = max)
+  unsigned char *d_mask = nullptr;
+  int slot_dirty[32] = {0};
   // reductions
   double *d_partial = nullptr, *d_scal = nullptr;
   double h_scal[32];
@@ -323,13 +327,16 @@ static int op_axpby(spk_handle *h, long n, double a, const double *x, double b, 
 }
 
 // mode 0: d_scal[slot] (+)= sum x.*y ; mode 1: d_scal[slot] = max|x|
-static int op_reduce(spk_handle *h, long n, int mode, const double *x, const double *y, int slot, int accumulate) {
+// moff: offset of x[0] inside the (z|v) index space (selects the part of the ownership mask; multi-rank SuperMann only)
+static int op_reduce(spk_handle *h, long n, int mode, const double *x, const double *y, int slot, int accumulate, long moff = 0) {
   ProfScope ps(h, PC_VEC);
   const int blk = SPK_EMU ? 1 : 256;
   long g = (n + blk - 1) / blk;
   if (g > h->red_blocks) g = h->red_blocks;
   if (g < 1) g = 1;
-  SPK_LAUNCH(spk_k_reduce_partial, (unsigned)g, blk, blk * sizeof(double), h->stream, n, mode, x, y, h->d_partial);
+  const unsigned char *mask = (h->d_mask && mode != 2) ? h->d_mask + moff : nullptr;
+  if (h->world > 1) h->slot_dirty[slot] = (mode == 1) ? 2 : 1;
+  SPK_LAUNCH(spk_k_reduce_partial, (unsigned)g, blk, blk * sizeof(double), h->stream, n, mode, x, y, h->d_partial, mask);
   SPK_LAUNCH(spk_k_reduce_final, 1, blk, blk * sizeof(double), h->stream, (int)g, mode, h->d_partial, h->d_scal, slot,
              accumulate);
   COUNT_LAUNCH(h, PC_VEC);
@@ -337,9 +344,17 @@ static int op_reduce(spk_handle *h, long n, int mode, const double *x, const dou
   return rt_launch_check();
 }
 static int fetch_scalars(spk_handle *h, int count) {
-  if (h->world > 1) {  // xi1, xi2 are maxima over the ranks' owned families
+  if (h->world > 1) {
     std::string cerr;
-    if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+    if (h->alg == SPK_CP) {  // xi1, xi2 are maxima over the ranks' owned families (left in d_scal[0..1] by the dual kernels)
+      if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+    } else {  // SuperMann: every slot reduced since the last fetch holds a rank-local sum / maximum
+      for (int k = 0; k < count && k < 32; ++k) {
+        if (h->slot_dirty[k] == 1 && !h->comm.allreduce_sum(h->d_scal + k, 1, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+        if (h->slot_dirty[k] == 2 && !h->comm.allreduce_max(h->d_scal + k, 1, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+        h->slot_dirty[k] = 0;
+      }
+    }
   }
   return rt_d2h(h->h_scal, h->d_scal, sizeof(double) * count, h->stream);
 }
@@ -718,13 +733,15 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
         if (b <= a) continue;
         SpkFusedArgs A2 = A;
         A2.children_are_leaves = part;
-        A2.pnorm = A.pnorm ? A.pnorm + pn_off : nullptr;
+        // <r, P r> of the replicated families above the cut is counted by rank 0 only
+        const bool count_pn = A.pnorm && !(h->world > 1 && h->rank != 0 && h->t_cut > 0 && r == 0);
+        A2.pnorm = count_pn ? A.pnorm + pn_off : nullptr;
         long g;
 #ifndef SPK_HOST_EMU
         if (h->k_dual3[part][0]) {  // 4c. one group of lanes per family, everything in registers
           const long fpc = 4L * (32 / spk_dual3_group(D.nx, D.nu, D.d));  // families per CTA (4 warps)
           g = (b - a + fpc - 1) / fpc;
-          spk_dual3_kernel_t k3 = h->k_dual3[part][A.pnorm ? 1 : 0];
+          spk_dual3_kernel_t k3 = h->k_dual3[part][A2.pnorm ? 1 : 0];
           k3<<<(unsigned)g, 128, 0, h->stream>>>(D, h->P, A2, a, b - a);
         } else
 #endif
@@ -736,7 +753,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
           SPK_LAUNCH(kfn, (unsigned)g, T, h->dual2_smem, h->stream, D, h->P, A2, h->dual2_F, a, b - a);
         }
         COUNT_LAUNCH(h, PC_PROX_H);
-        pn_off += g;
+        if (count_pn) pn_off += g;
       }
     }
     pn_parts = pn_off;
@@ -796,6 +813,7 @@ static int graph_segment(spk_handle *h, const double *zv_in, double *zv_out, dou
 // node costs a fraction of a stream launch.  With several GPUs the two kernel segments around the cut-level exchange are
 // separate graphs and the NCCL all-gathers are issued on the stream between them (a collective inside a capture hung).
 static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot) {
+  if (h->world > 1 && pnorm_slot >= 0) h->slot_dirty[pnorm_slot] = 1;  // (a graph replay does not pass through op_reduce)
 #ifndef SPK_HOST_EMU
   if (h->use_graphs && !h->prof_on) {
     if (h->world == 1) return graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 15);
@@ -832,7 +850,7 @@ static int launch_termination(spk_handle *h, const LoopState &S) {
   SPK_TRY(op_Lt(h, h->dzv + nz, 1.0, -1.0 / S.gamma, h->dzv, h->xi12));               // xi_1 = L'dv - dz/gamma
   SPK_TRY(op_L(h, h->dzv, 1.0, -1.0 / S.sigma, h->dzv + nz, h->xi12 + nz));           // xi_2 = L dz - dv/sigma
   SPK_TRY(op_reduce(h, nz, 1, h->xi12, nullptr, 0, 0));
-  SPK_TRY(op_reduce(h, nv, 1, h->xi12 + nz, nullptr, 1, 0));
+  SPK_TRY(op_reduce(h, nv, 1, h->xi12 + nz, nullptr, 1, 0, nz));
   if (S.verbose_log && h->alg == SPK_CP) {  // cp.jl:82-86
     SPK_TRY(op_Lt(h, h->xi12 + nz, 1.0, 1.0, h->xi12, h->xi));
     SPK_TRY(op_reduce(h, nz, 1, h->xi, nullptr, 2, 0));
@@ -1121,7 +1139,6 @@ static int check_problem(const spk_problem *p) {
   if (p->world_size > 1) {
     if (!p->comm_id) return fail(SPK_ERR_INVALID, "world_size > 1 needs comm_id (spk_comm_unique_id)");
     if (p->rank < 0 || p->rank >= p->world_size) return fail(SPK_ERR_INVALID, "rank out of range");
-    if (p->algorithm != SPK_CP) return fail(SPK_ERR_INVALID, "the subtree partition supports the CP algorithm only");
   }
   double dn = 1.0;
   for (int k = 0; k < p->N; ++k) dn *= p->d;
@@ -1285,6 +1302,40 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
     h->m_sub = spk_level_count(d, tc) / h->world;
     std::string cerr;
     if (!h->comm.init(h->rank, h->world, p->comm_id, cerr)) return fail(SPK_ERR_COMM, cerr);
+  }
+  if (h->world > 1 && h->alg == SPK_SP) {
+    // Entries of (z|v) this rank counts in SuperMann's global sums and maxima: those of its owned families, and of the
+    // replicated families above the cut on rank 0 only.  Family i counts x_i, u_i, y_i, s_i, tau of its children, x and s
+    // of its leaf children, and its dual blocks (the partition the dual kernel uses for <r, P r>); every operand of L / L'
+    // at such an entry is valid on the counting rank.
+    std::vector<unsigned char> mask((size_t)nr, 0);
+    SpkFusedArgs R;
+    fill_ranges(h, R);
+    for (int k = 0; k < R.n_ranges; ++k) {
+      if (k == 0 && h->t_cut > 0 && h->rank != 0) continue;
+      const long lo = R.r_start[k], cnt = R.r_prefix[k + 1] - R.r_prefix[k];
+      for (long i0 = lo; i0 < lo + cnt; ++i0) {
+        const long c0 = (long)d * i0 + 1;
+        auto setz = [&](long a, long len) { std::fill(mask.begin() + a, mask.begin() + a + len, 1); };
+        auto setv = [&](long a, long len) { std::fill(mask.begin() + D.nz + a, mask.begin() + D.nz + a + len, 1); };
+        setz(i0 * nx, nx); setz(D.zo[1] + i0 * nu, nu); setz(D.zo[4] + i0 * ny, ny); setz(D.zo[2] + i0, 1);
+        setz(D.zo[3] + c0 - 1, d);
+        setv(i0 * ny, ny); setv(D.vo[1] + i0, 1); setv(D.vo[6] + i0 * (nx + nu), nx + nu);
+        setv(D.vo[2] + (c0 - 1) * nx, (long)d * nx); setv(D.vo[3] + (c0 - 1) * nu, (long)d * nu);
+        setv(D.vo[4] + c0 - 1, d); setv(D.vo[5] + c0 - 1, d);
+        if (c0 >= nnl) {
+          const long l0 = c0 - nnl;
+          setz(c0 * nx, (long)d * nx); setz(D.zo[2] + c0, d);
+          setv(D.vo[7] + l0 * nx, (long)d * nx); setv(D.vo[8] + l0, d); setv(D.vo[9] + l0, d); setv(D.vo[10] + l0 * nx, (long)d * nx);
+        }
+      }
+    }
+    void *q = nullptr;
+    SPK_TRY(rt_malloc(&q, (size_t)nr));
+    h->allocs.push_back(q);
+    h->bytes += nr;
+    h->d_mask = (unsigned char *)q;
+    SPK_TRY(rt_h2d(h->d_mask, mask.data(), (size_t)nr, h->stream));
   }
   h->res_0[0] = h->res_0[1] = -INFINITY;
   {

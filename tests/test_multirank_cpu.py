@@ -9,7 +9,7 @@ import threading
 import numpy as np
 import pytest
 
-from oracle.oracle import CP
+from oracle.oracle import CP, SP
 from spock_b200 import _lib
 from spock_b200.handle import Handle
 from tests.helpers import flat_of, relerr
@@ -22,13 +22,18 @@ def _comm_id(lib):
     return np.frombuffer(bytes(raw), dtype=np.uint8).copy()
 
 
-def _run_rank(lib, flat, fm, rank, world, cid, K, out):
+def _run_rank(lib, flat, fm, rank, world, cid, K, out, alg=CP):
     try:
-        h = Handle(flat, CP, factor_mode=fm, rank=rank, world_size=world, comm_id=cid, lib=lib)
+        h = Handle(flat, alg, factor_mode=fm, rank=rank, world_size=world, comm_id=cid, lib=lib)
         h.set_x0(0.1 * np.ones(flat.nx))
         h.step(K)
         z, v = h.get_iterate()
-        out[rank] = (h.owned_ranges(), z, v, h.residuals(), h.z_off, h.v_off)
+        xi = h.residuals()
+        extra = None
+        if alg == SP:  # then solve_model! to tolerance from this point: every rank must take the same decisions
+            res, log = h.solve(0.1 * np.ones(flat.nx), tol=1e-4)
+            extra = (res["passes"], res["converged"], res["k1_count"], res["k2_count"], res["fallback_count"], log["xi1"].copy())
+        out[rank] = (h.owned_ranges(), z, v, xi, h.z_off, h.v_off, extra)
         h.close()
     except Exception as e:  # surface the failure in the main thread
         out[rank] = e
@@ -64,6 +69,38 @@ def test_partition_matches_single_rank_threads(emu_lib, name, world):
         for first, count in out[g][0]:
             owned[first - 1: first - 1 + count] += 1
     assert owned.min() >= 1 and (owned[owned > 1] == world).all()
+
+
+@pytest.mark.parametrize("name,world", [("heat_N7_d2_nx5", 2), ("heat_N7_d2_nx5", 4), ("l2ball_N4_d3_nx3", 3),
+                                        ("random_N5_d2_nx6_nu3", 4)])
+def test_supermann_over_the_partition_threads(emu_lib, name, world):
+    """SuperMann over the subtree partition: the global sums (P-norms, Anderson's Gram-Schmidt dots, the K2 inner product)
+    and maxima are reduced over each rank's counted entries and all-reduced; the assembled iterate after K passes equals
+    the single-rank one up to the rounding of the re-associated sums."""
+    flat = flat_of(name)
+    K = 12
+    ref = Handle(flat, SP, lib=emu_lib)
+    ref.set_x0(0.1 * np.ones(flat.nx))
+    ref.step(K)
+    zr, vr = ref.get_iterate()
+    xr = ref.residuals()
+    cid = _comm_id(emu_lib)
+    out = {}
+    threads = [threading.Thread(target=_run_rank, args=(emu_lib, flat, g % 2, g, world, cid, K, out, SP)) for g in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(180)
+    for g in range(world):
+        assert g in out and not isinstance(out[g], Exception), out.get(g)
+    z, v, worst = assemble(flat, out[0][4], out[0][5], [(out[g][0], out[g][1], out[g][2]) for g in range(world)])
+    assert worst < 1e-9
+    assert relerr(z, zr) < 1e-9 and relerr(v, vr) < 1e-9
+    for g in range(world):
+        assert abs(out[g][3][0] - xr[0]) < 1e-7 * xr[0] and abs(out[g][3][1] - xr[1]) < 1e-7 * xr[1]
+    for g in range(1, world):  # identical stopping pass, branch counts and residual trace on every rank
+        assert out[g][6][:5] == out[0][6][:5] and out[0][6][1] == 1
+        assert np.array_equal(out[g][6][5], out[0][6][5])
 
 
 def test_uneven_split_is_rejected(emu_lib):
