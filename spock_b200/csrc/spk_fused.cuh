@@ -284,121 +284,42 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   // (G, K', Rinv) -- and the ABK' mat-vec runs child by child, so that a child's matrix is re-fetched for the next family as
   // soon as it is consumed instead of after the whole family (see spk_k_fwd_s1).
   constexpr bool SPLIT = !SPK_EMU && NX_ > 0 && D_ <= 4 && NX_ * NX_ * 8 >= 16 * 1024 && NX_ * spk_cslices(T_, NX_) <= T_;
+  uint64_t *cbar = reinterpret_cast<uint64_t *>(rv11 + (long)d * nx);  // SPLIT: D_ barriers in the 4 spare doubles behind the staging
   if constexpr (SPLIT) {
-    uint64_t *cbar = reinterpret_cast<uint64_t *>(rv11 + (long)d * nx);  // D_ barriers in the 4 spare doubles behind the staging
     if (tid == 0)
       for (int c = 0; c < D_; ++c) spk_mbar_init(cbar + c, 1);
     SPK_SYNCTHREADS();
-    auto fetch_child = [&](long i0, int c) {
-      const long aslot = D.per_node ? (long)d * i0 : (long)t * d;
-      spk_mbar_expect_tx(cbar + c, (uint32_t)(D.abk_stride * sizeof(double)));
-      spk_bulk_g2s(mABKt + (long)c * D.abk_stride, P.ABKt + (aslot + c) * D.abk_stride, (uint32_t)(D.abk_stride * sizeof(double)), cbar + c);
-    };
-    auto fetch_rest = [&](long i0) {
-      const long kslot = D.per_node ? i0 : t;
-      spk_mbar_expect_tx(bar, 2 * bytes_k + bytes_r);
-      spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
-      spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
-      spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
-    };
-    if ((long)blockIdx.x < count) {
-      if (tid == 0) {
+  }
+  auto fetch_child = [&](long i0, int c) {
+    const long aslot = D.per_node ? (long)d * i0 : (long)t * d;
+    spk_mbar_expect_tx(cbar + c, (uint32_t)(D.abk_stride * sizeof(double)));
+    spk_bulk_g2s(mABKt + (long)c * D.abk_stride, P.ABKt + (aslot + c) * D.abk_stride, (uint32_t)(D.abk_stride * sizeof(double)), cbar + c);
+  };
+  auto fetch_rest = [&](long i0) {
+    const long kslot = D.per_node ? i0 : t;
+    spk_mbar_expect_tx(bar, 2 * bytes_k + bytes_r);
+    spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
+    spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
+    spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
+  };
+  if ((long)blockIdx.x < count) {
+    if (tid == 0) {
+      if constexpr (SPLIT) {
         for (int c = 0; c < D_; ++c) fetch_child(first0 + blockIdx.x, c);
         fetch_rest(first0 + blockIdx.x);
+      } else {
+        fetch(first0 + blockIdx.x);
       }
-      stage_raw(first0 + blockIdx.x);
     }
-    uint32_t cph = 0;  // bit c: phase of child barrier c
-    const bool activeA = tid < NX_ * cSA;
-    for (long p = blockIdx.x; p < count; p += gridDim.x) {
-      const long i0 = first0 + p;
-      const long cfirst = (long)d * i0 + 1;
-      const bool fresh = D.per_node || p == (long)blockIdx.x, more = D.per_node && p + gridDim.x < count;
-      spk_cp_async_wait_all();
-      SPK_SYNCTHREADS();
-      // ---- P0 (as below)
-      for (int k = tid; k < nu; k += T) {
-        double val = rv7[nx + k];
-        for (int c = 0; c < d; ++c) val += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, rv4 + c * nu);
-        tu[k] = rzu[k] - gamma * val;
-      }
-      for (int k = tid; k < nx; k += T) {
-        double val = rv7[k];
-        for (int c = 0; c < d; ++c) val += spk_cost_row(spk_sqrtQ(D, P, cfirst + c), D.cost_dense, nx, k, rv3 + c * nx);
-        tx[k] = rzx[k] - gamma * val;
-      }
-      for (int idx = tid; idx < d * nx; idx += T) {
-        if (leaves) {
-          const int c = (idx == tid) ? qc_c : idx / nx, k = (idx == tid) ? qc_k : idx - (idx / nx) * nx;
-          const double val = rv14[idx] + spk_cost_row(spk_sqrtQN(D, P, cfirst + c - D.nnl), D.cost_dense, nx, k, rv11 + c * nx);
-          qc[idx] = -(rq[idx] - gamma * val);
-        } else {
-          qc[idx] = rq[idx];
-        }
-      }
-      SPK_SYNCTHREADS();
-      if (p + gridDim.x < count) stage_raw(i0 + gridDim.x);
-      // ---- P1: sum_c B_w' q_c from the L1-resident table, then sum_c ABK_c' q_c child by child
-      for (int o = tid; o < nu * SB; o += T) {
-        const SpkItem it = (o == tid) ? itB : spk_make_item(o, nu, SB, nx, nu);
-        double acc = 0.0;
-        for (int c = 0; c < d; ++c)
-          acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_child_mode_dev(d, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
-        partB[o] = acc;
-      }
-      double accA = 0.0;
-#pragma unroll
-      for (int c = 0; c < D_; ++c) {
-        if (fresh) {
-          spk_mbar_wait(cbar + c, (cph >> c) & 1u);
-          cph ^= 1u << c;
-        }
-        if (activeA) accA += spk_dot_fixed<PER_AX>(mABKt + (long)c * D.abk_stride + itA.r, NX_, qc + c * NX_, itA.m0, NX_);
-        if (c == D_ - 1 && activeA) partA[tid] = accA;
-        SPK_SYNCTHREADS();  // ABK_c' is consumed (after the last child: partA, partB complete)
-        if (more && tid == 0) fetch_child(i0 + gridDim.x, c);
-      }
-      if (fresh) {
-        spk_mbar_wait(bar, phase);
-        phase ^= 1;
-      }
-      // ---- P2+P3
-      for (int k = lane; k < nu; k += WL) {
-        double s2 = 0.0;
-        for (int sl = 0; sl < SB; ++sl) s2 += partB[sl * nu + k];
-        wrhs[k] = tu[k] - s2;
-      }
-      SPK_SYNCWARP();
-      for (int k = lane; k < nu; k += WL) {
-        const double acc = spk_dot_any<NU_>(mRinv + k, nu, wrhs, 0, nu, nu);
-        wdv[k] = acc;
-        wdmt[k] = acc - tu[k];
-        if (warp == 0) A.dd[i0 * nu + k] = acc;
-      }
-      SPK_SYNCWARP();
-      // ---- P4
-      if (activeA)
-        partA[tid] += spk_dot_any<PER_AU>(mG + itA.r, nx, wdv, itA.k0, itA.k1, nu) + spk_dot_any<PER_AU>(mKt + itA.r, nx, wdmt, itA.k0, itA.k1, nu);
-      SPK_SYNCTHREADS();
-      if (more && tid == 0) fetch_rest(i0 + gridDim.x);
-      // ---- P5
-      for (int r = tid; r < nx; r += T) {
-        double acc = 0.0;
-        for (int sl = 0; sl < SA; ++sl) acc += partA[sl * nx + r];
-        A.q[i0 * nx + r] = acc - tx[r];
-      }
-      SPK_SYNCTHREADS();
-    }
-    return;
-  }
-  if ((long)blockIdx.x < count) {
-    if (tid == 0) fetch(first0 + blockIdx.x);
     stage_raw(first0 + blockIdx.x);
   }
+  uint32_t cph = 0;     // SPLIT: bit c = phase of child barrier c
   bool pending = true;  // a fetch is in flight / not yet consumed
   for (long p = blockIdx.x; p < count; p += gridDim.x) {
     const long i0 = first0 + p;
     const long cfirst = (long)d * i0 + 1;  // first child (0-based node), children are consecutive
+    const bool fresh = D.per_node || p == (long)blockIdx.x;   // this family's factors are (still) in flight
+    const bool more = D.per_node && p + gridDim.x < count;    // the next family needs its own factors
     spk_cp_async_wait_all();  // this thread's raw copies have landed
     SPK_SYNCTHREADS();
     // ---- P0: (z - gamma L'v) for u_i, x_i (L_transpose! :351-373, :399-420) and the children's q, from the raw staging
@@ -431,19 +352,39 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_child_mode_dev(d, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
       partB[o] = acc;
     }
-    if (pending && (D.per_node || p == (long)blockIdx.x)) {
-      spk_mbar_wait(bar, phase);
-      phase ^= 1;
+    if constexpr (SPLIT) {  // child by child; one work item per thread (nx * SA <= T)
+      const bool activeA = tid < NX_ * cSA;
+      double accA = 0.0;
+#pragma unroll
+      for (int c = 0; c < D_; ++c) {
+        if (fresh) {
+          spk_mbar_wait(cbar + c, (cph >> c) & 1u);
+          cph ^= 1u << c;
+        }
+        if (activeA) accA += spk_dot_fixed<PER_AX>(mABKt + (long)c * D.abk_stride + itA.r, NX_, qc + c * NX_, itA.m0, NX_);
+        if (c == D_ - 1 && activeA) partA[tid] = accA;
+        SPK_SYNCTHREADS();  // ABK_c' is consumed (after the last child: partA, partB complete)
+        if (more && tid == 0) fetch_child(i0 + gridDim.x, c);
+      }
+      if (fresh) {
+        spk_mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+    } else {
+      if (pending && fresh) {
+        spk_mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      pending = false;
+      for (int o = tid; o < nx * SA; o += T) {
+        const SpkItem it = (o == tid) ? itA : spk_make_item(o, nx, SA, nx, nu);
+        double acc = 0.0;
+        for (int c = 0; c < d; ++c)
+          acc += spk_dot_any<PER_AX>(mABKt + (long)c * D.abk_stride + it.r, nx, qc + c * nx, it.m0, it.m1, nx);
+        partA[o] = acc;
+      }
+      SPK_SYNCTHREADS();
     }
-    pending = false;
-    for (int o = tid; o < nx * SA; o += T) {
-      const SpkItem it = (o == tid) ? itA : spk_make_item(o, nx, SA, nx, nu);
-      double acc = 0.0;
-      for (int c = 0; c < d; ++c)
-        acc += spk_dot_any<PER_AX>(mABKt + (long)c * D.abk_stride + it.r, nx, qc + c * nx, it.m0, it.m1, nx);
-      partA[o] = acc;
-    }
-    SPK_SYNCTHREADS();
     // ---- P2+P3, redundantly in every warp (no CTA barrier): rhs (:598-600), d_i = Rtilde^{-1} rhs (:601)
     for (int k = lane; k < nu; k += WL) {
       double s2 = 0.0;
@@ -465,8 +406,11 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     }
     SPK_SYNCTHREADS();
     // the matrices are consumed: start the next family's transfer before finishing this one
-    if (D.per_node && p + gridDim.x < count) {
-      if (tid == 0) fetch(i0 + gridDim.x);
+    if (more) {
+      if (tid == 0) {
+        if constexpr (SPLIT) fetch_rest(i0 + gridDim.x);
+        else fetch(i0 + gridDim.x);
+      }
       pending = true;
     }
     // ---- P5: q_i (:634-636)
