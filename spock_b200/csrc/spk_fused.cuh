@@ -469,76 +469,36 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     for (int k = tid; k < nx; k += T) spk_cp_async8(dst + k, (t == 0) ? P.x0 + k : A.zbar + i0 * nx + k);
     for (int k = tid; k < nu; k += T) spk_cp_async8(dst + nx + k, A.dd + i0 * nu + k);
   };
-  if constexpr (SPLIT) {
-    auto fetch_half = [&](long i0, int hf) {  // columns [0, HC) or [HC, nx) of ABK_0..ABK_{d-1} and K
-      const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
-      const int c0h = hf ? HC : 0, nc = hf ? NX_ - HC : HC;
-      uint64_t *br = bar + hf;
-      spk_mbar_expect_tx(br, (uint32_t)((D_ * NX_ + NU_) * nc * sizeof(double)));
-      for (int c = 0; c < D_; ++c)
-        spk_bulk_g2s(mABK + (long)c * D.abk_stride + c0h * NX_, P.ABK + (aslot + c) * D.abk_stride + c0h * NX_,
-                     (uint32_t)(nc * NX_ * sizeof(double)), br);
-      spk_bulk_g2s(mK + c0h * NU_, P.K + kslot * D.k_stride + c0h * NU_, (uint32_t)(nc * NU_ * sizeof(double)), br);
-    };
-    constexpr int PA = spk_cper(HC, 2), PB = spk_cper(NX_ - HC, 2);  // columns per sub-slice of each half
-    const int ss = tid / R, r = tid - ss * R;                       // this thread's item: row r, sub-slice ss of both halves
-    const bool active = tid < 2 * R;
-    const int c = r < NU_ ? 0 : (r - NU_) / NX_, rr = r < NU_ ? r : (r - NU_) - c * NX_;
-    const int k0 = ss * PER_U;
-    uint32_t ph0 = 0, ph1 = 0;
-    if ((long)blockIdx.x < count) {
-      if (tid == 0) { fetch_half(first0 + blockIdx.x, 0); fetch_half(first0 + blockIdx.x, 1); }
-      stage_raw(first0 + blockIdx.x, 0);
-    }
-    spk_cp_async_commit();
-    int buf = 0;
-    for (long p = blockIdx.x; p < count; p += gridDim.x, buf ^= 1) {
-      const long i0 = first0 + p;
-      const long cfirst = (long)d * i0 + 1;
-      const bool fresh = D.per_node || p == (long)blockIdx.x, more = D.per_node && p + gridDim.x < count;
-      if (p + gridDim.x < count) stage_raw(i0 + gridDim.x, buf ^ 1);  // one family ahead
-      spk_cp_async_commit();
-      spk_cp_async_wait_prev();  // this family's entries have landed
-      SPK_SYNCTHREADS();
-      const double *xb = raw0 + (long)buf * (nx + nu), *ds = xb + nx;
-      if (t == 0)
-        for (int k = tid; k < nx; k += T) A.zbar[k] = xb[k];
-      if (fresh) { spk_mbar_wait(bar, ph0); ph0 ^= 1; }
-      double acc = 0.0;
-      if (active) {  // first column half; rows 0..nu-1: K x_i (:670); rows nu + c*nx + rr: ABK_c x_i + B_w d_i (:675-679)
-        if (r < NU_) acc = spk_dot_fixed<PA>(mK + rr, NU_, xb, ss * PA, HC);
-        else acc = spk_dot_fixed<PA>(mABK + (long)c * D.abk_stride + rr, NX_, xb, ss * PA, HC) +
-                   spk_dot_fixed<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, NX_, ds, k0, NU_);
-      }
-      SPK_SYNCTHREADS();  // the first half is consumed: refill it while the second half is processed
-      if (more && tid == 0) fetch_half(i0 + gridDim.x, 0);
-      if (fresh) { spk_mbar_wait(bar + 1, ph1); ph1 ^= 1; }
-      if (active) {
-        if (r < NU_) acc += spk_dot_fixed<PB>(mK + rr, NU_, xb, HC + ss * PB, NX_);
-        else acc += spk_dot_fixed<PB>(mABK + (long)c * D.abk_stride + rr, NX_, xb, HC + ss * PB, NX_);
-        part[tid] = acc;
-      }
-      SPK_SYNCTHREADS();
-      if (more && tid == 0) fetch_half(i0 + gridDim.x, 1);
-      for (int r2 = tid; r2 < R; r2 += T) {
-        const double sum = part[r2] + part[R + r2];
-        if (r2 < nu) A.zbar[D.zo[1] + i0 * nu + r2] = sum + ds[r2];  // :671-673
-        else A.zbar[cfirst * nx + (r2 - nu)] = sum;
-      }
-      SPK_SYNCTHREADS();
-    }
-    return;
-  }
+  auto fetch_half = [&](long i0, int hf) {  // SPLIT: columns [0, HC) or [HC, nx) of ABK_0..ABK_{d-1} and K
+    const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+    const int c0h = hf ? HC : 0, nc = hf ? NX_ - HC : HC;
+    uint64_t *br = bar + hf;
+    spk_mbar_expect_tx(br, (uint32_t)((D_ * NX_ + NU_) * nc * sizeof(double)));
+    for (int c = 0; c < D_; ++c)
+      spk_bulk_g2s(mABK + (long)c * D.abk_stride + c0h * NX_, P.ABK + (aslot + c) * D.abk_stride + c0h * NX_,
+                   (uint32_t)(nc * NX_ * sizeof(double)), br);
+    spk_bulk_g2s(mK + c0h * NU_, P.K + kslot * D.k_stride + c0h * NU_, (uint32_t)(nc * NU_ * sizeof(double)), br);
+  };
   if ((long)blockIdx.x < count) {
-    if (tid == 0) fetch(first0 + blockIdx.x);
+    if (tid == 0) {
+      if constexpr (SPLIT) {
+        fetch_half(first0 + blockIdx.x, 0);
+        fetch_half(first0 + blockIdx.x, 1);
+      } else {
+        fetch(first0 + blockIdx.x);
+      }
+    }
     stage_raw(first0 + blockIdx.x, 0);
   }
   spk_cp_async_commit();
+  uint32_t phase1 = 0;  // SPLIT: phase of the second half's barrier
   bool pending = true;
   int buf = 0;
   for (long p = blockIdx.x; p < count; p += gridDim.x, buf ^= 1) {
     const long i0 = first0 + p;
     const long cfirst = (long)d * i0 + 1;
+    const bool fresh = D.per_node || p == (long)blockIdx.x;   // this family's factors are (still) in flight
+    const bool more = D.per_node && p + gridDim.x < count;    // the next family needs its own factors
     if (p + gridDim.x < count) stage_raw(i0 + gridDim.x, buf ^ 1);  // one family ahead
     spk_cp_async_commit();
     spk_cp_async_wait_prev();  // this family's entries have landed
@@ -546,32 +506,57 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     const double *xb = raw0 + (long)buf * (nx + nu), *ds = xb + nx;
     if (t == 0)
       for (int k = tid; k < nx; k += T) A.zbar[k] = xb[k];
-    if (pending && (D.per_node || p == (long)blockIdx.x)) {
-      spk_mbar_wait(bar, phase);
-      phase ^= 1;
-    }
-    pending = false;
     // rows 0..nu-1: K x_i (:670); rows nu + c*nx + rr: ABK_c x_i + B_w d_i (:675-679)
-    for (int o = tid; o < R * S; o += T) {
-      SpkItem it = it0;
-      int c = c0, rr = rr0;
-      if (o != tid) {
-        it = spk_make_item(o, R, S, nx, nu);
-        c = it.r < nu ? 0 : (it.r - nu) / nx;
-        rr = it.r < nu ? it.r : (it.r - nu) - c * nx;
+    if constexpr (SPLIT) {  // half by half; one work item per thread: row r, sub-slice ss of both column halves
+      constexpr int PA = spk_cper(HC, 2), PB = spk_cper(NX_ - HC, 2);
+      const int ss = tid / R, r = tid - ss * R;
+      const bool active = tid < 2 * R;
+      const int c = r < NU_ ? 0 : (r - NU_) / NX_, rr = r < NU_ ? r : (r - NU_) - c * NX_;
+      if (fresh) { spk_mbar_wait(bar, phase); phase ^= 1; }
+      double acc = 0.0;
+      if (active) {
+        if (r < NU_) acc = spk_dot_fixed<PA>(mK + rr, NU_, xb, ss * PA, HC);
+        else acc = spk_dot_fixed<PA>(mABK + (long)c * D.abk_stride + rr, NX_, xb, ss * PA, HC) +
+                   spk_dot_fixed<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, NX_, ds, ss * PER_U, NU_);
       }
-      double acc;
-      if (it.r < nu) {
-        acc = spk_dot_any<PER_X>(mK + rr, nu, xb, it.m0, it.m1, nx);
-      } else {
-        acc = spk_dot_any<PER_X>(mABK + (long)c * D.abk_stride + rr, nx, xb, it.m0, it.m1, nx) +
-              spk_dot_any<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
+      SPK_SYNCTHREADS();  // the first half is consumed: refill it while the second half is processed
+      if (more && tid == 0) fetch_half(i0 + gridDim.x, 0);
+      if (fresh) { spk_mbar_wait(bar + 1, phase1); phase1 ^= 1; }
+      if (active) {
+        if (r < NU_) acc += spk_dot_fixed<PB>(mK + rr, NU_, xb, HC + ss * PB, NX_);
+        else acc += spk_dot_fixed<PB>(mABK + (long)c * D.abk_stride + rr, NX_, xb, HC + ss * PB, NX_);
+        part[tid] = acc;
       }
-      part[o] = acc;
+    } else {
+      if (pending && fresh) {
+        spk_mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      pending = false;
+      for (int o = tid; o < R * S; o += T) {
+        SpkItem it = it0;
+        int c = c0, rr = rr0;
+        if (o != tid) {
+          it = spk_make_item(o, R, S, nx, nu);
+          c = it.r < nu ? 0 : (it.r - nu) / nx;
+          rr = it.r < nu ? it.r : (it.r - nu) - c * nx;
+        }
+        double acc;
+        if (it.r < nu) {
+          acc = spk_dot_any<PER_X>(mK + rr, nu, xb, it.m0, it.m1, nx);
+        } else {
+          acc = spk_dot_any<PER_X>(mABK + (long)c * D.abk_stride + rr, nx, xb, it.m0, it.m1, nx) +
+                spk_dot_any<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
+        }
+        part[o] = acc;
+      }
     }
     SPK_SYNCTHREADS();
-    if (D.per_node && p + gridDim.x < count) {  // matrices consumed: start the next family's transfer
-      if (tid == 0) fetch(i0 + gridDim.x);
+    if (more) {  // matrices (SPLIT: the second half) consumed: start the next family's transfer
+      if (tid == 0) {
+        if constexpr (SPLIT) fetch_half(i0 + gridDim.x, 1);
+        else fetch(i0 + gridDim.x);
+      }
       pending = true;
     }
     for (int r = tid; r < R; r += T) {
