@@ -49,6 +49,9 @@ class SolverOptions:  # model.jl:71-74
     # extensions (not in the reference): where the Riccati factors live, and an override of the hard-coded L_norm
     factor_mode: int = _lib.FACTORS_PER_NODE
     L_norm: float = 0.0
+    # estimate ||L||^2 by power iteration at build time instead of the reference's hard-coded 10.0 / 3.28
+    # (cpock.jl:62-63, spock.jl:63-64: valid for its server_heat data only); ignored when L_norm > 0
+    estimate_L_norm: bool = False
 
 
 @dataclass
@@ -91,6 +94,8 @@ class _Model:
         self.flat = flat
         self.handle = Handle(flat, int(self.algorithm), L_norm=options.L_norm, factor_mode=options.factor_mode, lib=lib)
         h = self.handle
+        if options.estimate_L_norm and not options.L_norm > 0:
+            h.estimate_L_norm(apply=True)
         self.solver_state = GenericSolverState(h.nz, h.nv, h.L_norm, np.zeros(h.nz), np.zeros(h.nv))
         zo = h.z_off + [h.nz]
         self.solver_state_internal = SolverStateInternal(

@@ -140,3 +140,24 @@ def test_operator_calls_do_not_disturb_the_supermann_memory(emu_lib):
         h.close()
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
     assert np.array_equal(out[0][2][0], out[1][2][0]) and np.array_equal(out[0][2][1], out[1][2][1])
+
+
+def test_build_model_with_estimated_L_norm(emu_lib):
+    """SolverOptions(estimate_L_norm=True): the step sizes come from the power-iteration estimate of ||L||^2 instead of the
+    reference's hard-coded constant, and the solve still converges (with fewer passes: the constant over-estimates it)."""
+    import numpy as np
+
+    from spock_b200 import SolverOptions, build_model, get_server_heat_specs, solve_model_
+    from spock_b200 import model as M
+
+    spec = get_server_heat_specs(5, 4, 2)
+    x0 = 0.1 * np.ones(4)
+    passes = []
+    for est in (False, True):
+        m = build_model(*spec, SolverOptions(M.CP, None, estimate_L_norm=est), lib=emu_lib)
+        assert (m.solver_state.L_norm == 10.0) != est and 0.5 < m.solver_state.L_norm <= 10.0
+        solve_model_(m, x0, tol=1e-3, quiet=True)
+        assert m.last_result["converged"] == 1
+        passes.append(m.last_result["passes"])
+        m.handle.close()
+    assert passes[1] < passes[0]
