@@ -1023,9 +1023,9 @@ static void ctl_end(spk_handle *h) {
   h->last_xi1 = c.xi1; h->last_xi2 = c.xi2;
 }
 
-#ifndef SPK_HOST_EMU
 static unsigned vec_grid(const spk_handle *h, long n) {
-  long g = (n + SPK_SP_THREADS - 1) / SPK_SP_THREADS;
+  const long blk = SPK_EMU ? 1 : SPK_SP_THREADS;
+  long g = (n + blk - 1) / blk;
   return (unsigned)std::max(1L, std::min(g, (long)h->red_blocks));
 }
 // should_terminate! on the device for one finished pass (CP: xi1, xi2 come out of the dual kernel in d_scal[0..1])
@@ -1034,7 +1034,7 @@ static int launch_terminate(spk_handle *h, int xi_slot, int is_sp) {
     std::string cerr;
     if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
   }
-  spk_k_terminate<<<1, 1, 0, h->stream>>>(h->d_ctl, h->d_scal, xi_slot, is_sp, h->d_log);
+  SPK_LAUNCH(spk_k_terminate, 1, 1, 0, h->stream, h->d_ctl, h->d_scal, xi_slot, is_sp, h->d_log);
   COUNT_LAUNCH(h, PC_VEC);
   return rt_launch_check();
 }
@@ -1051,39 +1051,45 @@ static int sp_pass_device_launch(spk_handle *h, double gamma, double sigma) {
   double *scal = h->d_scal, *part = h->d_sp_partial;
   unsigned *tick = h->d_ticket;
   const unsigned g = vec_grid(h, nr), gz = vec_grid(h, nz), gv = vec_grid(h, nv);
-  const int T = SPK_SP_THREADS;
+  const int T = SPK_EMU ? 1 : SPK_SP_THREADS;
+  auto kLt = spk_k_Lop_ctl<true>;
+  auto kL = spk_k_Lop_ctl<false>;
+  const double *nodp = nullptr;
+  double *nop = nullptr;
+  const int *always = nullptr;
   SPK_TRY(op_T_fused_launch(h, h->zv, h->zvbar, gamma, sigma, 4));                       // :389-390 and <r, P r>
   {
     ProfScope ps(h, PC_VEC);
-    spk_k_sp_a<<<g, T, 0, h->stream>>>(nr, V, c, scal, part, tick);
-    spk_k_sp_b<<<g, T, 0, h->stream>>>(nr, V, c, part, tick);
-    spk_k_sp_c<<<g, T, 0, h->stream>>>(nr, V, c, part, tick);
-    spk_k_sp_d<<<g, T, 0, h->stream>>>(nr, V, c, part, tick);
-    spk_k_sp_e<<<g, T, 0, h->stream>>>(nr, V, c);
+    SPK_LAUNCH(spk_k_sp_a, g, T, 0, h->stream, nr, V, c, scal, part, tick);
+    SPK_LAUNCH(spk_k_sp_b, g, T, 0, h->stream, nr, V, c, part, tick);
+    SPK_LAUNCH(spk_k_sp_c, g, T, 0, h->stream, nr, V, c, part, tick);
+    SPK_LAUNCH(spk_k_sp_d, g, T, 0, h->stream, nr, V, c, part, tick);
+    SPK_LAUNCH(spk_k_sp_e, g, T, 0, h->stream, nr, V, c);
     for (int k = 0; k < 5; ++k) COUNT_LAUNCH(h, PC_VEC);
   }
   SPK_TRY(op_T_fused_launch(h, h->wu, h->wubar, gamma, sigma, 5));                       // :133-164
   {
     ProfScope ps(h, PC_VEC);
-    spk_k_sp_f_decide<<<1, 1, 0, h->stream>>>(c, scal);
-    spk_k_sp_f<<<g, T, 0, h->stream>>>(nr, V, c);
+    SPK_LAUNCH(spk_k_sp_f_decide, 1, 1, 0, h->stream, c, scal);
+    SPK_LAUNCH(spk_k_sp_f, g, T, 0, h->stream, nr, V, c);
     // K2: rho = <r~, P (r~ - d)> (spock_dot :485-516), only when K1 failed
-    spk_k_Lop_ctl<true><<<gz, T, 0, h->stream>>>(D, h->P, h->ws_rho + nz, -gamma, 1.0, h->ws_rho, nullptr, h->rwu, scal + 6, 0, nullptr,
-                                                  c, &c->need_k2, part, tick);
-    spk_k_Lop_ctl<false><<<gv, T, 0, h->stream>>>(D, h->P, h->ws_rho, -sigma, 1.0, h->ws_rho + nz, nullptr, h->rwu + nz, scal + 6, 1,
-                                                   nullptr, c, &c->need_k2, part, tick);
-    spk_k_sp_g_decide<<<1, 1, 0, h->stream>>>(c, scal);
-    spk_k_sp_g<<<g, T, 0, h->stream>>>(nr, V, c);
+    SPK_LAUNCH(kLt, gz, T, 0, h->stream, D, h->P, h->ws_rho + nz, -gamma, 1.0, h->ws_rho, nop, h->rwu, scal + 6, 0, nop, c, &c->need_k2,
+               part, tick);
+    SPK_LAUNCH(kL, gv, T, 0, h->stream, D, h->P, h->ws_rho, -sigma, 1.0, h->ws_rho + nz, nop, h->rwu + nz, scal + 6, 1, nop, c,
+               &c->need_k2, part, tick);
+    SPK_LAUNCH(spk_k_sp_g_decide, 1, 1, 0, h->stream, c, scal);
+    SPK_LAUNCH(spk_k_sp_g, g, T, 0, h->stream, nr, V, c);
     // should_terminate! (sp.jl:270-344): xi1 = ||L'dv - dz/gamma||_inf, xi2 = ||L dz - dv/sigma||_inf
-    spk_k_Lop_ctl<true><<<gz, T, 0, h->stream>>>(D, h->P, h->dzv + nz, 1.0, -1.0 / gamma, h->dzv, nullptr, nullptr, nullptr, 0, scal + 10,
-                                                  c, nullptr, part, tick);
-    spk_k_Lop_ctl<false><<<gv, T, 0, h->stream>>>(D, h->P, h->dzv, 1.0, -1.0 / sigma, h->dzv + nz, nullptr, nullptr, nullptr, 0, scal + 11,
-                                                   c, nullptr, part, tick);
+    SPK_LAUNCH(kLt, gz, T, 0, h->stream, D, h->P, h->dzv + nz, 1.0, -1.0 / gamma, h->dzv, nop, nodp, nop, 0, scal + 10, c, always, part,
+               tick);
+    SPK_LAUNCH(kL, gv, T, 0, h->stream, D, h->P, h->dzv, 1.0, -1.0 / sigma, h->dzv + nz, nop, nodp, nop, 0, scal + 11, c, always, part,
+               tick);
     for (int k = 0; k < 8; ++k) COUNT_LAUNCH(h, PC_VEC);
   }
   return launch_terminate(h, 10, 1);
 }
 static int sp_pass_device(spk_handle *h, double gamma, double sigma) {
+#ifndef SPK_HOST_EMU
   if (h->use_graphs && !h->prof_on) {
     if (h->sp_graph && (h->sp_graph_gamma != gamma || h->sp_graph_sigma != sigma)) {
       cudaGraphExecDestroy(h->sp_graph);
@@ -1108,9 +1114,9 @@ static int sp_pass_device(spk_handle *h, double gamma, double sigma) {
     h->launches += h->sp_graph_kernels;
     return SPK_OK;
   }
+#endif
   return sp_pass_device_launch(h, gamma, sigma);
 }
-#endif
 
 // passes per host poll: large problems are polled every pass (a pass is milliseconds), small ones every 8 passes
 static int poll_batch(const spk_handle *h) { return (h->D.nz + h->D.nv) > (1L << 21) ? 1 : 8; }
@@ -1340,7 +1346,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   h->res_0[0] = h->res_0[1] = -INFINITY;
   {
     const char *nd = getenv("SPK_HOST_LOOP");
-    h->dev_loop = !SPK_EMU && h->fused_ok && !(nd && nd[0] == '1') && (h->alg == SPK_CP || h->world == 1);
+    h->dev_loop = h->fused_ok && !(nd && nd[0] == '1') && (h->alg == SPK_CP || h->world == 1);
   }
   if (h->alg == SPK_SP) {  // spock.jl:160-202
     SPK_TRY(dev_alloc(h, &h->rzv, nr));
@@ -1549,7 +1555,6 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   S.gamma = gamma; S.sigma = sigma; S.tol = 0.0; S.verbose_log = 0;
   SPK_TRY(ctl_begin(h, 0.0, 0, 1));  // also clears the device-side `done` flag that gates the fused kernels
   LoopTimer timer(h);
-#ifndef SPK_HOST_EMU
   if (h->dev_loop && h->alg == SPK_SP) {  // SuperMann without host decisions (spk_sp.cuh)
     for (int k = 0; k < K; ++k) {
       SPK_TRY(sp_pass_device(h, gamma, sigma));
@@ -1563,7 +1568,6 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
     if (ms) *ms = t;
     return SPK_OK;
   }
-#endif
   for (int k = 0; k < K; ++k) {
     S.iter = k;
     int bc = 0;
@@ -1686,7 +1690,6 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
   double xi = NAN, xi1 = NAN, xi2 = NAN;
   SPK_TRY(ctl_begin(h, tol, verbose_log, 0));
   LoopTimer timer(h);
-#ifndef SPK_HOST_EMU
   // Device-resident loop: CP (SILENT; LOG needs the xi vector, cp.jl:82-86) and SP (both modes, sp.jl:304)
   if (h->dev_loop && (h->alg == SPK_SP || !verbose_log)) {
     const int batch = poll_batch(h);
@@ -1734,7 +1737,6 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
     }
     return SPK_OK;
   }
-#endif
   while (iter < max_iter) {
     int bc = 0;
     S.iter = iter;

@@ -21,14 +21,30 @@ struct SpkCtl {
   int k, it, branch, need_k2, rot, k1, k2, fb;
 };
 
-#if !SPK_EMU
 #define SPK_SP_THREADS 256
-#define SPK_SP_MAXSUM 4
+#if !SPK_EMU
+#define SPK_SP_KERNEL __global__ void __launch_bounds__(SPK_SP_THREADS)
+#define SPK_LDCG(p) __ldcg(p)
+#else  // host emulation (tests only): blocks run one after the other with one thread each
+#define SPK_SP_KERNEL static void
+#define SPK_LDCG(p) (*(p))
+#endif
 
 // Folds NS running sums of every thread of the grid.  Returns true in thread 0 of the LAST block to arrive, with the
 // grid totals in tot[]; every other thread gets false.  partial: gridDim.x * NS doubles; ticket: self-resetting counter.
 template <int NS>
-__device__ __forceinline__ bool spk_grid_fold(double (&acc)[NS], double *partial, unsigned *ticket, double (&tot)[NS]) {
+SPK_D bool spk_grid_fold(double (&acc)[NS], double *partial, unsigned *ticket, double (&tot)[NS]) {
+#if SPK_EMU
+  (void)ticket;
+  for (int j = 0; j < NS; ++j) partial[(size_t)blockIdx.x * NS + j] = acc[j];
+  if (blockIdx.x != gridDim.x - 1) return false;  // blocks are emulated in order: the last one folds
+  for (int j = 0; j < NS; ++j) {
+    double v = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += partial[(size_t)b * NS + j];
+    tot[j] = v;
+  }
+  return true;
+#else
   __shared__ double s_w[SPK_SP_THREADS / 32][NS];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -57,7 +73,7 @@ __device__ __forceinline__ bool spk_grid_fold(double (&acc)[NS], double *partial
 #pragma unroll
   for (int j = 0; j < NS; ++j) {
     double v = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += __ldcg(partial + (size_t)b * NS + j);
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += SPK_LDCG(partial + (size_t)b * NS + j);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -72,17 +88,18 @@ __device__ __forceinline__ bool spk_grid_fold(double (&acc)[NS], double *partial
     tot[j] = v;
   }
   return true;
+#endif
 }
 
 struct SpkSpVecs {
   double *zv, *zvbar, *zv_old, *dzv, *rzv, *rzv_old, *dir, *wu, *wubar, *rwu, *ws_rho;
   double *MP[3], *MR[3], *AQ[3];  // PHYSICAL column slots; logical column j is slot (j + 2 rot) % 3
 };
-__device__ __forceinline__ int spk_sp_slot(int j, int rot) { return (j + 2 * rot) % 3; }
+SPK_HD int spk_sp_slot(int j, int rot) { return (j + 2 * rot) % 3; }
 
 // ---- KA (after T(z,v)): update_residual!, update_delta_r!, update_sy! (sp.jl:34-51, :232-268), the new Anderson
 //      columns (anderson.jl:13-65, rotating slots instead of shifting) and the first Gram-Schmidt dots (:78-91)
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_a(long nr, SpkSpVecs V, SpkCtl *c, const double *scal, double *partial,
+SPK_SP_KERNEL spk_k_sp_a(long nr, SpkSpVecs V, SpkCtl *c, const double *scal, double *partial,
                                                                unsigned *ticket) {
   if (c->done) return;
   const int rot = c->rot + 1;  // this pass's rotation; stored by the epilogue after every block has read the old value
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_a(long nr, SpkSpVecs 
   }
 }
 // ---- KB: Q1 -= rho2 Q2 (anderson.jl:78-91, j = 2) and the dots for j = 3
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_b(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
+SPK_SP_KERNEL spk_k_sp_b(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
   if (c->done) return;
   const int rot = c->rot;
   double *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_b(long nr, SpkSpVecs 
   }
 }
 // ---- KC: Q1 -= rho3 Q3, ||Q1|| (anderson.jl:68-76 / :93-98)
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_c(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
+SPK_SP_KERNEL spk_k_sp_c(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
   if (c->done) return;
   const int rot = c->rot;
   double *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -175,7 +192,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_c(long nr, SpkSpVecs 
   }
 }
 // ---- KD: Q1 /= R11, Q'r (anderson.jl:111), then gamma = R^{-1} Q'r (:113)
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_d(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
+SPK_SP_KERNEL spk_k_sp_d(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
   if (c->done) return;
   const int rot = c->rot;
   double *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_d(long nr, SpkSpVecs 
   }
 }
 // ---- KE: d = -r - MP gamma (anderson.jl:116-122), candidate (w,u) = (z,v) + d (sp.jl:118-131, tau = 1)
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_e(long nr, SpkSpVecs V, const SpkCtl *c) {
+SPK_SP_KERNEL spk_k_sp_e(long nr, SpkSpVecs V, const SpkCtl *c) {
   if (c->done) return;
   const int rot = c->rot;
   const double *p0 = V.MP[spk_sp_slot(0, rot)], *p1 = V.MP[spk_sp_slot(1, rot)], *p2 = V.MP[spk_sp_slot(2, rot)];
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_e(long nr, SpkSpVecs 
   }
 }
 // ---- SF (one thread): the K1 test (sp.jl:166-191)
-__global__ void spk_k_sp_f_decide(SpkCtl *c, const double *scal) {
+SPK_KERNEL void spk_k_sp_f_decide(SpkCtl *c, const double *scal) {
   if (c->done) return;
   const double c1 = 0.99, q = 0.99;  // sp.jl:366-372
   const double rt = sqrt(scal[5]);
@@ -233,7 +250,7 @@ __global__ void spk_k_sp_f_decide(SpkCtl *c, const double *scal) {
   }
 }
 // ---- KF: candidate residual (sp.jl:133-164) and, unless K1 holds, r~ - d for the K2 inner product (:419-424)
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_f(long nr, SpkSpVecs V, const SpkCtl *c) {
+SPK_SP_KERNEL spk_k_sp_f(long nr, SpkSpVecs V, const SpkCtl *c) {
   if (c->done) return;
   const bool k2 = c->need_k2 != 0;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -244,7 +261,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_f(long nr, SpkSpVecs 
   }
 }
 // ---- SG (one thread): K2 test or fallback (sp.jl:193-222, :443-446)
-__global__ void spk_k_sp_g_decide(SpkCtl *c, double *scal) {
+SPK_KERNEL void spk_k_sp_g_decide(SpkCtl *c, double *scal) {
   if (c->done) return;
   const double sigma_k2 = 0.1, lambda_sp = 1.0;
   if (c->need_k2) {
@@ -262,7 +279,7 @@ __global__ void spk_k_sp_g_decide(SpkCtl *c, double *scal) {
   scal[11] = 0.0;
 }
 // ---- KG: the accepted update and delta = (z,v) - (z,v)_old for should_terminate! and the next Anderson step
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_g(long nr, SpkSpVecs V, const SpkCtl *c) {
+SPK_SP_KERNEL spk_k_sp_g(long nr, SpkSpVecs V, const SpkCtl *c) {
   if (c->done) return;
   const int branch = c->branch;
   const double coef = c->coef;
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_sp_g(long nr, SpkSpVecs 
 //   absmax != NULL: *absmax = max |that value|                (residual maxima; exact, order-free integer atomicMax)
 //   run_if != NULL: the kernel only runs when *run_if != 0
 template <bool TRANS>
-__global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_Lop_ctl(SpkDims D, SpkPtrs P, const double *__restrict__ x, double alpha, double beta,
+SPK_SP_KERNEL spk_k_Lop_ctl(SpkDims D, SpkPtrs P, const double *__restrict__ x, double alpha, double beta,
                                                                   const double *__restrict__ in, double *__restrict__ out,
                                                                   const double *__restrict__ dot_with, double *dot_out, int dot_accumulate,
                                                                   double *absmax, const SpkCtl *c, const int *run_if, double *partial,
@@ -299,6 +316,9 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_Lop_ctl(SpkDims D, SpkPt
     mx = fmax(mx, fabs(val));
   }
   if (absmax) {
+#if SPK_EMU
+    if (mx > *absmax) *absmax = mx;
+#else
     __shared__ double s_m[SPK_SP_THREADS / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -308,6 +328,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_Lop_ctl(SpkDims D, SpkPt
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, s_m[w]);
       if (mx > __ldcg(absmax)) atomicMax(reinterpret_cast<unsigned long long *>(absmax), (unsigned long long)__double_as_longlong(mx));
     }
+#endif
   }
   if (dot_with) {
     double tot[1];
@@ -317,7 +338,7 @@ __global__ void __launch_bounds__(SPK_SP_THREADS) spk_k_Lop_ctl(SpkDims D, SpkPt
 
 // ---- SH (one thread): should_terminate! (sp.jl:270-344 / cp.jl:54-123), per-pass log, counters
 //      xi_slot: where the pass left (xi1, xi2); bc_from_branch: SuperMann's backtrack_count (9 on fallback)
-__global__ void spk_k_terminate(SpkCtl *c, const double *scal, int xi_slot, int is_sp, double *log) {
+SPK_KERNEL void spk_k_terminate(SpkCtl *c, const double *scal, int xi_slot, int is_sp, double *log) {
   if (c->done) return;
   const double xi1 = scal[xi_slot], xi2 = scal[xi_slot + 1];
   bool stop;
@@ -340,4 +361,3 @@ __global__ void spk_k_terminate(SpkCtl *c, const double *scal, int xi_slot, int 
   c->it++;
   if (stop && !c->ignore_done) c->done = 1;
 }
-#endif

@@ -37,7 +37,10 @@ def test_offline_factors(emu_lib, name):
     ("l2ball_N4_d3_nx3", CP, 200), ("pernode_cost_tv_N4_d2_nx3", CP, 150), ("pernode_cost_tv_N4_d2_nx3", SP, 15),
     ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
 ])
-def test_k_step_iterates(emu_lib, name, alg, K):
+@pytest.mark.parametrize("host_loop", ["0", "1"])
+def test_k_step_iterates(emu_lib, name, alg, K, host_loop, monkeypatch):
+    """both loop drivers: device-resident control block (default) and the host-driven loop (SPK_HOST_LOOP=1)"""
+    monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
     check_k_steps(emu_lib, flat_of(name), alg, K, factor_mode=K % 2)
 
 
@@ -49,7 +52,9 @@ def test_cp_golden_trace_prefix(emu_lib):
     assert np.max(np.abs(log["xi"] - gold[:400]) / gold[:400]) < 1e-9
 
 
-def test_sp_golden_trace_prefix(emu_lib):
+@pytest.mark.parametrize("host_loop", ["0", "1"])
+def test_sp_golden_trace_prefix(emu_lib, host_loop, monkeypatch):
+    monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
     xi, bc = golden_sp()
     h = Handle(flat_of("heat_N7_d2_nx5"), SP, lib=emu_lib)
     res, log = h.solve(0.1 * np.ones(5), tol=1e-5, verbose_log=True, max_iter=60)
@@ -57,7 +62,9 @@ def test_sp_golden_trace_prefix(emu_lib):
     assert np.array_equal(log["backtrack_count"][:60], bc[:60])
 
 
-def test_silent_termination_and_warm_start(emu_lib):
+@pytest.mark.parametrize("host_loop", ["0", "1"])
+def test_silent_termination_and_warm_start(emu_lib, host_loop, monkeypatch):
+    monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
     flat = flat_of("heat_N7_d2_nx5")
     for alg in (CP, SP):
         h, o = Handle(flat, alg, lib=emu_lib), Oracle(flat, alg)
