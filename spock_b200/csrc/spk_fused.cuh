@@ -8,19 +8,25 @@
 //   2. spk_k_fwd_s1, one launch per level 0 .. N-2: u_i, x_children (:667-681)                -> zbar (x, u)
 //   3. spk_k_s2t, one launch: (z - gamma L'v) on (y_i, s_children, tau_children) and projection_S2! (:688-727),
 //      prox_f!'s s_1 -= gamma (:741)                                                          -> zbar (s, tau, y)
-//   4. spk_k_dual, one launch over all families: L(2 zbar - z) (:177-318) and prox_h_conj! (:911-951) for v1_i, v2_i,
-//      v7_i, (v3..v6)_children and, for leaf children, (v11..v14); plus the residuals of should_terminate!
-//      (cp.jl:54-80) xi1 = ||L'dv - dz/gamma||_inf, xi2 = ||L dz - dv/sigma||_inf and <r, P r> (spock_dot :485-516),
-//      which are all family-local                                                             -> vbar, xi1, xi2, pnorm
+//   4. the dual kernel, one launch for the families with non-leaf children and one for those with leaf children:
+//      L(2 zbar - z) (:177-318) and prox_h_conj! (:911-951) for v1_i, v2_i, v7_i, (v3..v6)_children and, for leaf
+//      children, (v11..v14); plus the residuals of should_terminate! (cp.jl:54-80) xi1 = ||L'dv - dz/gamma||_inf,
+//      xi2 = ||L dz - dv/sigma||_inf and <r, P r> (spock_dot :485-516), which are all family-local
+//                                                                                             -> vbar, xi1, xi2, pnorm
+//      Three implementations of the same arithmetic: spk_k_dual3 (register-resident, one lane per column; specialised
+//      shapes with Diagonal costs -- the production kernel), spk_k_dual2 (batched through shared memory; dense costs and
+//      unspecialised shapes), spk_k_dual (one warp per family; fallback when a batch does not fit in shared memory).
 // z and v are read twice per pass, zbar and vbar written once, q and d written and read once.
 //
-// Kernels 1 and 2 stream the Riccati factors: one CTA per family at a time, the family's factor slots are contiguous in
-// HBM and are fetched with TMA bulk copies (cp.async.bulk -> UBLKCP) into shared memory, completing on an mbarrier,
-// while the threads gather the family's vector entries with ordinary coalesced loads; the mat-vecs run out of shared
-// memory with the inner dimension split over the CTA and only 3-6 CTA barriers per family, so that the time a CTA
-// spends NOT waiting for HBM is short (microbenchmarks/stream_bench.cu: single-shot bulk copies of 20-60 KB reach the
-// HBM roofline as long as the consumer is quick).  With per-stage factors the matrices are fetched once per CTA.
-// Kernel 4 is one warp per family without any CTA barrier.
+// Kernels 1 and 2 stream the per-node Riccati factors: one CTA per family at a time, the family's factor slots are
+// contiguous in HBM and are fetched with TMA bulk copies (cp.async.bulk -> UBLKCP) into shared memory, completing on
+// mbarriers (large shapes: in chunks that are re-fetched for the next family as soon as they are consumed), while the
+// family's vector entries are staged one family ahead with cp.async; the mat-vecs run out of shared memory with the inner
+// dimension split over the CTA and only 3-6 CTA barriers per family, so that the time a CTA spends NOT waiting for HBM is
+// short (tools/microbench/stream_bench.cu: single-shot bulk copies of 20-60 KB reach the HBM roofline as long as the
+// consumer is quick).  With per-stage factors the matrices are fetched once per CTA; the wide levels then run the
+// tensor-pipe kernels of spk_mm.cuh instead.
+// Every kernel returns immediately when the loop's device-side `done` flag (SpkFusedArgs.gate, spk_sp.cuh) is set.
 #pragma once
 #include "spk_types.h"
 
