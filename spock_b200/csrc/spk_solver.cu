@@ -349,10 +349,14 @@ static int fetch_scalars(spk_handle *h, int count) {
     if (h->alg == SPK_CP) {  // xi1, xi2 are maxima over the ranks' owned families (left in d_scal[0..1] by the dual kernels)
       if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
     } else {  // SuperMann: every slot reduced since the last fetch holds a rank-local sum / maximum
-      for (int k = 0; k < count && k < 32; ++k) {
-        if (h->slot_dirty[k] == 1 && !h->comm.allreduce_sum(h->d_scal + k, 1, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
-        if (h->slot_dirty[k] == 2 && !h->comm.allreduce_max(h->d_scal + k, 1, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
-        h->slot_dirty[k] = 0;
+      for (int k = 0; k < count && k < 32;) {  // one collective per run of consecutive slots of the same kind
+        const int kind = h->slot_dirty[k];
+        int e = k + 1;
+        while (e < count && e < 32 && h->slot_dirty[e] == kind) ++e;
+        if (kind == 1 && !h->comm.allreduce_sum(h->d_scal + k, e - k, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+        if (kind == 2 && !h->comm.allreduce_max(h->d_scal + k, e - k, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+        for (int j = k; j < e; ++j) h->slot_dirty[j] = 0;
+        k = e;
       }
     }
   }
