@@ -180,6 +180,12 @@ int spk_comm_unique_id(uint8_t id[128]);
  * rank's local view: entries of owned families (and of the replicated top) are valid, the rest is stale. */
 int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int64_t *count);
 
+/* Collective over all ranks (no-op with world_size 1): all-gathers the entries every rank's families own, so that
+ * afterwards the device-resident iterate -- and hence spk_get_iterate -- is the complete (z, v) on every rank
+ * (model.solver_state.z / .v of the reference).  Every level below the cut is a rank-major contiguous slice of every
+ * segment, so this is one in-place all-gather per (segment, level). */
+int spk_gather_iterate(spk_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,4 +139,10 @@ function estimate_L_norm!(m::Model; iters = 50)
   return out[]
 end
 
+"""    gather_iterate!(model): multi-GPU only -- completes model.z / model.v on every rank (collective)."""
+function gather_iterate!(m::Model)
+  check(ccall((:spk_gather_iterate, LIB), Cint, (Ptr{Cvoid},), m.handle))
+  check(ccall((:spk_get_iterate, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.handle, m.z, m.v))
+end
+
 end # module

@@ -1805,6 +1805,45 @@ int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int
   return SPK_OK;
 }
 
+int spk_gather_iterate(spk_handle *h) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->world <= 1) return SPK_OK;
+  const SpkDims &D = h->D;
+  double *z = h->z(), *v = h->v();
+  std::string cerr;
+  auto gather = [&](double *base, long first, long per_rank, long stride) -> int {  // entries [first, first + world*per_rank) x stride
+    if (!h->comm.allgather_inplace(base + first * stride, per_rank * stride, h->stream, cerr)) return comm_fail(cerr);
+    return SPK_OK;
+  };
+  for (int t = h->t_cut; t <= D.N - 2; ++t) {
+    long lo, cnt;
+    level_range(h, t, lo, cnt);  // this rank's families of level t: positions [rank*cnt, (rank+1)*cnt)
+    const long f0 = spk_level_first0(D.d, t), c0 = spk_level_first0(D.d, t + 1), ccnt = cnt * D.d;
+    // indexed by the family's node: u_i, y_i, v1_i, v2_i, v7_i
+    SPK_TRY(gather(z + D.zo[1], f0, cnt, D.nu));
+    SPK_TRY(gather(z + D.zo[4], f0, cnt, D.ny));
+    SPK_TRY(gather(v + D.vo[0], f0, cnt, D.ny));
+    SPK_TRY(gather(v + D.vo[1], f0, cnt, 1));
+    SPK_TRY(gather(v + D.vo[6], f0, cnt, D.nx + D.nu));
+    // indexed by the children: x_c, s_c, tau_c and (v3..v6)_c (entry c-1); leaf children: (v11..v14) by leaf ordinal
+    SPK_TRY(gather(z, c0, ccnt, D.nx));
+    SPK_TRY(gather(z + D.zo[2], c0, ccnt, 1));
+    SPK_TRY(gather(z + D.zo[3], c0 - 1, ccnt, 1));
+    SPK_TRY(gather(v + D.vo[2], c0 - 1, ccnt, D.nx));
+    SPK_TRY(gather(v + D.vo[3], c0 - 1, ccnt, D.nu));
+    SPK_TRY(gather(v + D.vo[4], c0 - 1, ccnt, 1));
+    SPK_TRY(gather(v + D.vo[5], c0 - 1, ccnt, 1));
+    if (t == D.N - 2) {
+      const long l0 = c0 - D.nnl;
+      SPK_TRY(gather(v + D.vo[7], l0, ccnt, D.nx));
+      SPK_TRY(gather(v + D.vo[8], l0, ccnt, 1));
+      SPK_TRY(gather(v + D.vo[9], l0, ccnt, 1));
+      SPK_TRY(gather(v + D.vo[10], l0, ccnt, D.nx));
+    }
+  }
+  return rt_sync(h->stream);
+}
+
 #ifdef SPK_HOST_EMU
 // Test hook of the host-emulation build only (tests/test_mm_fragments.py): the fragment-ordered weight tables that the
 // tensor-pipe S1 kernels of the CUDA build read (spk_mm_layout.h), so that the CPU test-suite can check the host-side

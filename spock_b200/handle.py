@@ -65,6 +65,10 @@ class Handle:
         check(self.lib, self.lib.spk_get_iterate(self._h, dptr(z), dptr(v)))
         return z, v
 
+    def gather_iterate(self):
+        """Collective over all ranks: afterwards get_iterate() returns the complete (z, v) on every rank."""
+        check(self.lib, self.lib.spk_gather_iterate(self._h))
+
     def get_state(self):
         """Solver memory that persists across solves besides (z, v) (checkpoint / resume; layout: include/spock_b200.h)."""
         n = C.c_int64()

@@ -29,6 +29,12 @@ def _run_rank(lib, flat, fm, rank, world, cid, K, out, alg=CP):
         h.step(K)
         z, v = h.get_iterate()
         xi = h.residuals()
+        if alg == CP:  # spk_gather_iterate: the complete iterate on every rank; the passes that follow are unaffected
+            h.gather_iterate()
+            zfull, vfull = h.get_iterate()
+            h.step(3)
+            h.gather_iterate()
+            out[("full", rank)] = (zfull, vfull) + h.get_iterate()
         extra = None
         if alg == SP:  # then solve_model! to tolerance from this point: every rank must take the same decisions
             res, log = h.solve(0.1 * np.ones(flat.nx), tol=1e-4)
@@ -63,6 +69,12 @@ def test_partition_matches_single_rank_threads(emu_lib, name, world):
     assert relerr(z, zr) < 1e-12 and relerr(v, vr) < 1e-12
     for g in range(world):                   # xi1, xi2 are global maxima on every rank
         assert abs(out[g][3][0] - xr[0]) < 1e-12 * xr[0] and abs(out[g][3][1] - xr[1]) < 1e-12 * xr[1]
+    # spk_gather_iterate: every rank holds the complete single-rank iterate, also after further passes
+    ref.step(3)
+    zr3, vr3 = ref.get_iterate()
+    for g in range(world):
+        zf, vf, zf3, vf3 = out[("full", g)]
+        assert relerr(zf, zr) < 1e-12 and relerr(vf, vr) < 1e-12 and relerr(zf3, zr3) < 1e-12 and relerr(vf3, vr3) < 1e-12
     # ownership: every non-leaf node of the levels below the cut belongs to exactly one rank
     owned = np.zeros(flat.n_non_leaf, int)
     for g in range(world):
