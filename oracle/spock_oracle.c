@@ -725,7 +725,7 @@ static double norm_inf(const double *x, long k) {
   double r = 0.0;
   for (long i = 0; i < k; ++i) {
     double a = fabs(x[i]);
-    if (a > r) r = a;
+    if (a > r || a != a) r = a; /* LinearAlgebra.norm(x, Inf) propagates NaN (r stays NaN once set) */
   }
   return r;
 }

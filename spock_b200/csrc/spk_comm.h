@@ -10,7 +10,7 @@
 #include <cstring>
 #include <string>
 
-#include "spk_runtime.h"
+#include "spk_types.h"
 
 #ifndef SPK_HOST_EMU
 #include <dlfcn.h>
@@ -78,7 +78,8 @@ struct SpkComm {
   }
   bool allreduce_max(double *buf, int n, spk_stream_t s, std::string &err) {
     if (world <= 1) return true;
-    const int rc = allreduce(buf, buf, (size_t)n, 8, 2 /*ncclMax*/, comm, s);
+    // residual maxima are non-negative: the unsigned maximum of their bit patterns is exact and keeps a NaN (spk_max_nn)
+    const int rc = allreduce(buf, buf, (size_t)n, 5 /*ncclUint64*/, 2 /*ncclMax*/, comm, s);
     if (rc != 0) { err = std::string("ncclAllReduce: ") + (errstr ? errstr(rc) : "?"); return false; }
     return true;
   }
@@ -165,7 +166,7 @@ struct SpkComm {
     barrier();
     for (int k = 0; k < n; ++k) {
       double mx = seg->data[k];
-      for (int g = 1; g < world; ++g) mx = seg->data[(long)g * n + k] > mx ? seg->data[(long)g * n + k] : mx;
+      for (int g = 1; g < world; ++g) mx = spk_max_nn(mx, seg->data[(long)g * n + k]);
       buf[k] = mx;
     }
     barrier();

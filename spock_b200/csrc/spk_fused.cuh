@@ -83,8 +83,7 @@ SPK_D double spk_warp_max(double v) {
 #if !SPK_EMU
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const double w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = w > v ? w : v;
+    v = spk_max_nn(v, __shfl_xor_sync(0xffffffffu, v, o));
   }
 #endif
   return v;
@@ -112,7 +111,7 @@ SPK_D void spk_atomic_max_nonneg(double *addr, double val) {
 #if !SPK_EMU
   atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(val));
 #else
-  if (val > *addr) *addr = val;
+  *addr = spk_max_nn(*addr, val);
 #endif
 }
 
@@ -684,7 +683,7 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     A.vbar[gidx_] = vnew_;                                              \
     const double dl_ = vnew_ - (vold_);                                 \
     dslot_ = dl_;                                                       \
-    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
+    my_xi2 = spk_max_nn(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
     my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
   }
     // ---- own blocks: v1_i (dual-cone projection :833-845), v2_i (:849-851), v7_i box (:903-908)
@@ -729,7 +728,7 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
       if (lane == 0) {
         A.vbar[D.vo[1] + i0] = v2new;
         const double l2 = ds_i - bdy;
-        my_xi2 = fmax(my_xi2, fabs(l2 - dv2 * inv_sigma));
+        my_xi2 = spk_max_nn(my_xi2, fabs(l2 - dv2 * inv_sigma));
         my_pn += dv2 * (dv2 - sigma * l2);
       }
     }
@@ -782,10 +781,10 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         if (lane == 0) {
           A.vbar[D.vo[4] + jm] = v5new;
           A.vbar[D.vo[5] + jm] = v6new;
-          my_xi2 = fmax(my_xi2, fmax(fabs(ld - d5 * inv_sigma), fabs(ld - d6 * inv_sigma)));
+          my_xi2 = spk_max_nn(my_xi2, spk_max_nn(fabs(ld - d5 * inv_sigma), fabs(ld - d6 * inv_sigma)));
           my_pn += d5 * (d5 - sigma * ld) + d6 * (d6 - sigma * ld);
           const double lt = 0.5 * d5 + 0.5 * d6;
-          xi1_tau = fmax(xi1_tau, fabs(lt - dtau * inv_gamma));
+          xi1_tau = spk_max_nn(xi1_tau, fabs(lt - dtau * inv_gamma));
           my_pn += dtau * (dtau - gamma * lt);
         }
       }
@@ -822,22 +821,22 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         if (lane == 0) {
           A.vbar[D.vo[8] + l] = v12new;
           A.vbar[D.vo[9] + l] = v13new;
-          my_xi2 = fmax(my_xi2, fmax(fabs(lds - d12 * inv_sigma), fabs(lds - d13 * inv_sigma)));
+          my_xi2 = spk_max_nn(my_xi2, spk_max_nn(fabs(lds - d12 * inv_sigma), fabs(lds - d13 * inv_sigma)));
           my_pn += d12 * (d12 - sigma * lds) + d13 * (d13 - sigma * lds);
           const double lt = 0.5 * d12 + 0.5 * d13;  // s_leaf :445-448
-          xi1_tau = fmax(xi1_tau, fabs(lt - dsl * inv_gamma));
+          xi1_tau = spk_max_nn(xi1_tau, fabs(lt - dsl * inv_gamma));
           my_pn += dsl * (dsl - gamma * lt);
         }
       }
     }
 #undef SPK_FIN
-    my_xi1 = fmax(my_xi1, xi1_tau);
+    my_xi1 = spk_max_nn(my_xi1, xi1_tau);
     SPK_SYNCWARP();
     // ---- xi1 = || L'dv - dz/gamma ||_inf and the z-part of <r, P r> for the z entries owned by this family
 #define SPK_Z(dz_, lt_)                                        \
   {                                                            \
     const double dzv_ = (dz_), ltv_ = (lt_);                   \
-    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
+    my_xi1 = spk_max_nn(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
     my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
   }
     _Pragma("unroll") for (int k = lane; k < nx; k += WL) {  // x_i :351-373
@@ -1040,7 +1039,7 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
     A.vbar[gidx_] = vnew_;                                              \
     const double dl_ = vnew_ - (vold_);                                 \
     S[Wslot] = dl_;                                                     \
-    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
+    my_xi2 = spk_max_nn(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
     my_pn += dl_ * (dl_ - sigma * (Ld_));                               \
   }
     for (int e = tid; e < f * ny; e += T) {  // v1: projection on the dual risk cone (:833-845), one thread per entry
@@ -1127,7 +1126,7 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
 #define SPK_Z(dz_, lt_)                                        \
   {                                                            \
     const double dzv_ = (dz_), ltv_ = (lt_);                   \
-    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
+    my_xi1 = spk_max_nn(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
     my_pn += dzv_ * (dzv_ - gamma * ltv_);                     \
   }
     for (int e = tid; e < f * nx; e += T) {  // x_i :351-373
@@ -1173,8 +1172,8 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
   if (tid == 0) {
     double a1 = 0.0, a2 = 0.0, a3 = 0.0;
     for (int w2 = 0; w2 < nwarps; ++w2) {
-      a1 = fmax(a1, S[M.red + w2]);
-      a2 = fmax(a2, S[M.red + 32 + w2]);
+      a1 = spk_max_nn(a1, S[M.red + w2]);
+      a2 = spk_max_nn(a2, S[M.red + 32 + w2]);
       a3 += S[M.red + 64 + w2];
     }
     spk_atomic_max_nonneg(A.xi + 0, a1);
@@ -1208,7 +1207,7 @@ SPK_CONSTEXPR_HD int spk_dual3_group(int nx, int nu, int d) {
 // the residual maxima only ever grow: skip the atomic when the value cannot raise the maximum (a stale read only
 // causes a redundant atomic, never a missed one)
 SPK_D void spk_atomic_max_lazy(double *addr, double val) {
-  if (val > __ldcg(addr)) spk_atomic_max_nonneg(addr, val);
+  if (spk_bits_nn(val) > spk_bits_nn(__ldcg(addr))) spk_atomic_max_nonneg(addr, val);
 }
 
 // exact maximum of non-negative doubles over the warp with two integer REDUX operations (high words, then the low
@@ -1250,7 +1249,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
 #define SPK_Z3(dz_, lt_)                                       \
   {                                                            \
     const double dzv_ = (dz_), ltv_ = (lt_);                   \
-    my_xi1 = fmax(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
+    my_xi1 = spk_max_nn(my_xi1, fabs(ltv_ - dzv_ * inv_gamma));      \
     if (PN) my_pn += dzv_ * (dzv_ - gamma * ltv_);             \
   }
   // vbar = sigma (W - Proj W), delta v, xi2 and the v-part of <r, P r> of one dual entry
@@ -1259,7 +1258,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     const double vnew_ = sigma * ((w_) - (pr_));                        \
     *(ptr_) = vnew_;                                                    \
     dl_ = vnew_ - (vold_);                                              \
-    my_xi2 = fmax(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
+    my_xi2 = spk_max_nn(my_xi2, fabs((Ld_) - dl_ * inv_sigma));               \
     if (PN) my_pn += dl_ * (dl_ - sigma * (Ld_));                       \
   }
   // ---------------------------------------------------------------- loads (all independent)
@@ -1463,7 +1462,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     if (lane == 0) {
       vb[D.vo[1] + i0] = v2new;
       const double l2 = ds_i - bdy;
-      my_xi2 = fmax(my_xi2, fabs(l2 - dv2 * inv_sigma));
+      my_xi2 = spk_max_nn(my_xi2, fabs(l2 - dv2 * inv_sigma));
       if (PN) my_pn += dv2 * (dv2 - sigma * l2);
     }
   }
@@ -1562,8 +1561,8 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   if (!valid) my_pn = 0.0;
   const double m1 = spk_warp_max_nonneg(my_xi1), m2 = spk_warp_max_nonneg(my_xi2);
   if (wlane == 0) {
-    if (m1 > seen_xi1) spk_atomic_max_nonneg(A.xi + 0, m1);
-    if (m2 > seen_xi2) spk_atomic_max_nonneg(A.xi + 1, m2);
+    if (spk_bits_nn(m1) > spk_bits_nn(seen_xi1)) spk_atomic_max_nonneg(A.xi + 0, m1);
+    if (spk_bits_nn(m2) > spk_bits_nn(seen_xi2)) spk_atomic_max_nonneg(A.xi + 1, m2);
   }
   if (PN) {
     const double ps = spk_warp_sum(my_pn);

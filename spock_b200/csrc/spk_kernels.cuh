@@ -438,14 +438,14 @@ SPK_KERNEL void spk_k_reduce_partial(long n, int mode, const double *__restrict_
     if (mask && !mask[i]) continue;
     if (mode == 0) acc += x[i] * y[i];
     else if (mode == 2) acc += x[i];
-    else { const double a = fabs(x[i]); acc = a > acc ? a : acc; }
+    else acc = spk_max_nn(acc, fabs(x[i]));
   }
   sm[threadIdx.x] = acc;
   SPK_SYNCTHREADS();
   for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       const double o = sm[threadIdx.x + s];
-      sm[threadIdx.x] = (mode != 1) ? sm[threadIdx.x] + o : (o > sm[threadIdx.x] ? o : sm[threadIdx.x]);
+      sm[threadIdx.x] = (mode != 1) ? sm[threadIdx.x] + o : spk_max_nn(sm[threadIdx.x], o);
     }
     SPK_SYNCTHREADS();
   }
@@ -458,14 +458,14 @@ SPK_KERNEL void spk_k_reduce_final(int np, int mode, const double *__restrict__ 
   double acc = 0.0;
   for (int i = threadIdx.x; i < np; i += blockDim.x) {
     const double o = partial[i];
-    acc = (mode != 1) ? acc + o : (o > acc ? o : acc);
+    acc = (mode != 1) ? acc + o : spk_max_nn(acc, o);
   }
   sm[threadIdx.x] = acc;
   SPK_SYNCTHREADS();
   for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       const double o = sm[threadIdx.x + s];
-      sm[threadIdx.x] = (mode != 1) ? sm[threadIdx.x] + o : (o > sm[threadIdx.x] ? o : sm[threadIdx.x]);
+      sm[threadIdx.x] = (mode != 1) ? sm[threadIdx.x] + o : spk_max_nn(sm[threadIdx.x], o);
     }
     SPK_SYNCTHREADS();
   }

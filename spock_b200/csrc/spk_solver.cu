@@ -159,7 +159,9 @@ struct spk_handle {
   int dual2_F = 1;          // families per batch of the batched dual kernel
   size_t dual2_smem = 0;
   bool use_dual2 = true;
-  int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1, num_sms = 148;
+  int fused_threads_bwd = 0, fused_threads_fwd = 0, dual_warps = 4, occ_bwd = 1, occ_fwd = 1;
+  int num_sms = 148;   // replaced by the device's multiProcessorCount in spk_create
+  long max_ctas = 0;   // SPK_MAX_CTAS (test switch): cap of every persistent grid, so that small trees reach the steady-state loop
   size_t fused_smem_bwd = 0, fused_smem_fwd = 0, fused_smem_dual = 0;
   double *d_pnorm = nullptr;
   // CUDA graphs of the fused operator evaluation, keyed by (input, output, gamma, sigma, pnorm slot)
@@ -319,7 +321,7 @@ static int op_axpby(spk_handle *h, long n, double a, const double *x, double b, 
   ProfScope ps(h, PC_VEC);
   const int blk = elem_block();
   long g = (n + blk - 1) / blk;
-  if (g > 148L * 32) g = 148L * 32;
+  if (g > (long)h->num_sms * 32) g = (long)h->num_sms * 32;
   if (g < 1) g = 1;
   SPK_LAUNCH(spk_k_axpby, (unsigned)g, blk, 0, h->stream, n, a, x, b, y, out);
   COUNT_LAUNCH(h, PC_VEC);
@@ -561,9 +563,6 @@ static int fused_setup(spk_handle *h) {
   RT_CHECK(cudaFuncSetAttribute((const void *)h->k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_dual));
   if (h->use_dual2)
     RT_CHECK(cudaFuncSetAttribute((const void *)h->k_dual2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dual2_smem));
-  cudaDeviceProp prop;
-  RT_CHECK(cudaGetDeviceProperties(&prop, h->device));
-  h->num_sms = prop.multiProcessorCount;
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, (const void *)h->k_bwd, Tb, h->fused_smem_bwd));
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, (const void *)h->k_fwd, Tf, h->fused_smem_fwd));
   h->occ_bwd = std::max(1, h->occ_bwd);
@@ -609,6 +608,10 @@ static int fused_setup(spk_handle *h) {
 #endif
   h->fused_ok = true;
   {
+    const char *mc = getenv("SPK_MAX_CTAS");
+    h->max_ctas = mc ? atol(mc) : 0;
+  }
+  {
     const char *ng = getenv("SPK_NO_GRAPH");
     h->use_graphs = !SPK_EMU && !(ng && ng[0] == '1');
   }
@@ -620,6 +623,7 @@ static unsigned fused_grid(const spk_handle *h, long count, int occ) {
   // paid once per kernel; with per-stage factors the level's matrices are also fetched only once per CTA
   long g = std::min(count, (long)h->num_sms * occ);
   if (SPK_EMU) g = std::min(count, 3L);
+  if (h->max_ctas > 0) g = std::min(g, h->max_ctas);
   return (unsigned)std::max(1L, g);
 }
 
@@ -667,7 +671,9 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
       if (h->use_mm && A.p_cnt >= h->mm_min_count) {  // per-stage factors: the level is a chain of mat-mats on the fp64 tensor pipe
         // small levels: fewer warps (tiles) per CTA so that the tiles spread over the SMs (a DMMA chain is bound by
         // the tensor pipe of its SM sub-partition)
-        const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_bwd_mm;
+        long cap = (long)h->num_sms * h->occ_bwd_mm;
+        if (h->max_ctas > 0) cap = std::min(cap, h->max_ctas);
+        const long tiles = (A.p_cnt + 7) / 8;
         const long wpb = std::min(8L, std::max(1L, (tiles + h->num_sms - 1) / h->num_sms));  // one tile per SM sub-partition first
         const long ctas = std::min((tiles + wpb - 1) / wpb, cap);
         spk_mm_kernel_t kmm = h->k_bwd_mm[A.children_are_leaves ? 1 : 0];
@@ -711,7 +717,9 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     level_range(h, t, A.p_lo, A.p_cnt);
 #ifndef SPK_HOST_EMU
     if (h->use_mm && A.p_cnt >= h->mm_min_count) {
-      const long tiles = (A.p_cnt + 7) / 8, cap = (long)h->num_sms * h->occ_fwd_mm;
+      long cap = (long)h->num_sms * h->occ_fwd_mm;
+      if (h->max_ctas > 0) cap = std::min(cap, h->max_ctas);
+      const long tiles = (A.p_cnt + 7) / 8;
       const long wpb = std::min(8L, std::max(1L, (tiles + h->num_sms - 1) / h->num_sms));
       const long ctas = std::min((tiles + wpb - 1) / wpb, cap);
       h->k_fwd_mm<<<(unsigned)std::max(1L, ctas), (unsigned)(32 * wpb), spk_mm_smem_bytes((int)h->mm_fwd_frags), h->stream>>>(
@@ -753,6 +761,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
           const long nbatch = (b - a + h->dual2_F - 1) / h->dual2_F;
           g = std::min(nbatch, (long)h->num_sms * 8);
           if (SPK_EMU) g = std::min(g, 3L);
+          if (h->max_ctas > 0) g = std::min(g, h->max_ctas);
           spk_dual2_kernel_t kfn = h->k_dual2;
           SPK_LAUNCH(kfn, (unsigned)g, T, h->dual2_smem, h->stream, D, h->P, A2, h->dual2_F, a, b - a);
         }
@@ -868,7 +877,7 @@ static bool decide_termination(spk_handle *h, const LoopState &S, double *xi, do
   *xi = NAN;
   bool res = false;
   if (S.verbose_log) {
-    *xi = (h->alg == SPK_CP) ? h->h_scal[2] : std::max(*xi1, *xi2);  // sp.jl:304
+    *xi = (h->alg == SPK_CP) ? h->h_scal[2] : spk_max_nn(*xi1, *xi2);  // sp.jl:304 (Julia's max propagates NaN)
     res = *xi <= S.tol;
   } else {
     const double t1 = std::max(S.tol * h->res_0[0], S.tol), t2 = std::max(S.tol * h->res_0[1], S.tol);
@@ -1262,7 +1271,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
     SPK_TRY(dev_alloc(h, &nG, nnl * D.k_stride, false));
     SPK_TRY(dev_alloc(h, &nR, nnl * D.r_stride, false));
     const int b = elem_block();
-    const unsigned g = SPK_EMU ? 64 : 148 * 16;
+    const unsigned g = SPK_EMU ? 64 : (unsigned)h->num_sms * 16;
     SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 0, D.abk_stride, n - 1, tABK, nABK);
     SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 0, D.abk_stride, n - 1, tABKt, nABKt);
     SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tK, nK);
@@ -1286,7 +1295,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(dev_alloc(h, &h->ric_q, n * nx));
   SPK_TRY(dev_alloc(h, &h->ric_d, std::max(nnl, 1L) * nu));
   SPK_TRY(dev_alloc(h, &h->ws_L, nr));
-  h->red_blocks = SPK_EMU ? 8 : 148 * 8;
+  h->red_blocks = SPK_EMU ? 8 : h->num_sms * 8;
   SPK_TRY(dev_alloc(h, &h->d_partial, h->red_blocks));
   SPK_TRY(dev_alloc(h, &h->d_scal, 32));
   SPK_TRY(dev_alloc(h, &h->d_pnorm, nnl + 64));
@@ -1397,6 +1406,10 @@ int spk_create(const spk_problem *p, spk_handle **out) {
     if (cudaSetDevice(p->device) != cudaSuccess) { delete h; return fail(SPK_ERR_CUDA, "cudaSetDevice failed"); }
   }
   cudaGetDevice(&h->device);
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->num_sms = sms;
+  }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(SPK_ERR_CUDA, "cudaStreamCreate failed");
@@ -1719,7 +1732,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
     if (h->alg == SPK_CP && ((launched - passes) & 1)) std::swap(h->zv, h->zvbar);  // gated passes did not move the iterate
     ctl_end(h);
     xi1 = c.xi1; xi2 = c.xi2;
-    xi = verbose_log ? std::max(xi1, xi2) : NAN;
+    xi = verbose_log ? spk_max_nn(xi1, xi2) : NAN;
     S.k1 = c.k1; S.k2 = c.k2; S.fb = c.fb;
     const float ms = timer.stop();
     if ((log_xi || log_xi1 || log_xi2 || log_bc) && passes > 0) {
@@ -1727,7 +1740,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
       std::vector<double> lg((size_t)3 * cnt);
       if (cnt > 0) SPK_TRY(rt_d2h(lg.data(), h->d_log, sizeof(double) * 3 * cnt, h->stream));
       for (int k = 0; k < cnt; ++k) {
-        if (log_xi) log_xi[k] = verbose_log ? std::max(lg[3 * k], lg[3 * k + 1]) : NAN;
+        if (log_xi) log_xi[k] = verbose_log ? spk_max_nn(lg[3 * k], lg[3 * k + 1]) : NAN;
         if (log_xi1) log_xi1[k] = lg[3 * k];
         if (log_xi2) log_xi2[k] = lg[3 * k + 1];
         if (log_bc) log_bc[k] = (int32_t)lg[3 * k + 2];

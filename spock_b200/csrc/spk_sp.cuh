@@ -313,20 +313,20 @@ SPK_SP_KERNEL spk_k_Lop_ctl(SpkDims D, SpkPtrs P, const double *__restrict__ x, 
     const double val = (beta == 0.0) ? alpha * op : alpha * op + beta * in[e];
     if (out) out[e] = val;
     if (dot_with) acc[0] += dot_with[e] * val;
-    mx = fmax(mx, fabs(val));
+    mx = spk_max_nn(mx, fabs(val));
   }
   if (absmax) {
 #if SPK_EMU
-    if (mx > *absmax) *absmax = mx;
+    *absmax = spk_max_nn(*absmax, mx);
 #else
     __shared__ double s_m[SPK_SP_THREADS / 32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) mx = spk_max_nn(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, s_m[w]);
-      if (mx > __ldcg(absmax)) atomicMax(reinterpret_cast<unsigned long long *>(absmax), (unsigned long long)__double_as_longlong(mx));
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = spk_max_nn(mx, s_m[w]);
+      if (spk_bits_nn(mx) > spk_bits_nn(__ldcg(absmax))) atomicMax(reinterpret_cast<unsigned long long *>(absmax), (unsigned long long)__double_as_longlong(mx));
     }
 #endif
   }
@@ -343,7 +343,7 @@ SPK_KERNEL void spk_k_terminate(SpkCtl *c, const double *scal, int xi_slot, int 
   const double xi1 = scal[xi_slot], xi2 = scal[xi_slot + 1];
   bool stop;
   if (c->verbose_log) {  // sp.jl:304: xi = max(xi1, xi2) <= tol
-    stop = fmax(xi1, xi2) <= c->tol;
+    stop = (xi1 <= c->tol) && (xi2 <= c->tol);  // false for a NaN residual, like Julia's max(NaN, x) = NaN
   } else {
     const double t1 = fmax(c->tol * c->res0[0], c->tol), t2 = fmax(c->tol * c->res0[1], c->tol);
     stop = (xi1 <= t1) && (xi2 <= t2);

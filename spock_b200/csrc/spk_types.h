@@ -64,4 +64,19 @@ SPK_HD const double *spk_sqrtQN(const SpkDims &D, const SpkPtrs &P, long leaf) {
   return P.sqrtQN + id * (D.cost_dense ? (long)D.nx * D.nx : (long)D.nx);
 }
 
+// Maximum of NON-NEGATIVE doubles (|.| of residual entries) that PROPAGATES NaN like LinearAlgebra.norm(., Inf) in
+// should_terminate! (cp.jl:77-78, sp.jl:294-295): the IEEE bit patterns of non-negative doubles are monotone as
+// integers and every sign-cleared NaN pattern lies above +Inf, so an integer maximum of the bit patterns is exact and
+// keeps a NaN once it has been seen (fmax and `a > b ? a : b` both drop it: a diverged iterate would look converged).
+SPK_HD long long spk_bits_nn(double a) {
+#if !SPK_EMU && defined(__CUDA_ARCH__)
+  return __double_as_longlong(a);
+#else
+  long long i;
+  memcpy(&i, &a, sizeof(i));
+  return i;
+#endif
+}
+SPK_HD double spk_max_nn(double a, double b) { return spk_bits_nn(a) >= spk_bits_nn(b) ? a : b; }
+
 SPK_HD double spk_clip(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }  // constraints.jl:28-30

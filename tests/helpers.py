@@ -104,3 +104,161 @@ def check_k_steps(lib, flat, alg, K, factor_mode=0, tol=1e-9, x0=None):
     h.close()
     assert ez <= tol and ev <= tol, (ez, ev)
     return ez, ev
+
+
+# ------------------------------------------------------------------------------------------------ SOC branches, warm start, NaN
+# (shared by tests/test_gpu_headline_parity.py -- the CUDA path -- and tests/test_hostemu_parity.py)
+
+def soc_mode(t, x):
+    """risk_measures.jl:57-70: 0 = inside (||x|| <= t), 1 = polar (||x|| <= -t), 2 = general."""
+    n = np.linalg.norm(x)
+    return 0 if n <= t else (1 if n <= -t else 2)
+
+
+def force_soc_branches(flat, vo, v, big=60.0):
+    """Overwrites the `t` entries of the three SOC families in v so that block j takes branch j % 3:
+    child SOC (t = v6_j; x = v3_j, v4_j, v5_j; implicit_l.jl:854-900), leaf SOC (t = v13; x = v11, v12; :752-810) and,
+    with an SOC inside the risk cone, its t entry in v1_i (:833-845)."""
+    n, nnl, nl = flat.n, flat.n_non_leaf, flat.n_leaf
+    pattern = np.array([big, -big, 0.0])
+    j = np.arange(n - 1)
+    sel = j % 3 != 2
+    v[vo[5] + j[sel]] = pattern[j[sel] % 3]
+    l = np.arange(nl)
+    sel = l % 3 != 2
+    v[vo[9] + l[sel]] = pattern[l[sel] % 3]
+    off = 0
+    for ct, cd in zip(flat.cone_type, flat.cone_dim):
+        if ct == 4:
+            i = np.arange(nnl)
+            sel = i % 3 != 2
+            v[vo[0] + i[sel] * flat.ny + off] = pattern[i[sel] % 3]
+        off += int(cd)
+    return v
+
+
+def classify_soc_after_one_pass(flat, o, z0, v0, sigma):
+    """Branch taken by every SOC block of prox_h_conj! in the oracle's first pass from (z0, v0), recomputed in numpy from
+    w = (v + sigma L(2 zbar - z)) / sigma with the +-1/2 shifts (implicit_l.jl:911-951)."""
+    n, nnl, nl, nx, nu, ny = flat.n, flat.n_non_leaf, flat.n_leaf, flat.nx, flat.nu, flat.ny
+    _, vo = o.offsets()
+    zbar = o.z.copy()  # lambda = 1: z after the pass is zbar
+    w = (v0 + sigma * o.L(2 * zbar - z0)) / sigma
+    w[vo[4]:vo[4] + n - 1] -= 0.5
+    w[vo[5]:vo[5] + n - 1] += 0.5
+    w[vo[8]:vo[8] + nl] -= 0.5
+    w[vo[9]:vo[9] + nl] += 0.5
+    child = [soc_mode(w[vo[5] + j], np.concatenate([w[vo[2] + j * nx: vo[2] + (j + 1) * nx], w[vo[3] + j * nu: vo[3] + (j + 1) * nu],
+                                                    [w[vo[4] + j]]])) for j in range(n - 1)]
+    leaf = [soc_mode(w[vo[9] + l], np.concatenate([w[vo[7] + l * nx: vo[7] + (l + 1) * nx], [w[vo[8] + l]]])) for l in range(nl)]
+    risk, off = [], 0
+    for ct, cd in zip(flat.cone_type, flat.cone_dim):
+        if ct == 4:
+            risk = [soc_mode(w[vo[0] + i * ny + off], w[vo[0] + i * ny + off + 1: vo[0] + i * ny + off + cd]) for i in range(nnl)]
+        off += int(cd)
+    return child, leaf, risk
+
+
+def check_soc_branches(lib, flat):
+    """Every branch of the SOC projection, for the child, leaf and (l2-ball) risk-cone SOCs, through one full pass of the
+    operator evaluation against the oracle at 1e-12 (which dual kernel runs is chosen by the caller's environment)."""
+    rng = np.random.default_rng(99)
+    o = Oracle(flat, CP)
+    _, vo = o.offsets()
+    z0 = 0.2 * rng.standard_normal(o.nz)
+    v0 = force_soc_branches(flat, vo, rng.standard_normal(o.nv))
+    x0 = 0.1 * np.ones(flat.nx)
+    o.set_x0(x0)
+    o.z[:], o.v[:] = z0, v0
+    o.step(1)
+    child, leaf, risk = classify_soc_after_one_pass(flat, o, z0, v0, o.default_step())
+    assert set(child) == {0, 1, 2} and set(leaf) == {0, 1, 2}
+    if 4 in list(flat.cone_type):
+        assert set(risk) == {0, 1, 2}
+    for fm in (0, 1):
+        h = Handle(flat, CP, factor_mode=fm, lib=lib)
+        h.set_x0(x0)
+        h.set_iterate(z0, v0)
+        h.step(1)
+        z, v = h.get_iterate()
+        h.close()
+        assert relerr(z, o.z) < 1e-12 and relerr(v, o.v) < 1e-12, fm
+        assert np.max(np.abs(v - o.v)) < 1e-10
+
+
+def check_soc_edge_vectors(lib):
+    """Explicit vectors through spk_apply(SPK_OP_PROX_HCONJ): for one child SOC and one leaf SOC each of
+    inside / polar / general / zero-norm (x = 0 with t > 0, t < 0 and t = 0; risk_measures.jl:57-70 never divides by a zero
+    norm because ||x|| > |t| >= 0 in the general branch) and the boundary ||x|| == t."""
+    flat = flatten_problem(*get_server_heat_specs(4, 3, 3, risk="l2ball"))
+    o = Oracle(flat, CP)
+    _, vo = o.offsets()
+    n, nl, nx, nu = flat.n, flat.n_leaf, flat.nx, flat.nu
+    sigma = 0.4
+    h = Handle(flat, CP, lib=lib)
+    rng = np.random.default_rng(5)
+    cases = [("inside", 5.0, 1.0), ("polar", -5.0, 1.0), ("general", 0.3, 1.0), ("zero_norm_pos_t", 2.0, 0.0),
+             ("zero_norm_neg_t", -2.0, 0.0), ("zero_norm_zero_t", 0.0, 0.0), ("boundary", 1.0, None)]
+    for name, t, scale in cases:
+        w = np.zeros(o.nv)  # the vector AFTER the 1/sigma scaling and the +-1/2 shifts; mapped back to prox_h_conj!'s argument below
+        j, l = 4, 2
+        xc = rng.standard_normal(nx + nu + 1)
+        xl = rng.standard_normal(nx + 1)
+        if scale is None:
+            xc, xl = xc / np.linalg.norm(xc) * t, xl / np.linalg.norm(xl) * t
+        else:
+            xc, xl = xc * scale, xl * scale
+        w[vo[2] + j * nx: vo[2] + (j + 1) * nx] = xc[:nx]
+        w[vo[3] + j * nu: vo[3] + (j + 1) * nu] = xc[nx:nx + nu]
+        w[vo[4] + j], w[vo[5] + j] = xc[-1], t
+        w[vo[7] + l * nx: vo[7] + (l + 1) * nx] = xl[:nx]
+        w[vo[8] + l], w[vo[9] + l] = xl[-1], t
+        arg = w.copy()
+        arg[vo[4]:vo[4] + n - 1] += 0.5
+        arg[vo[5]:vo[5] + n - 1] -= 0.5
+        arg[vo[8]:vo[8] + nl] += 0.5
+        arg[vo[9]:vo[9] + nl] -= 0.5
+        arg *= sigma
+        got, want = h.prox_h_conj(arg, sigma), o.prox_h_conj(arg, sigma)
+        assert np.all(np.isfinite(got)), name
+        assert np.max(np.abs(got - want)) < 1e-13 * max(1.0, np.max(np.abs(want))), name
+    h.close()
+
+
+def check_warm_started_second_solve(lib, alg, tol):
+    """solve_model! twice on the same model (cpock.jl:169-189 / spock.jl:231-251): the second solve starts from the first
+    one's (z, v) -- and, for SuperMann, from its stale Anderson memory, z_old, rz_old, delta -- with a new x0.
+    Same number of passes and the iterate within 1e-9 of the oracle after both solves.  (SuperMann: a loose tolerance keeps
+    both solves inside the <= 30 passes for which SP parity is defined.)"""
+    flat = flatten_problem(*get_server_heat_specs(7, 5, 2))
+    for fm in (0, 1):
+        h, o = Handle(flat, alg, factor_mode=fm, lib=lib), Oracle(flat, alg)
+        total = 0
+        for x0 in (0.1 * np.ones(5), np.array([0.3, -0.2, 0.1, 0.25, -0.3])):
+            rh, _ = h.solve(x0, tol=tol)
+            ro, _ = o.solve(x0, tol=tol)
+            assert rh["passes"] == ro["passes"] and rh["converged"] == ro["converged"] == 1
+            total += ro["passes"]
+            if alg == SP:
+                assert total <= 30
+                assert (rh["k1_count"], rh["k2_count"], rh["fallback_count"]) == (ro["k1_count"], ro["k2_count"], ro["fallback_count"])
+            z, v = h.get_iterate()
+            assert relerr(z, o.z) < 1e-9 and relerr(v, o.v) < 1e-9
+        h.close()
+
+
+def check_nan_never_converges(lib, alg):
+    """A NaN in x0 makes every residual NaN; the reference's `xi <= tol` is then false and it runs to MAX_ITER
+    (cp.jl:102, sp.jl:323).  The residual maxima of the product path must keep the NaN (spk_max_nn)."""
+    flat = flatten_problem(*get_server_heat_specs(5, 5, 2))
+    x0 = 0.1 * np.ones(5)
+    x0[2] = np.nan
+    for fm in (0, 1):
+        h = Handle(flat, alg, factor_mode=fm, lib=lib)
+        res, _ = h.solve(x0, tol=1e-3, max_iter=12)
+        assert res["converged"] == 0 and res["passes"] == 12
+        assert np.isnan(res["xi1"]) or np.isnan(res["xi2"])
+        h.close()
+    o = Oracle(flat, alg)
+    ro, _ = o.solve(x0, tol=1e-3, max_iter=12)
+    assert ro["converged"] == 0 and ro["passes"] == 12

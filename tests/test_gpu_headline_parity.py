@@ -1,0 +1,139 @@
+"""GPU parity in the regime the headline numbers are measured in (VERDICT r01 "weak" 1-2):
+
+* the steady-state body of the persistent family kernels -- a CTA takes a second, third ... family only when a level
+  has more families than resident CTAs, so the chunked TMA re-fetch into shared memory that was just consumed, the
+  mbarrier phase flips and the one-family-ahead cp.async staging run only there (spk_fused.cuh spk_k_bwd /
+  spk_k_fwd_s1): wide levels of the config-3 shapes, and every specialised shape with the grid capped at 3 CTAs
+  (SPK_MAX_CTAS) so that even a 63-family level loops 21 times per CTA;
+* config 5's combination: (10,10,4) with the l2-ball (SOC) risk measure on 4096-family levels;
+* the three branches of the SOC projection (risk_measures.jl:57-70) for the leaf, child and risk-cone SOCs on the
+  CUDA path: forced per node, classified from the oracle's pre-projection vector, all present, and compared with the
+  oracle on every implementation of the dual kernel;
+* a warm-started second solve (cpock.jl:180-186) against the oracle;
+* a NaN iterate never reports convergence (LinearAlgebra.norm(., Inf) propagates NaN, cp.jl:77-78,102).
+All through the C ABI (ctypes), fp64, tolerance 1e-9 relative after K passes (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import CP, SP, Oracle
+from spock_b200.examples import get_random_system_specs, get_server_heat_specs
+from spock_b200.handle import Handle
+from spock_b200.problem import flatten_problem
+from tests.helpers import (check_nan_never_converges, check_soc_branches, check_soc_edge_vectors,
+                           check_warm_started_second_solve, relerr)
+
+pytestmark = pytest.mark.gpu
+
+X0 = 0.1
+
+
+def _run_pair(cuda_lib, flat, alg, K, factor_modes=(0, 1), z0=None, v0=None, x0=None):
+    """K passes on the GPU (each factor mode) and in the oracle from the same start; returns the GPU iterates."""
+    x0 = X0 * np.ones(flat.nx) if x0 is None else x0
+    o = Oracle(flat, alg)
+    o.set_x0(x0)
+    if z0 is not None:
+        o.z[:], o.v[:] = z0, v0
+    o.step(K)
+    out = []
+    for fm in factor_modes:
+        h = Handle(flat, alg, factor_mode=fm, lib=cuda_lib)
+        h.set_x0(x0)
+        if z0 is not None:
+            h.set_iterate(z0, v0)
+        h.step(K)
+        z, v = h.get_iterate()
+        xi = h.residuals()
+        h.close()
+        ez, ev = relerr(z, o.z), relerr(v, o.v)
+        assert ez < 1e-9 and ev < 1e-9, (alg, fm, ez, ev)
+        out.append((z, v, xi))
+    return o, out
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(50, 20, 2, 13), (50, 50, 2, 12)])
+@pytest.mark.parametrize("alg,K", [(CP, 10), (SP, 5)])
+def test_wide_levels_of_the_headline_shapes_match_oracle(cuda_lib, nx, nu, d, N, alg, K):
+    """Per-node factors at N=12/13: 1024-2048 families on the deepest level against <= 444-592 resident CTAs, i.e. every
+    CTA of spk_k_bwd / spk_k_fwd_s1 runs the SPLIT re-fetch loop 2-5 times; per-stage factors run the DMMA kernels on the
+    same levels.  Both against the oracle and against each other (1e-11)."""
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    _, out = _run_pair(cuda_lib, flat, alg, K)
+    (zn, vn, _), (zs, vs, _) = out
+    assert relerr(zn, zs) < 1e-11 and relerr(vn, vs) < 1e-11
+
+
+@pytest.mark.parametrize("alg,K", [(CP, 10), (SP, 5)])
+def test_config5_combination_matches_oracle(cuda_lib, alg, K):
+    """(10,10,4) with the l2-ball ambiguity set (SOC inside the risk cone, ny = 2d+2), N=8: 21845 nodes, 4096 families on
+    the deepest non-leaf level -- config 5's kernels (spk_k_dual3<10,10,4>, spk_k_s2t<10,4>) at a width where they loop."""
+    flat = flatten_problem(*get_server_heat_specs(8, 10, 4, risk="l2ball"))
+    _, out = _run_pair(cuda_lib, flat, alg, K)
+    (zn, vn, _), (zs, vs, _) = out
+    assert relerr(zn, zs) < 1e-11 and relerr(vn, vs) < 1e-11
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(50, 20, 2, 7), (50, 50, 2, 7), (20, 20, 2, 8), (10, 10, 4, 5), (10, 10, 2, 8),
+                                       (5, 5, 2, 8), (20, 20, 3, 5), (10, 10, 3, 6), (7, 3, 2, 7)])
+def test_persistent_loop_body_with_capped_grid(cuda_lib, nx, nu, d, N, monkeypatch):
+    """SPK_MAX_CTAS=3: every level with more than 3 families makes each CTA stride over many families, so the loop body
+    after the first family (prefetch of the next family's vector entries, factor re-fetch, barrier phases) is what
+    computes the result -- for every specialised shape and for the runtime-size instantiation ((7,3,2) has no
+    specialisation).  Random start so that no block of the iterate is trivially zero."""
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    rng = np.random.default_rng(nx * 100 + d)
+    o = Oracle(flat, CP)
+    z0, v0 = 0.3 * rng.standard_normal(o.nz), 0.3 * rng.standard_normal(o.nv)
+    monkeypatch.setenv("SPK_MAX_CTAS", "3")
+    _, capped = _run_pair(cuda_lib, flat, CP, 6, z0=z0, v0=v0)
+    _run_pair(cuda_lib, flat, SP, 4, z0=z0, v0=v0)
+    monkeypatch.setenv("SPK_MAX_CTAS", "0")
+    _, free = _run_pair(cuda_lib, flat, CP, 6, z0=z0, v0=v0)
+    for (zc, vc, xc), (zf, vf, xf) in zip(capped, free):
+        # the family-to-CTA assignment does not change any family's arithmetic: bitwise equal iterates, equal residual maxima
+        assert np.array_equal(zc, zf) and np.array_equal(vc, vf) and xc == xf
+
+
+# ------------------------------------------------------------------------------------------------ SOC branches
+
+def _set_dual_variant(monkeypatch, variant):
+    for name in ("SPK_NO_DUAL3", "SPK_DUAL_V1", "SPK_DISABLE_FUSED"):
+        monkeypatch.setenv(name, "0")
+    if variant in ("dual2", "dual_v1"):
+        monkeypatch.setenv("SPK_NO_DUAL3", "1")
+    if variant == "dual_v1":
+        monkeypatch.setenv("SPK_DUAL_V1", "1")
+    if variant == "modular":
+        monkeypatch.setenv("SPK_DISABLE_FUSED", "1")
+
+
+@pytest.mark.parametrize("variant", ["dual3", "dual2", "dual_v1", "modular"])
+@pytest.mark.parametrize("spec", [("heat_l2", 5, 10, 4), ("heat_l2", 4, 3, 3), ("random", 6, 50, 20, 2)])
+def test_soc_branches_on_the_cuda_path(cuda_lib, spec, variant, monkeypatch):
+    """Every branch of the SOC projection, for the child, leaf and (l2-ball) risk-cone SOCs, through one full pass of the
+    fused path -- on the register-resident dual kernel (the production kernel), the batched and the warp-per-family dual
+    kernels, and the modular prox_h_conj kernels -- against the oracle at 1e-12."""
+    if spec[0] == "heat_l2":
+        flat = flatten_problem(*get_server_heat_specs(spec[1], spec[2], spec[3], risk="l2ball"))
+    else:
+        flat = flatten_problem(*get_random_system_specs(spec[1], spec[4], spec[2], spec[3]))
+    _set_dual_variant(monkeypatch, variant)
+    check_soc_branches(cuda_lib, flat)
+
+
+def test_soc_edge_vectors_through_prox_h_conj(cuda_lib):
+    check_soc_edge_vectors(cuda_lib)
+
+
+# ------------------------------------------------------------------------------------------------ warm start, NaN
+
+@pytest.mark.parametrize("alg,tol", [(CP, 1e-4), (SP, 1e-1)])
+def test_warm_started_second_solve_matches_oracle(cuda_lib, alg, tol):
+    check_warm_started_second_solve(cuda_lib, alg, tol)
+
+
+@pytest.mark.parametrize("alg", [CP, SP])
+@pytest.mark.parametrize("host_loop", ["0", "1"])
+def test_nan_iterate_never_reports_convergence(cuda_lib, alg, host_loop, monkeypatch):
+    monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
+    check_nan_never_converges(cuda_lib, alg)

@@ -6,7 +6,8 @@ import pytest
 
 from oracle.oracle import CP, SP, Oracle
 from spock_b200.handle import Handle
-from tests.helpers import SMALL_PROBLEMS, check_k_steps, check_operators, flat_of, golden_cp, golden_sp, relerr
+from tests.helpers import (SMALL_PROBLEMS, check_k_steps, check_nan_never_converges, check_operators, check_soc_branches,
+                           check_soc_edge_vectors, check_warm_started_second_solve, flat_of, golden_cp, golden_sp, relerr)
 
 
 @pytest.mark.parametrize("factor_mode", [0, 1])
@@ -168,3 +169,30 @@ def test_build_model_with_estimated_L_norm(emu_lib):
         passes.append(m.last_result["passes"])
         m.handle.close()
     assert passes[1] < passes[0]
+
+
+@pytest.mark.parametrize("variant", ["dual2", "dual_v1", "modular"])
+@pytest.mark.parametrize("name", ["l2ball_N4_d3_nx3", "heat_N7_d2_nx5"])
+def test_soc_branches(emu_lib, name, variant, monkeypatch):
+    """inside / polar / general branch of the child, leaf and risk-cone SOCs through one pass (see tests/helpers.py)"""
+    monkeypatch.setenv("SPK_DUAL_V1", "1" if variant == "dual_v1" else "0")
+    monkeypatch.setenv("SPK_DISABLE_FUSED", "1" if variant == "modular" else "0")
+    check_soc_branches(emu_lib, flat_of(name))
+
+
+def test_soc_edge_vectors(emu_lib):
+    check_soc_edge_vectors(emu_lib)
+
+
+@pytest.mark.parametrize("alg,tol", [(CP, 1e-4), (SP, 1e-1)])
+@pytest.mark.parametrize("host_loop", ["0", "1"])
+def test_warm_started_second_solve_matches_oracle(emu_lib, alg, tol, host_loop, monkeypatch):
+    monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
+    check_warm_started_second_solve(emu_lib, alg, tol)
+
+
+@pytest.mark.parametrize("alg", [CP, SP])
+@pytest.mark.parametrize("host_loop", ["0", "1"])
+def test_nan_iterate_never_reports_convergence(emu_lib, alg, host_loop, monkeypatch):
+    monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
+    check_nan_never_converges(emu_lib, alg)
