@@ -137,6 +137,7 @@ struct spk_handle {
   SpkComm comm;
   int rank = 0, world = 1, t_cut = 0;
   long m_sub = 1;
+  bool gathered = false;  // the device iterate is complete on this rank (spk_gather_iterate since the last pass)
   // fused path (spk_fused.cuh)
   bool fused_ok = false, shape_specialised = false;
   void (*k_bwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
@@ -1458,10 +1459,68 @@ int spk_set_iterate(spk_handle *h, const double *z, const double *v) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
   if (z) SPK_TRY(rt_h2d(h->z(), z, sizeof(double) * h->D.nz, h->stream));
   if (v) SPK_TRY(rt_h2d(h->v(), v, sizeof(double) * h->D.nv, h->stream));
+  h->gathered = z && v;  // complete host vectors make the device iterate complete on this rank
   return SPK_OK;
 }
+// The contiguous slices [off, off+len) of z and of v that the families of this rank write: for a
+// range [a, b) of owned families the entries indexed by the family's node (u, y, v1, v2, v7), by its children (x, s, tau,
+// v3..v6) and, for leaf children, by the leaf ordinal (v11..v14); plus x_1 and s_1 with the root family.
+template <class F>
+static void for_each_owned_slice(const spk_handle *h, F &&fn) {  // fn(bool in_v, long off, long len)
+  const SpkDims &D = h->D;
+  SpkFusedArgs R;
+  R.gate = nullptr; R.vec2 = 0;
+  fill_ranges(h, R);
+  for (int k = 0; k < R.n_ranges; ++k) {
+    const long a = R.r_start[k], b = a + (R.r_prefix[k + 1] - R.r_prefix[k]);
+    if (b <= a) continue;
+    const long c0 = (long)D.d * a + 1, c1 = (long)D.d * b + 1;  // children nodes [c0, c1)
+    if (a == 0) { fn(false, 0, D.nx); fn(false, D.zo[2], 1); }
+    fn(false, D.zo[1] + a * D.nu, (b - a) * D.nu);
+    fn(false, D.zo[4] + a * D.ny, (b - a) * D.ny);
+    fn(false, c0 * D.nx, (c1 - c0) * D.nx);
+    fn(false, D.zo[2] + c0, c1 - c0);
+    fn(false, D.zo[3] + c0 - 1, c1 - c0);
+    fn(true, D.vo[0] + a * D.ny, (b - a) * D.ny);
+    fn(true, D.vo[1] + a, b - a);
+    fn(true, D.vo[6] + a * (D.nx + D.nu), (b - a) * (D.nx + D.nu));
+    fn(true, D.vo[2] + (c0 - 1) * D.nx, (c1 - c0) * D.nx);
+    fn(true, D.vo[3] + (c0 - 1) * D.nu, (c1 - c0) * D.nu);
+    fn(true, D.vo[4] + c0 - 1, c1 - c0);
+    fn(true, D.vo[5] + c0 - 1, c1 - c0);
+    if (c1 - 1 >= D.nnl) {  // (part of) the children are leaves; a level is either all leaves or none
+      const long l0 = std::max(c0, D.nnl) - D.nnl, l1 = c1 - D.nnl;
+      fn(true, D.vo[7] + l0 * D.nx, (l1 - l0) * D.nx);
+      fn(true, D.vo[8] + l0, l1 - l0);
+      fn(true, D.vo[9] + l0, l1 - l0);
+      fn(true, D.vo[10] + l0 * D.nx, (l1 - l0) * D.nx);
+    }
+  }
+}
+
 int spk_get_iterate(spk_handle *h, double *z, double *v) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->world > 1 && !h->gathered) {
+    // subtree partition: only the entries this rank's families write are valid here, so only they are copied (1/world of
+    // the iterate plus the replicated top); the other entries of the host vectors are left untouched.  After
+    // spk_gather_iterate the whole device iterate is valid and is copied in one piece.
+    int rc = SPK_OK;
+#ifndef SPK_HOST_EMU
+    for_each_owned_slice(h, [&](bool in_v, long off, long len) {
+      double *dst = in_v ? v : z;
+      if (!dst || len <= 0 || rc != SPK_OK) return;
+      const cudaError_t e = cudaMemcpyAsync(dst + off, (in_v ? h->v() : h->z()) + off, sizeof(double) * len, cudaMemcpyDeviceToHost, h->stream);
+      if (e != cudaSuccess) rc = fail(SPK_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e));
+    });
+#else
+    for_each_owned_slice(h, [&](bool in_v, long off, long len) {
+      double *dst = in_v ? v : z;
+      if (dst && len > 0) memcpy(dst + off, (in_v ? h->v() : h->z()) + off, sizeof(double) * len);
+    });
+#endif
+    SPK_TRY(rc);
+    return rt_sync(h->stream);
+  }
   if (z) SPK_TRY(rt_d2h(z, h->z(), sizeof(double) * h->D.nz, h->stream));
   if (v) SPK_TRY(rt_d2h(v, h->v(), sizeof(double) * h->D.nv, h->stream));
   return SPK_OK;
@@ -1568,6 +1627,7 @@ struct LoopTimer {
 int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
   LoopState S;
+  h->gathered = false;
   default_steps(h, gamma, sigma);
   S.gamma = gamma; S.sigma = sigma; S.tol = 0.0; S.verbose_log = 0;
   SPK_TRY(ctl_begin(h, 0.0, 0, 1));  // also clears the device-side `done` flag that gates the fused kernels
@@ -1697,6 +1757,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
     SPK_TRY(spk_set_iterate(h, z0, v0));
   }
   if (h->world > 1 && verbose_log) return fail(SPK_ERR_INVALID, "verbose=LOG is single-GPU only");
+  h->gathered = false;
   SPK_TRY(spk_set_x0(h, x0));                      // :185
   h->res_0[0] = h->res_0[1] = -INFINITY;           // :186
   LoopState S;
@@ -1854,6 +1915,7 @@ int spk_gather_iterate(spk_handle *h) {
       SPK_TRY(gather(v + D.vo[10], l0, ccnt, D.nx));
     }
   }
+  h->gathered = true;
   return rt_sync(h->stream);
 }
 

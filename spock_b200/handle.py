@@ -34,6 +34,7 @@ class Handle:
         check(self.lib, self.lib.spk_offsets(self._h, zo, vo))
         self.z_off, self.v_off = [int(x) for x in zo], [int(x) for x in vo]
         self.L_norm = L_norm if L_norm > 0 else (3.28 if algorithm == SP else 10.0)
+        self.rank, self.world_size = rank, max(1, world_size)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -60,8 +61,13 @@ class Handle:
             raise ValueError("z or v has the wrong length")  # implicit_l.jl:184-186
         check(self.lib, self.lib.spk_set_iterate(self._h, dptr(z), dptr(v)))
 
-    def get_iterate(self):
-        z, v = np.empty(self.nz), np.empty(self.nv)
+    def get_iterate(self, z=None, v=None):
+        """(z, v) in the reference layout.  Under the subtree partition (world_size > 1) only the entries this rank's
+        families own are copied -- the rest keeps the caller's values (zeros in fresh arrays) -- unless gather_iterate()
+        was called since the last pass."""
+        alloc = np.empty if self.world_size == 1 else np.zeros
+        z = alloc(self.nz) if z is None else z
+        v = alloc(self.nv) if v is None else v
         check(self.lib, self.lib.spk_get_iterate(self._h, dptr(z), dptr(v)))
         return z, v
 

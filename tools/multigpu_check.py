@@ -96,6 +96,19 @@ for name, spec, K in (("heat N=8 nx=5", get_server_heat_specs(8, 5, 2), 12), ("r
         ref.close()
     h.close()
     dist.barrier()
+# the headline shape on wide levels (2048-4096 families per level and rank: the persistent family kernels loop), over NCCL
+# incl. spk_gather_iterate: the complete iterate on every rank equals the single-GPU one
+from spock_b200.distributed import partition_parity  # noqa: E402
+
+wide = []
+flat = flatten_problem(*get_random_system_specs(14, 2, 50, 20))
+for alg, K, fm in ((1, 10, 0), (1, 10, 1), (2, 5, 1), (2, 5, 0)):
+    r = partition_parity(lib, flat, alg, K, fm, rank, world, local)
+    assert r["relerr_z"] < 1e-9 and r["relerr_v"] < 1e-9 and r["gathered_iterate_identical_on_all_ranks"], r
+    wide.append(r)
+if rank == 0:
+    import json
+    print("MULTIGPU_WIDE " + json.dumps(wide), flush=True)
 if rank == 0:
     print(f"MULTIGPU_OK world={world} max_rel_err={worst_all:.2e} supermann_max_rel_err={sp_err:.2e}", flush=True)
 dist.destroy_process_group()
