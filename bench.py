@@ -444,9 +444,33 @@ def main():
     gen, N, d, nx, nu, desc = WORKLOADS[args.workload]
     fm = 0 if args.factor_mode == "per_node" else 1
 
+    # `--gpus N` without torchrun: ONE process drives the N GPUs through a device-group handle (spk_problem.devices: one
+    # host thread, stream and NCCL rank per device) -- the way the single-process Julia host reaches several GPUs
+    devices = list(range(args.gpus)) if (world == 1 and args.gpus > 1) else None
+    ngpu = world * (len(devices) if devices else 1)
+
     # ---- N > 1: before anything is timed, the partitioned path against one GPU on a slice of the workload
     #      (K passes, spk_gather_iterate, compared on rank 0): Chambolle-Pock in the benchmarked factor mode and SuperMann
     mg_parity = None
+    if devices:
+        Ns = min(N, SAMPLE_N[args.workload] + (1 if d == 2 else 0))
+        flat_s = flatten_problem(*make_spec(args.workload, Ns))
+        mg_parity = {}
+        for key, alg, K, mode in (("cp", 1, 10, fm), ("sp", 2, 5, 1)):
+            out = []
+            for dv in (devices, None):
+                hh = Handle(flat_s, alg, factor_mode=mode, device=0, devices=dv)
+                hh.set_x0(0.1 * np.ones(nx))
+                hh.step(K)
+                out.append(hh.get_iterate() + (hh.residuals(), hh.device_bytes()))
+                hh.close()
+            (zg, vg, xg, bg), (zr, vr, xr, _) = out
+            mg_parity[key] = {"nodes": int(flat_s.n), "passes": K, "algorithm": key.upper(), "devices": len(devices),
+                              "factor_mode": "per_node" if mode == 0 else "per_stage", "relerr_z": relerr(zg, zr), "relerr_v": relerr(vg, vr),
+                              "relerr_xi": abs(xg[0] - xr[0]) / xr[0], "device_bytes_all_devices": bg,
+                              "how": "single-process device group: spk_get_iterate assembles (z, v) from the devices' owned slices"}
+        mg_parity["ok"] = all(p["relerr_z"] < 1e-9 and p["relerr_v"] < 1e-9 for p in (mg_parity["cp"], mg_parity["sp"]))
+        del flat_s
     if world > 1:
         Ns = min(N, SAMPLE_N[args.workload] + (1 if d == 2 else 0))
         flat_s = flatten_problem(*make_spec(args.workload, Ns))
@@ -458,17 +482,18 @@ def main():
 
     flat = flatten_problem(*make_spec(args.workload))
     comm_id = broadcast_comm_id(lib, rank) if world > 1 else None
-    h = Handle(flat, 1, factor_mode=fm, device=local_rank, rank=rank, world_size=world, comm_id=comm_id)
+    h = Handle(flat, 1, factor_mode=fm, device=local_rank, rank=rank, world_size=world, comm_id=comm_id, devices=devices)
 
     def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
+        for dv in (devices or [local_rank]):
+            torch.cuda.synchronize(dv)
+        if dist.is_initialized():
             dist.barrier()
             torch.cuda.synchronize()
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
+        if dist.is_initialized():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -477,7 +502,7 @@ def main():
     h.set_x0(x0)
     PARITY_K = 10
     z_pn = v_pn = None
-    want_parity = (not args.no_extras) and world == 1 and fm == 0
+    want_parity = (not args.no_extras) and world == 1 and not devices and fm == 0
     h.step(PARITY_K if want_parity else args.warmup)  # from (z, v) = 0: also the first PARITY_K passes of the parity block
     if want_parity:
         z_pn, v_pn = h.get_iterate()
@@ -486,6 +511,7 @@ def main():
     # ---- timed region: exactly K passes, device time from CUDA events on the solver stream, max over ranks
     sampler = ClockSampler(local_rank)
     sampler.start()
+    world_t, world = world, ngpu  # from here on `world` = GPUs sharing the work (ranks x devices per process)
     l0 = h.launch_count()
     barrier()
     ms = h.step(args.steps)
@@ -529,7 +555,7 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     t_steps = max_over_ranks(t_steps)
-    d2h_iterate = 8 * (h.nz + h.nv) / world
+    d2h_iterate = 8 * (h.nz + h.nv) / world_t
     e2e = {"value": args.steps / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 8 * nx,
            "d2h_bytes_per_step": 16 + d2h_iterate / args.steps,
            "value_without_final_iterate_copy": args.steps / t_steps,
@@ -569,6 +595,7 @@ def main():
             "metric": "cp_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+            "launch_mode": ("one process, device group of %d GPUs" % len(devices)) if devices else ("torchrun, one process per GPU" if world > 1 else "one process, one GPU"),
             "device_bytes": h.device_bytes(), "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "protocol": protocol,
         }
@@ -690,7 +717,7 @@ def main():
         print(json.dumps(line), flush=True)
     else:
         h.close()
-    if world > 1:
+    if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
 

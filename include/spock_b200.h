@@ -12,6 +12,8 @@
  *
  * Every function returns 0 (SPK_OK) or a spk_status code and never throws; spk_last_error() returns a
  * message for the calling thread's last failure.  One handle = one owner thread; calls are synchronous.
+ * Multi-GPU: either one process per GPU (spk_problem.rank / world_size / comm_id; torchrun, MPI) or all GPUs of
+ * the node behind one handle in one process (spk_problem.n_devices / devices).
  * There is no CPU fallback: without a CUDA device spk_create fails with SPK_ERR_CUDA.
  *
  * All matrices are column-major (Julia layout), all reals are IEEE binary64, node numbers are the
@@ -86,6 +88,12 @@ typedef struct {
   /* multi-GPU: this process owns the subtrees rank*m .. (rank+1)*m-1 below the cut stage; world_size 1 = whole tree */
   int32_t rank, world_size;
   const uint8_t *comm_id; /* 128 bytes from spk_comm_unique_id (rank 0), broadcast by the host; NULL if world_size == 1 */
+  /* multi-GPU inside ONE process (the reference's host is one Julia process, src/models/cpock.jl:169): n_devices > 1
+   * partitions the tree over these CUDA ordinals behind a single handle -- one host thread, stream and NCCL rank per
+   * device, bootstrapped internally; rank / world_size / comm_id must then be 0 / 1 / NULL.  Every call on the handle
+   * fans out to all devices; spk_get_iterate assembles the complete (z, v) in the caller's host vectors.  0 or 1: `device`. */
+  int32_t n_devices;
+  const int32_t *devices;
 } spk_problem;
 
 typedef struct {

@@ -43,6 +43,7 @@ class SpkProblem(C.Structure):
         ("x_min", C.c_double), ("x_max", C.c_double), ("u_min", C.c_double), ("u_max", C.c_double),
         ("algorithm", C.c_int32), ("L_norm", C.c_double), ("factor_mode", C.c_int32), ("device", C.c_int32),
         ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.POINTER(C.c_uint8)),
+        ("n_devices", C.c_int32), ("devices", _i32p),
     ]
 
 
@@ -129,7 +130,7 @@ def dptr(a):
 
 
 def make_problem(flat, algorithm: int, L_norm: float = 0.0, factor_mode: int = FACTORS_PER_NODE, device: int = -1,
-                 rank: int = 0, world_size: int = 1, comm_id=None):
+                 rank: int = 0, world_size: int = 1, comm_id=None, devices=None):
     """FlatProblem -> (SpkProblem, keepalive list)."""
     ct = np.ascontiguousarray(flat.cone_type, dtype=np.int32)
     cd = np.ascontiguousarray(flat.cone_dim, dtype=np.int32)
@@ -146,6 +147,10 @@ def make_problem(flat, algorithm: int, L_norm: float = 0.0, factor_mode: int = F
         flat.N, flat.d, flat.nx, flat.nu, dptr(A), dptr(B), flat.cost_dense, flat.n_sqrtQ, dptr(sQ), dptr(sR),
         flat.n_sqrtQN, dptr(sQN), flat.ny, dptr(E), dptr(F), dptr(b), len(ct), ct.ctypes.data_as(_i32p),
         cd.ctypes.data_as(_i32p), flat.x_min, flat.x_max, flat.u_min, flat.u_max, int(algorithm), float(L_norm),
-        int(factor_mode), int(device), int(rank), int(world_size), cid,
+        int(factor_mode), int(device), int(rank), int(world_size), cid, 0, None,
     )
+    if devices is not None and len(devices) > 0:
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        keep.append(dv)
+        p.n_devices, p.devices = len(dv), dv.ctypes.data_as(_i32p)
     return p, keep

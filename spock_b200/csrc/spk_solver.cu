@@ -3,7 +3,11 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -110,7 +114,27 @@ struct ProfSection {
 #endif
 };
 
+// Single-process multi-GPU (SURVEY.md section 8(b) "Threading": the Julia host is ONE process): a group handle owns one
+// sub-handle per device -- rank g of the subtree partition, with its own stream and NCCL rank -- and one persistent host
+// thread per device that issues every call of that sub-handle (the CUDA current device is per thread, and the ranks'
+// collectives must be issued concurrently).  Every C ABI call on the group handle fans out to the workers and joins.
+struct SpkWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, stop = false, done = false;
+  int rc = 0;
+  std::string err;
+};
+struct spk_handle;
+struct SpkGroup {
+  std::vector<spk_handle *> subs;
+  std::vector<SpkWorker *> workers;
+};
+
 struct spk_handle {
+  SpkGroup *group = nullptr;  // non-NULL: this handle is the front of a device group (only D and `group` are used)
   SpkDims D;
   SpkPtrs P;
   int alg = SPK_CP;
@@ -137,6 +161,7 @@ struct spk_handle {
   SpkComm comm;
   int rank = 0, world = 1, t_cut = 0;
   long m_sub = 1;
+  bool in_group = false;  // sub-handle of a device group
   bool gathered = false;  // the device iterate is complete on this rank (spk_gather_iterate since the last pass)
   // fused path (spk_fused.cuh)
   bool fused_ok = false, shape_specialised = false;
@@ -1135,6 +1160,82 @@ static int sp_pass_device(spk_handle *h, double gamma, double sigma) {
 // passes per host poll: large problems are polled every pass (a pass is milliseconds), small ones every 8 passes
 static int poll_batch(const spk_handle *h) { return (h->D.nz + h->D.nv) > (1L << 21) ? 1 : 8; }
 
+// ------------------------------------------------------------------------------------------------ device group
+
+static void worker_main(SpkWorker *w, int device) {
+#ifndef SPK_HOST_EMU
+  if (device >= 0) cudaSetDevice(device);
+#else
+  (void)device;
+#endif
+  std::unique_lock<std::mutex> lk(w->m);
+  for (;;) {
+    w->cv.wait(lk, [&] { return w->has_job || w->stop; });
+    if (w->stop) return;
+    std::function<int()> job = std::move(w->job);
+    w->has_job = false;
+    lk.unlock();
+    const int rc = job();
+    const std::string err = rc != SPK_OK ? g_last_error : std::string();  // thread-local of THIS worker
+    lk.lock();
+    w->rc = rc;
+    w->err = err;
+    w->done = true;
+    w->cv.notify_all();
+  }
+}
+static void worker_submit(SpkWorker *w, std::function<int()> job) {
+  std::lock_guard<std::mutex> lk(w->m);
+  w->job = std::move(job);
+  w->has_job = true;
+  w->done = false;
+  w->cv.notify_all();
+}
+static int worker_wait(SpkWorker *w, std::string &err) {
+  std::unique_lock<std::mutex> lk(w->m);
+  w->cv.wait(lk, [&] { return w->done; });
+  if (w->rc != SPK_OK) err = w->err;
+  return w->rc;
+}
+// fn(sub-handle, rank) on every device of the group, concurrently, each on its own worker thread
+template <class F>
+static int group_all(const spk_handle *h, F fn) {
+  SpkGroup *G = h->group;
+  for (size_t g = 0; g < G->workers.size(); ++g) {
+    spk_handle *sub = G->subs[g];
+    worker_submit(G->workers[g], [fn, sub, g]() { return fn(sub, (int)g); });
+  }
+  int rc = SPK_OK;
+  std::string err, e;
+  for (size_t g = 0; g < G->workers.size(); ++g) {
+    const int r = worker_wait(G->workers[g], e);
+    if (r != SPK_OK && rc == SPK_OK) { rc = r; err = e; }
+  }
+  return rc == SPK_OK ? SPK_OK : fail(rc, err);
+}
+// fn(sub-handle 0) on rank 0's worker thread (queries and the single-GPU operator interface)
+template <class F>
+static int group_first(const spk_handle *h, F fn) {
+  SpkGroup *G = h->group;
+  spk_handle *sub = G->subs[0];
+  worker_submit(G->workers[0], [fn, sub]() { return fn(sub); });
+  std::string err;
+  const int rc = worker_wait(G->workers[0], err);
+  return rc == SPK_OK ? SPK_OK : fail(rc, err);
+}
+static void group_shutdown(SpkGroup *G) {
+  for (SpkWorker *w : G->workers) {
+    {
+      std::lock_guard<std::mutex> lk(w->m);
+      w->stop = true;
+      w->cv.notify_all();
+    }
+    if (w->th.joinable()) w->th.join();
+    delete w;
+  }
+  delete G;
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 
 static int check_problem(const spk_problem *p) {
@@ -1159,6 +1260,11 @@ static int check_problem(const spk_problem *p) {
   if (p->world_size > 1) {
     if (!p->comm_id) return fail(SPK_ERR_INVALID, "world_size > 1 needs comm_id (spk_comm_unique_id)");
     if (p->rank < 0 || p->rank >= p->world_size) return fail(SPK_ERR_INVALID, "rank out of range");
+  }
+  if (p->n_devices > 1) {
+    if (!p->devices) return fail(SPK_ERR_INVALID, "n_devices > 1 needs the devices array");
+    if (p->world_size > 1) return fail(SPK_ERR_INVALID, "n_devices > 1 (one process) and world_size > 1 (one process per GPU) are exclusive");
+    if (p->n_devices > 64) return fail(SPK_ERR_INVALID, "at most 64 devices");
   }
   double dn = 1.0;
   for (int k = 0; k < p->N; ++k) dn *= p->d;
@@ -1185,6 +1291,12 @@ int spk_tree_maps(int32_t N, int32_t d, int64_t *child_first, int64_t *anc, int3
 
 int spk_destroy(spk_handle *h) {
   if (!h) return SPK_OK;
+  if (h->group) {
+    group_all(h, [](spk_handle *s, int) { return spk_destroy(s); });
+    group_shutdown(h->group);
+    delete h;
+    return SPK_OK;
+  }
   rt_sync(h->stream);
   h->comm.destroy();
   for (void *p : h->allocs) rt_free(p);
@@ -1392,11 +1504,10 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   return rt_sync(h->stream);
 }
 
-int spk_create(const spk_problem *p, spk_handle **out) {
-  if (!out) return fail(SPK_ERR_INVALID, "out is NULL");
+static int create_single(const spk_problem *p, spk_handle **out, bool in_group) {
   *out = nullptr;
-  SPK_TRY(check_problem(p));
   spk_handle *h = new spk_handle();
+  h->in_group = in_group;
 #ifndef SPK_HOST_EMU
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1429,6 +1540,62 @@ int spk_create(const spk_problem *p, spk_handle **out) {
   return SPK_OK;
 }
 
+int spk_create(const spk_problem *p, spk_handle **out) {
+  if (!out) return fail(SPK_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  SPK_TRY(check_problem(p));
+  if (p->n_devices <= 1) {
+    if (p->n_devices == 1 && p->devices) {
+      spk_problem q = *p;
+      q.device = p->devices[0];
+      q.n_devices = 0;
+      return create_single(&q, out, false);
+    }
+    return create_single(p, out, false);
+  }
+  // ---- device group: one sub-handle (rank of the subtree partition) and one worker thread per device
+  const int G = p->n_devices;
+  uint8_t id[128];
+  SPK_TRY(spk_comm_unique_id(id));
+  spk_handle *h = new spk_handle();
+  h->group = new SpkGroup();
+  h->group->subs.assign((size_t)G, nullptr);
+  for (int g = 0; g < G; ++g) {
+    SpkWorker *w = new SpkWorker();
+    w->th = std::thread(worker_main, w, (int)p->devices[g]);
+    h->group->workers.push_back(w);
+  }
+  const spk_problem base = *p;
+  SpkGroup *grp = h->group;
+  const uint8_t *idp = id;
+  for (int g = 0; g < G; ++g)  // NCCL initialisation is a collective: all ranks enter create concurrently
+    worker_submit(grp->workers[g], [base, grp, g, G, idp]() {
+      spk_problem q = base;
+      q.n_devices = 0; q.devices = nullptr;
+      q.device = base.devices[g];
+      q.rank = g; q.world_size = G; q.comm_id = idp;
+      return create_single(&q, &grp->subs[g], true);
+    });
+  int rc = SPK_OK;
+  std::string err, e;
+  for (int g = 0; g < G; ++g) {
+    const int r = worker_wait(grp->workers[g], e);
+    if (r != SPK_OK && rc == SPK_OK) { rc = r; err = e; }
+  }
+  if (rc != SPK_OK) {
+    for (int g = 0; g < G; ++g)
+      if (grp->subs[g]) { spk_handle *sub = grp->subs[g]; worker_submit(grp->workers[g], [sub]() { return spk_destroy(sub); }); worker_wait(grp->workers[g], e); }
+    group_shutdown(grp);
+    delete h;
+    return fail(rc, err);
+  }
+  h->D = grp->subs[0]->D;
+  h->alg = grp->subs[0]->alg;
+  h->world = G;
+  *out = h;
+  return SPK_OK;
+}
+
 int spk_sizes(const spk_handle *h, int64_t s[5]) {
   if (!h || !s) return fail(SPK_ERR_INVALID, "NULL argument");
   s[0] = h->D.n; s[1] = h->D.nnl; s[2] = h->D.nl; s[3] = h->D.nz; s[4] = h->D.nv;
@@ -1442,21 +1609,33 @@ int spk_offsets(const spk_handle *h, int64_t zo[5], int64_t vo[11]) {
 }
 int spk_device_bytes(const spk_handle *h, int64_t *b) {
   if (!h || !b) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) {
+    *b = 0;
+    for (const spk_handle *s : h->group->subs) *b += s->bytes;
+    return SPK_OK;
+  }
   *b = h->bytes;
   return SPK_OK;
 }
 int spk_launch_count(const spk_handle *h, int64_t *l) {
   if (!h || !l) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) {
+    *l = 0;
+    for (const spk_handle *s : h->group->subs) *l += s->launches;
+    return SPK_OK;
+  }
   *l = h->launches;
   return SPK_OK;
 }
 
 int spk_set_x0(spk_handle *h, const double *x0) {
   if (!h || !x0) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) return group_all(h, [=](spk_handle *s, int) { return spk_set_x0(s, x0); });
   return rt_h2d(h->x0, x0, sizeof(double) * h->D.nx, h->stream);
 }
 int spk_set_iterate(spk_handle *h, const double *z, const double *v) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->group) return group_all(h, [=](spk_handle *s, int) { return spk_set_iterate(s, z, v); });
   if (z) SPK_TRY(rt_h2d(h->z(), z, sizeof(double) * h->D.nz, h->stream));
   if (v) SPK_TRY(rt_h2d(h->v(), v, sizeof(double) * h->D.nv, h->stream));
   h->gathered = z && v;  // complete host vectors make the device iterate complete on this rank
@@ -1472,6 +1651,8 @@ static void for_each_owned_slice(const spk_handle *h, F &&fn) {  // fn(bool in_v
   R.gate = nullptr; R.vec2 = 0;
   fill_ranges(h, R);
   for (int k = 0; k < R.n_ranges; ++k) {
+    // device group: all sub-handles copy into the SAME host vectors; the replicated top is rank 0's to write
+    if (h->in_group && h->world > 1 && h->t_cut > 0 && k == 0 && h->rank != 0) continue;
     const long a = R.r_start[k], b = a + (R.r_prefix[k + 1] - R.r_prefix[k]);
     if (b <= a) continue;
     const long c0 = (long)D.d * a + 1, c1 = (long)D.d * b + 1;  // children nodes [c0, c1)
@@ -1500,7 +1681,10 @@ static void for_each_owned_slice(const spk_handle *h, F &&fn) {  // fn(bool in_v
 
 int spk_get_iterate(spk_handle *h, double *z, double *v) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
-  if (h->world > 1 && !h->gathered) {
+  // device group: every device copies the entries its families own into the SAME host vectors -- together the complete
+  // iterate (solver_state.z / .v of the reference), without any device-side gather
+  if (h->group) return group_all(h, [=](spk_handle *s, int) { return spk_get_iterate(s, z, v); });
+  if (h->world > 1 && (!h->gathered || h->in_group)) {
     // subtree partition: only the entries this rank's families write are valid here, so only they are copied (1/world of
     // the iterate plus the replicated top); the other entries of the host vectors are left untouched.  After
     // spk_gather_iterate the whole device iterate is valid and is copied in one piece.
@@ -1528,6 +1712,7 @@ int spk_get_iterate(spk_handle *h, double *z, double *v) {
 
 int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double scalar) {
   if (!h || !in || !out) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) return group_first(h, [=](spk_handle *s) { return spk_apply(s, op, in, out, scalar); });
   const SpkDims &D = h->D;
   const long nz = D.nz, nv = D.nv;
   // scratch that carries nothing across passes or solves: zvbar (rewritten by every operator evaluation) and xi12
@@ -1567,6 +1752,13 @@ int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double s
 int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b_z, const double *b_v, double gamma,
             double sigma, double *out) {
   if (!h || !a_z || !a_v || !b_z || !b_v || !out) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) {  // every rank takes part (the scalar fetch is a collective under the partition); rank 0's value is returned
+    std::vector<double> loc(h->group->subs.size(), 0.0);
+    double *lp = loc.data();
+    SPK_TRY(group_all(h, [=](spk_handle *s, int g) { return spk_dot(s, a_z, a_v, b_z, b_v, gamma, sigma, lp + g); }));
+    *out = loc[0];
+    return SPK_OK;
+  }
   const long nz = h->D.nz, nv = h->D.nv;
   SPK_TRY(rt_h2d(h->zvbar, a_z, sizeof(double) * nz, h->stream));
   SPK_TRY(rt_h2d(h->zvbar + nz, a_v, sizeof(double) * nv, h->stream));
@@ -1580,6 +1772,7 @@ int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b
 
 int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, double *K, double *Rinv, double *ls) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->group) return spk_get_factors(h->group->subs[0], i, Pm, ABK, K, Rinv, ls);  // host tables only
   const SpkDims &D = h->D;
   if (i < 1 || i > D.n) return fail(SPK_ERR_INVALID, "node index out of range");
   const long i0 = i - 1;
@@ -1626,6 +1819,13 @@ struct LoopTimer {
 
 int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->group) {
+    std::vector<float> loc(h->group->subs.size(), 0.f);
+    float *lp = loc.data();
+    SPK_TRY(group_all(h, [=](spk_handle *s, int g) { return spk_step(s, K, gamma, sigma, lp + g); }));
+    if (ms) *ms = *std::max_element(loc.begin(), loc.end());
+    return SPK_OK;
+  }
   LoopState S;
   h->gathered = false;
   default_steps(h, gamma, sigma);
@@ -1663,6 +1863,7 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
 // ---- persistent solver memory (checkpoint / resume), layout documented in include/spock_b200.h
 int spk_state_size(const spk_handle *h, int64_t *doubles) {
   if (!h || !doubles) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) return spk_state_size(h->group->subs[0], doubles);
   const int64_t nr = h->D.nz + h->D.nv;
   *doubles = h->alg == SPK_SP ? 12 * nr + AA_M * AA_M : nr;
   return SPK_OK;
@@ -1737,12 +1938,15 @@ int spk_estimate_L_norm(spk_handle *h, int32_t iters, double *L_norm) {
 }
 int spk_set_L_norm(spk_handle *h, double L_norm) {
   if (!h || !(L_norm > 0)) return fail(SPK_ERR_INVALID, "L_norm must be positive");
+  if (h->group)
+    for (spk_handle *s : h->group->subs) s->L_norm = L_norm;
   h->L_norm = L_norm;
   return SPK_OK;
 }
 
 int spk_get_residuals(spk_handle *h, double out[2]) {
   if (!h || !out) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) h = h->group->subs[0];  // the residual pair is global on every rank
   out[0] = h->last_xi1;
   out[1] = h->last_xi2;
   return SPK_OK;
@@ -1752,6 +1956,12 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
               int32_t verbose_log, const double *z0, const double *v0, spk_result *result, double *log_xi,
               double *log_xi1, double *log_xi2, int32_t *log_bc, int32_t log_cap) {
   if (!h || !x0) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group)  // every rank runs the same loop and takes identical decisions; rank 0 reports
+    return group_all(h, [=](spk_handle *s, int g) {
+      const bool r0 = g == 0;
+      return spk_solve(s, x0, tol, max_iter, gamma, sigma, verbose_log, z0, v0, r0 ? result : nullptr, r0 ? log_xi : nullptr,
+                       r0 ? log_xi1 : nullptr, r0 ? log_xi2 : nullptr, r0 ? log_bc : nullptr, r0 ? log_cap : 0);
+    });
   if (z0 != nullptr || v0 != nullptr) {  // cpock.jl:180-183: logical-or guard, then both are copied
     if (z0 == nullptr || v0 == nullptr) return fail(SPK_ERR_INVALID, "z0 and v0 must be given together");
     SPK_TRY(spk_set_iterate(h, z0, v0));
@@ -1845,6 +2055,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
 
 int spk_profile(spk_handle *h, int32_t enable, int32_t reset) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->group) return group_all(h, [=](spk_handle *s, int) { return spk_profile(s, enable, reset); });
   prof_harvest(h);
   h->prof_on = enable != 0;
   if (reset) for (int c = 0; c < PC_COUNT; ++c) { h->prof_ms[c] = 0.0; h->prof_launches[c] = 0; }
@@ -1852,6 +2063,7 @@ int spk_profile(spk_handle *h, int32_t enable, int32_t reset) {
 }
 int spk_profile_get(spk_handle *h, int32_t cls, double *ms, int64_t *launches) {
   if (!h || cls < 0 || cls >= PC_COUNT) return fail(SPK_ERR_INVALID, "bad profile class");
+  if (h->group) return group_first(h, [=](spk_handle *s) { return spk_profile_get(s, cls, ms, launches); });
   prof_harvest(h);
   if (ms) *ms = h->prof_ms[cls];
   if (launches) *launches = h->prof_launches[cls];
@@ -1868,6 +2080,12 @@ int spk_comm_unique_id(uint8_t id[128]) {
 
 int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int64_t *count) {
   if (!h || !n_ranges) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) {  // the group as a whole computes every family
+    *n_ranges = 1;
+    if (start) start[0] = 1;
+    if (count) count[0] = h->D.nnl;
+    return SPK_OK;
+  }
   SpkFusedArgs A;
   A.gate = nullptr; A.vec2 = 0;
   fill_ranges(h, A);
@@ -1881,6 +2099,7 @@ int spk_owned_ranges(const spk_handle *h, int32_t *n_ranges, int64_t *start, int
 
 int spk_gather_iterate(spk_handle *h) {
   if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->group) return group_all(h, [](spk_handle *s, int) { return spk_gather_iterate(s); });
   if (h->world <= 1) return SPK_OK;
   const SpkDims &D = h->D;
   double *z = h->z(), *v = h->v();

@@ -20,11 +20,12 @@ def _f64(a):
 
 class Handle:
     def __init__(self, flat, algorithm: int = CP, L_norm: float = 0.0, factor_mode: int = FACTORS_PER_NODE,
-                 device: int = -1, rank: int = 0, world_size: int = 1, comm_id=None, lib=None):
+                 device: int = -1, rank: int = 0, world_size: int = 1, comm_id=None, lib=None, devices=None):
+        """devices: list of CUDA ordinals -> the tree is partitioned over them inside this one handle / process."""
         self.lib = lib if lib is not None else _lib.load()
         self.flat = flat
         self.algorithm = algorithm
-        prob, self._keep = _lib.make_problem(flat, algorithm, L_norm, factor_mode, device, rank, world_size, comm_id)
+        prob, self._keep = _lib.make_problem(flat, algorithm, L_norm, factor_mode, device, rank, world_size, comm_id, devices)
         self._h = C.c_void_p()
         check(self.lib, self.lib.spk_create(C.byref(prob), C.byref(self._h)))
         s = (C.c_int64 * 5)()

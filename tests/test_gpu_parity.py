@@ -394,3 +394,19 @@ def test_device_resident_loop_equals_host_driven_loop(cuda_lib, alg, verbose_log
         if verbose_log:
             assert np.allclose(la1["xi"][:k], lb1["xi"][:k], rtol=1e-7, atol=0)
             assert la1["xi"][-1] <= 1e-4 and lb1["xi"][-1] <= 1e-4 and la2["xi"][-1] <= 1e-4 and lb2["xi"][-1] <= 1e-4
+
+
+def test_single_process_device_group():
+    """All GPUs of the box behind ONE handle in ONE process (spk_problem.devices) == one GPU; needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "device_group_check.py")], capture_output=True, text=True,
+                         timeout=900, cwd=root)
+    assert res.returncode == 0 and "DEVICE_GROUP_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

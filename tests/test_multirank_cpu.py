@@ -165,3 +165,43 @@ def test_partition_world2_gloo_processes(emu_lib):
     assert abs(got[0][5] - r0["xi1"]) < 1e-12 * r0["xi1"]
     z, v, worst = assemble(flat, got[0][6], got[0][7], [(g[1], g[2], g[3]) for g in got])
     assert worst < 1e-12 and relerr(z, zr) < 1e-12 and relerr(v, vr) < 1e-12
+
+
+@pytest.mark.parametrize("name,G,alg", [("heat_N7_d2_nx5", 2, CP), ("heat_N7_d2_nx5", 4, CP), ("heat_N4_d3_nx3", 3, CP),
+                                        ("heat_N7_d2_nx5", 2, SP), ("l2ball_N4_d3_nx3", 3, SP)])
+def test_single_process_device_group(emu_lib, name, G, alg):
+    """spk_problem.n_devices / devices: ONE handle in ONE process drives G ranks of the subtree partition (one worker
+    thread per device; the Julia host of the reference is a single process, SURVEY 8(b) "Threading").  Same iterate,
+    residuals, stopping pass and branch counts as a single-device handle; spk_get_iterate assembles the complete (z, v)."""
+    flat = flat_of(name)
+    x0 = 0.1 * np.ones(flat.nx)
+    K = 20 if alg == CP else 8
+    ref = Handle(flat, alg, lib=emu_lib)
+    grp = Handle(flat, alg, lib=emu_lib, devices=list(range(G)))
+    assert (grp.nz, grp.nv, grp.n) == (ref.nz, ref.nv, ref.n) and grp.z_off == ref.z_off
+    for h in (ref, grp):
+        h.set_x0(x0)
+        h.step(K)
+    (zr, vr), (zg, vg) = ref.get_iterate(), grp.get_iterate()
+    assert relerr(zg, zr) < 1e-11 and relerr(vg, vr) < 1e-11
+    xr, xg = ref.residuals(), grp.residuals()
+    assert abs(xr[0] - xg[0]) <= 1e-10 * xr[0] and abs(xr[1] - xg[1]) <= 1e-10 * xr[1]
+    rr, _ = ref.solve(x0, tol=1e-3)
+    rg, lg = grp.solve(x0, tol=1e-3)
+    assert rg["converged"] == 1 and len(lg["xi1"]) == rg["passes"]
+    if alg == CP:
+        assert rg["passes"] == rr["passes"]
+    (zr, vr), (zg, vg) = ref.get_iterate(), grp.get_iterate()
+    if alg == CP:  # (SuperMann to 1e-3: different reduction orders end at different points of the tolerance ball)
+        assert relerr(zg, zr) < 1e-10 and relerr(vg, vr) < 1e-10
+    # inner operator interface and the P-inner product through the group handle
+    rng = np.random.default_rng(4)
+    z, v = rng.standard_normal(ref.nz), rng.standard_normal(ref.nv)
+    assert relerr(grp.L(z), ref.L(z)) < 1e-13 and relerr(grp.prox_h_conj(v, 0.3), ref.prox_h_conj(v, 0.3)) < 1e-13
+    assert abs(grp.dot(z, v, z, v, 0.2, 0.2) - ref.dot(z, v, z, v, 0.2, 0.2)) < 1e-10 * abs(ref.dot(z, v, z, v, 0.2, 0.2))
+    assert grp.device_bytes() > ref.device_bytes() and grp.owned_ranges() == [(1, flat.n_non_leaf)]
+    # argument errors surface from the worker threads
+    with pytest.raises(Exception, match="splits evenly|exclusive|devices"):
+        Handle(flat_of("heat_N4_d3_nx3"), CP, lib=emu_lib, devices=[0, 1])
+    grp.close()
+    ref.close()
