@@ -76,6 +76,13 @@ struct SpkComm {
     if (rc != 0) { err = std::string("ncclAllGather: ") + (errstr ? errstr(rc) : "?"); return false; }
     return true;
   }
+  // bytes_per_rank bytes of every rank, rank-major, in place at base (host-side bootstrap data, e.g. IPC handles)
+  bool allgather_bytes(void *base, size_t bytes_per_rank, spk_stream_t s, std::string &err) {
+    if (world <= 1) return true;
+    const int rc = allgather((char *)base + (size_t)rank * bytes_per_rank, base, bytes_per_rank, 1 /*ncclUint8*/, comm, s);
+    if (rc != 0) { err = std::string("ncclAllGather: ") + (errstr ? errstr(rc) : "?"); return false; }
+    return true;
+  }
   bool allreduce_max(double *buf, int n, spk_stream_t s, std::string &err) {
     if (world <= 1) return true;
     // residual maxima are non-negative: the unsigned maximum of their bit patterns is exact and keeps a NaN (spk_max_nn)

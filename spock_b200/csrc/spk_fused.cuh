@@ -88,6 +88,52 @@ SPK_D double spk_warp_max(double v) {
 #endif
   return v;
 }
+// Programmatic dependent launch (sm_90+): consecutive level launches of a sweep are chained so that the NEXT level's CTAs
+// may become resident, set up their barriers and issue the TMA fetch of their first family's factors (read-only data) while
+// the current level is still finishing; everything that depends on the previous level comes after spk_pdl_wait().
+// Both are no-ops for a kernel launched without the programmatic-serialization attribute.
+#if !SPK_EMU
+SPK_D void spk_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SPK_D void spk_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+SPK_D void spk_pdl_trigger() {}
+SPK_D void spk_pdl_wait() {}
+#endif
+
+// Top-of-tree kernels (spk_k_bwd_top / spk_k_fwd_top): all levels of a sweep that are narrower than one resident wave run
+// in ONE launch, a software grid barrier between levels instead of a kernel boundary (a level of a small tree costs a
+// few microseconds of work; 2(N-1) launches per evaluation dominated every latency-bound configuration).
+struct SpkTopPlan {
+  int n;                                  // level steps of this launch, in execution order
+  int t[SPK_MAX_LEVELS], leaves[SPK_MAX_LEVELS];
+  long p_lo[SPK_MAX_LEVELS], p_cnt[SPK_MAX_LEVELS], kshift[SPK_MAX_LEVELS];
+  unsigned *bar;                          // arrival counter, zeroed by the evaluation's first kernel (spk_k_s2t)
+};
+#if !SPK_EMU
+SPK_D unsigned spk_ld_acquire_gpu_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all CTAs of the grid are co-resident (grid <= one resident wave); target counts arrivals since the counter was zeroed
+SPK_D void spk_grid_barrier(unsigned *ctr, unsigned &target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (spk_ld_acquire_gpu_u32(ctr) < target) {}
+  }
+  __syncthreads();
+}
+SPK_D void spk_mbar_inval(uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(spk_smem_u32(bar)) : "memory"); }
+SPK_D double spk_ldcg(const double *p) { return __ldcg(p); }
+#else
+SPK_D void spk_grid_barrier(unsigned *, unsigned &) {}
+SPK_D void spk_mbar_inval(uint64_t *) {}
+SPK_D double spk_ldcg(const double *p) { return *p; }
+#endif
+
 // 8-byte asynchronous global->shared copies (LDGSTS); the reference layout guarantees no more than 8-byte alignment
 #if !SPK_EMU
 SPK_D void spk_cp_async8(double *dst_smem, const double *src) {
@@ -129,9 +175,12 @@ struct SpkFusedArgs {
   double *pnorm;           // per-family partial of <r, P r> (nnl doubles), or NULL
   int reset_xi;            // this launch zeroes xi[0..1] (block 0)
   int vec2;                // tensor-pipe kernels: every pair of consecutive entries they touch is 16-byte aligned
+  unsigned *topbar;        // 3 grid-barrier counters of the top-of-tree kernels (zeroed by spk_k_s2t), or NULL
   const int *gate;         // device-side "done" flag of the loop (spk_sp.cuh): every kernel returns at once when it is set
   // ownership (multi-GPU subtree partition; a single GPU owns everything):
   long p_lo, p_cnt;        // kernels 1, 2: positions [p_lo, p_lo + p_cnt) of level t are processed by this rank
+  long kshift;             // per-node factors: family i0 of this launch reads factor slot i0 - kshift (a rank stores only its
+                           // own families' factors, packed level by level; 0 on a single GPU)
   int n_ranges;            // kernels 3, 4: the owned families are n_ranges contiguous node ranges
   long r_start[SPK_MAX_LEVELS], r_prefix[SPK_MAX_LEVELS + 1];  // range k = nodes r_start[k] .. , flat offsets r_prefix
 };
@@ -226,10 +275,11 @@ SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
 }
 
 // NX_, NU_, D_, T_ > 0: sizes fixed at compile time (every loop unrolls, index arithmetic folds); 0: runtime sizes
-template <int NX_, int NU_, int D_, int T_>
-SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
-  SPK_SMEM_DECL(double, smem);
-  if (A.gate && *A.gate) return;
+// TOP: one level step inside a top-of-tree kernel -- the dependency on the previous step is a grid barrier instead of the
+// kernel boundary, and what other CTAs wrote in the previous step is read past the (incoherent) L1
+template <int NX_, int NU_, int D_, int T_, bool TOP>
+SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &A, double *smem, unsigned *gbar, unsigned &gtarget,
+                        bool first_step) {
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
   const int tid = threadIdx.x, t = A.t;
   const int WL = T < 32 ? T : 32, warp = tid / WL, lane = tid % WL;
@@ -248,10 +298,6 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
                  bytes_r = (uint32_t)(D.r_stride * sizeof(double));
   const bool leaves = A.children_are_leaves != 0;
   const double gamma = A.gamma;
-  if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
-    A.xi[0] = 0.0;
-    A.xi[1] = 0.0;
-  }
   if (tid == 0) spk_mbar_init(bar, 1);
   // family-independent work items of this thread
   const SpkItem itA = spk_make_item(tid, nx, SA, nx, nu), itB = spk_make_item(tid, nu, SB, nx, nu);
@@ -259,7 +305,7 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SYNCTHREADS();
   uint32_t phase = 0;
   auto fetch = [&](long i0) {  // TMA: the family's factor slots are contiguous
-    const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+    const long aslot = D.per_node ? (long)d * (i0 - A.kshift) : (long)t * d, kslot = D.per_node ? i0 - A.kshift : t;
     spk_mbar_expect_tx(bar, bytes_abk + 2 * bytes_k + bytes_r);
     spk_bulk_g2s(mABKt, P.ABKt + aslot * D.abk_stride, bytes_abk, bar);
     spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
@@ -280,6 +326,8 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
         spk_cp_async8(rq + k, A.z + cf * nx + k);
         spk_cp_async8(rv14 + k, A.v + D.vo[10] + lf * nx + k);
         spk_cp_async8(rv11 + k, A.v + D.vo[7] + lf * nx + k);
+      } else if constexpr (TOP) {
+        rq[k] = spk_ldcg(A.q + cf * nx + k);  // written by another CTA in the previous level step
       } else {
         spk_cp_async8(rq + k, A.q + cf * nx + k);
       }
@@ -296,28 +344,35 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     SPK_SYNCTHREADS();
   }
   auto fetch_child = [&](long i0, int c) {
-    const long aslot = D.per_node ? (long)d * i0 : (long)t * d;
+    const long aslot = D.per_node ? (long)d * (i0 - A.kshift) : (long)t * d;
     spk_mbar_expect_tx(cbar + c, (uint32_t)(D.abk_stride * sizeof(double)));
     spk_bulk_g2s(mABKt + (long)c * D.abk_stride, P.ABKt + (aslot + c) * D.abk_stride, (uint32_t)(D.abk_stride * sizeof(double)), cbar + c);
   };
   auto fetch_rest = [&](long i0) {
-    const long kslot = D.per_node ? i0 : t;
+    const long kslot = D.per_node ? i0 - A.kshift : t;
     spk_mbar_expect_tx(bar, 2 * bytes_k + bytes_r);
     spk_bulk_g2s(mG, P.G + kslot * D.k_stride, bytes_k, bar);
     spk_bulk_g2s(mKt, P.Kt + kslot * D.k_stride, bytes_k, bar);
     spk_bulk_g2s(mRinv, P.Rinv + kslot * D.r_stride, bytes_r, bar);
   };
-  if ((long)blockIdx.x < count) {
-    if (tid == 0) {
-      if constexpr (SPLIT) {
-        for (int c = 0; c < D_; ++c) fetch_child(first0 + blockIdx.x, c);
-        fetch_rest(first0 + blockIdx.x);
-      } else {
-        fetch(first0 + blockIdx.x);
-      }
+  if ((long)blockIdx.x < count && tid == 0) {  // the factors do not depend on the previous level: fetch before the wait
+    if constexpr (SPLIT) {
+      for (int c = 0; c < D_; ++c) fetch_child(first0 + blockIdx.x, c);
+      fetch_rest(first0 + blockIdx.x);
+    } else {
+      fetch(first0 + blockIdx.x);
     }
-    stage_raw(first0 + blockIdx.x);
   }
+  if constexpr (TOP) {
+    if (!first_step) spk_grid_barrier(gbar, gtarget);  // the level below (the children's q) is complete
+  } else {
+    spk_pdl_wait();  // the previous launch (the level below: the children's q) has completed and its writes are visible
+  }
+  if (A.reset_xi && blockIdx.x == 0 && tid == 0) {
+    A.xi[0] = 0.0;
+    A.xi[1] = 0.0;
+  }
+  if ((long)blockIdx.x < count) stage_raw(first0 + blockIdx.x);
   uint32_t cph = 0;     // SPLIT: bit c = phase of child barrier c
   bool pending = true;  // a fetch is in flight / not yet consumed
   for (long p = blockIdx.x; p < count; p += gridDim.x) {
@@ -426,6 +481,38 @@ SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     }
     SPK_SYNCTHREADS();  // work buffers are reused by the next family
   }
+  if constexpr (TOP) {  // the next level step re-initialises the barriers
+    if (tid == 0) {
+      spk_mbar_inval(bar);
+      if constexpr (SPLIT)
+        for (int c = 0; c < D_; ++c) spk_mbar_inval(cbar + c);
+    }
+    SPK_SYNCTHREADS();
+  }
+}
+
+template <int NX_, int NU_, int D_, int T_>
+SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  spk_pdl_trigger();
+  unsigned dummy = 0;
+  spk_bwd_body<NX_, NU_, D_, T_, false>(D, P, A, smem, nullptr, dummy, true);
+}
+
+// all narrow levels of the backward sweep (plan.t descending) in one launch
+template <int NX_, int NU_, int D_, int T_>
+SPK_KERNEL void spk_k_bwd_top(SpkDims D, SpkPtrs P, SpkFusedArgs A, SpkTopPlan plan) {
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  spk_pdl_wait();
+  unsigned target = 0;
+  for (int s = 0; s < plan.n; ++s) {
+    SpkFusedArgs B = A;
+    B.t = plan.t[s]; B.children_are_leaves = plan.leaves[s]; B.p_lo = plan.p_lo[s]; B.p_cnt = plan.p_cnt[s]; B.kshift = plan.kshift[s];
+    B.reset_xi = (s == 0) ? A.reset_xi : 0;
+    spk_bwd_body<NX_, NU_, D_, T_, true>(D, P, B, smem, plan.bar, target, s == 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ 2. forward S1
@@ -435,10 +522,9 @@ SPK_HD long spk_fwd_smem_doubles(const SpkDims &D, int T) {
   return 2 + (long)D.d * D.abk_stride + D.k_stride + 2L * (D.nx + D.nu) + R * S + 4;
 }
 
-template <int NX_, int NU_, int D_, int T_>
-SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
-  SPK_SMEM_DECL(double, smem);
-  if (A.gate && *A.gate) return;
+template <int NX_, int NU_, int D_, int T_, bool TOP>
+SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &A, double *smem, unsigned *gbar, unsigned &gtarget,
+                        bool first_step) {
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
   const int tid = threadIdx.x, t = A.t;
   const int R = nu + d * nx, S = spk_slices(T, R);
@@ -463,7 +549,7 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SYNCTHREADS();
   uint32_t phase = 0;
   auto fetch = [&](long i0) {
-    const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+    const long aslot = D.per_node ? (long)d * (i0 - A.kshift) : (long)t * d, kslot = D.per_node ? i0 - A.kshift : t;
     spk_mbar_expect_tx(bar, bytes_abk + bytes_k);
     spk_bulk_g2s(mABK, P.ABK + aslot * D.abk_stride, bytes_abk, bar);
     spk_bulk_g2s(mK, P.K + kslot * D.k_stride, bytes_k, bar);
@@ -471,11 +557,15 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   // x_i (:667: x0 at the root) and d_i of a family, asynchronously into one of the two small staging buffers
   auto stage_raw = [&](long i0, int buf) {
     double *dst = raw0 + (long)buf * (nx + nu);
-    for (int k = tid; k < nx; k += T) spk_cp_async8(dst + k, (t == 0) ? P.x0 + k : A.zbar + i0 * nx + k);
+    if constexpr (TOP) {  // x_i was written by another CTA in the previous level step: read it past L1
+      for (int k = tid; k < nx; k += T) dst[k] = (t == 0) ? P.x0[k] : spk_ldcg(A.zbar + i0 * nx + k);
+    } else {
+      for (int k = tid; k < nx; k += T) spk_cp_async8(dst + k, (t == 0) ? P.x0 + k : A.zbar + i0 * nx + k);
+    }
     for (int k = tid; k < nu; k += T) spk_cp_async8(dst + nx + k, A.dd + i0 * nu + k);
   };
   auto fetch_half = [&](long i0, int hf) {  // SPLIT: columns [0, HC) or [HC, nx) of ABK_0..ABK_{d-1} and K
-    const long aslot = D.per_node ? (long)d * i0 : (long)t * d, kslot = D.per_node ? i0 : t;
+    const long aslot = D.per_node ? (long)d * (i0 - A.kshift) : (long)t * d, kslot = D.per_node ? i0 - A.kshift : t;
     const int c0h = hf ? HC : 0, nc = hf ? NX_ - HC : HC;
     uint64_t *br = bar + hf;
     spk_mbar_expect_tx(br, (uint32_t)((D_ * NX_ + NU_) * nc * sizeof(double)));
@@ -484,17 +574,20 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
                    (uint32_t)(nc * NX_ * sizeof(double)), br);
     spk_bulk_g2s(mK + c0h * NU_, P.K + kslot * D.k_stride + c0h * NU_, (uint32_t)(nc * NU_ * sizeof(double)), br);
   };
-  if ((long)blockIdx.x < count) {
-    if (tid == 0) {
-      if constexpr (SPLIT) {
-        fetch_half(first0 + blockIdx.x, 0);
-        fetch_half(first0 + blockIdx.x, 1);
-      } else {
-        fetch(first0 + blockIdx.x);
-      }
+  if ((long)blockIdx.x < count && tid == 0) {  // the factors do not depend on the previous level: fetch before the wait
+    if constexpr (SPLIT) {
+      fetch_half(first0 + blockIdx.x, 0);
+      fetch_half(first0 + blockIdx.x, 1);
+    } else {
+      fetch(first0 + blockIdx.x);
     }
-    stage_raw(first0 + blockIdx.x, 0);
   }
+  if constexpr (TOP) {
+    if (!first_step) spk_grid_barrier(gbar, gtarget);  // the level above (x_i) is complete
+  } else {
+    spk_pdl_wait();  // the previous launch (the level above: x_i; the backward sweep: d_i) has completed
+  }
+  if ((long)blockIdx.x < count) stage_raw(first0 + blockIdx.x, 0);
   spk_cp_async_commit();
   uint32_t phase1 = 0;  // SPLIT: phase of the second half's barrier
   bool pending = true;
@@ -572,6 +665,36 @@ SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
     }
     SPK_SYNCTHREADS();
   }
+  if constexpr (TOP) {
+    if (tid == 0) {
+      spk_mbar_inval(bar);
+      if (SPLIT) spk_mbar_inval(bar + 1);
+    }
+    SPK_SYNCTHREADS();
+  }
+}
+
+template <int NX_, int NU_, int D_, int T_>
+SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  spk_pdl_trigger();
+  unsigned dummy = 0;
+  spk_fwd_body<NX_, NU_, D_, T_, false>(D, P, A, smem, nullptr, dummy, true);
+}
+
+// all narrow levels of the forward sweep (plan.t ascending) in one launch
+template <int NX_, int NU_, int D_, int T_>
+SPK_KERNEL void spk_k_fwd_top(SpkDims D, SpkPtrs P, SpkFusedArgs A, SpkTopPlan plan) {
+  SPK_SMEM_DECL(double, smem);
+  if (A.gate && *A.gate) return;
+  spk_pdl_wait();
+  unsigned target = 0;
+  for (int s = 0; s < plan.n; ++s) {
+    SpkFusedArgs B = A;
+    B.t = plan.t[s]; B.children_are_leaves = plan.leaves[s]; B.p_lo = plan.p_lo[s]; B.p_cnt = plan.p_cnt[s]; B.kshift = plan.kshift[s];
+    spk_fwd_body<NX_, NU_, D_, T_, true>(D, P, B, smem, plan.bar, target, s == 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ 3. S2 on (z - gamma L'v)
@@ -585,6 +708,9 @@ template <int NY_, int DD_>
 SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   if (A.gate && *A.gate) return;
   const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f == 0 && A.topbar) {  // arrival counters of this evaluation's top-of-tree kernels
+    A.topbar[0] = 0u; A.topbar[1] = 0u; A.topbar[2] = 0u;
+  }
   if (f >= A.r_prefix[A.n_ranges]) return;
   const long i0 = spk_owned_family(A, f);
   const int ny = NY_ > 0 ? NY_ : D.ny, d = NY_ > 0 ? DD_ : D.d, nls = ny + 2 * d;
@@ -1242,7 +1368,10 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   long f = ((long)blockIdx.x * wpb + warp) * FPW + wlane / G;
   const bool valid = f < fam_cnt;
   if (!valid) f = fam_cnt - 1;
-  const long i0 = fam_lo + f, cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
+  // fam_lo >= 0: families fam_lo .. fam_lo + fam_cnt - 1; fam_lo < 0: flat owned-family indices (-1 - fam_lo) + f over the
+  // rank's owned ranges (subtree partition: one launch covers the slices of all levels)
+  const long i0 = fam_lo >= 0 ? fam_lo + f : spk_owned_family(A, (-1 - fam_lo) + f);
+  const long cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
   double my_xi1 = 0.0, my_xi2 = 0.0, my_pn = 0.0;
 #define SPK_XON(r) ((NX % G == 0) || (r) < RX - 1 || lane + G * (r) < NX)
 #define SPK_UON(r) ((NU % G == 0) || (r) < RU - 1 || lane + G * (r) < NU)

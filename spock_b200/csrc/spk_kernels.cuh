@@ -472,24 +472,15 @@ SPK_KERNEL void spk_k_reduce_final(int np, int mode, const double *__restrict__ 
   if (threadIdx.x == 0) out[slot] = (accumulate && mode != 1) ? out[slot] + sm[0] : sm[0];
 }
 
-// replicate table slots into per-node slots: dst[s*stride + e] = src[id(s)*stride + e]
-// kind 0 (per child node, s = j0-1): id = level(parent)*d + c;  kind 1 (per non-leaf node, s = i0): id = level(i0)
-SPK_KERNEL void spk_k_replicate(SpkDims D, int kind, long stride, long n_slots, const double *__restrict__ src,
-                                double *__restrict__ dst) {
+// replicate table slots into the per-node slots of one tree level: dst[s*stride + e] = src[id(s)*stride + e]
+// kind 0 (per child node; slot s = d*family + c): id = t*d + c;  kind 1 (per non-leaf node): id = t
+SPK_KERNEL void spk_k_replicate_level(int d, int kind, int t, long stride, long n_slots, const double *__restrict__ src,
+                                      double *__restrict__ dst) {
   const long total = n_slots * stride;
   const long gs = (long)gridDim.x * blockDim.x;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gs) {
     const long s = idx / stride, e = idx - s * stride;
-    const long node0 = (kind == 0) ? s / D.d : s;  // the (parent) node whose level selects the table row
-    int t = 0;
-    long first_next = 1;  // first0 of level t+1
-    long cnt = 1;
-    while (node0 >= first_next) {
-      ++t;
-      cnt *= D.d;
-      first_next += cnt;
-    }
-    const long id = (kind == 0) ? (long)t * D.d + (s % D.d) : t;
+    const long id = (kind == 0) ? (long)t * d + (s % d) : t;
     dst[idx] = src[id * stride + e];
   }
 }

@@ -17,6 +17,7 @@
 #include "spk_fused.cuh"
 #include "spk_kernels.cuh"
 #include "spk_offline.h"
+#include "spk_peer.cuh"
 #include "spk_sp.cuh"
 
 #ifdef SPK_HOST_EMU
@@ -162,12 +163,23 @@ struct spk_handle {
   int rank = 0, world = 1, t_cut = 0;
   long m_sub = 1;
   bool in_group = false;  // sub-handle of a device group
+  // per-node factors under the partition: only this rank's families are stored, packed level by level (replicated top
+  // first); fac_start[t] = first packed family slot of level t
+  long fac_start[SPK_MAX_LEVELS] = {0};
+  SpkDims D_tab;          // the same dimensions with per_node = 0 and
+  SpkPtrs P_tab;          // the per-stage factor table: what the modular S1 kernels (spk_apply) read
   bool gathered = false;  // the device iterate is complete on this rank (spk_gather_iterate since the last pass)
   // fused path (spk_fused.cuh)
   bool fused_ok = false, shape_specialised = false;
   void (*k_bwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_fwd)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
   void (*k_dual)(SpkDims, SpkPtrs, SpkFusedArgs) = nullptr;
+  // top-of-tree kernels: every level of a sweep with at most top_cap families (one resident wave) in one launch
+  void (*k_bwd_top)(SpkDims, SpkPtrs, SpkFusedArgs, SpkTopPlan) = nullptr;
+  void (*k_fwd_top)(SpkDims, SpkPtrs, SpkFusedArgs, SpkTopPlan) = nullptr;
+  bool use_topk = false;
+  long top_cap_bwd = 0, top_cap_fwd = 0;
+  unsigned *d_topbar = nullptr;
   void (*k_dual2)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long) = nullptr;
   void (*k_dual3[2][2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {{nullptr, nullptr}, {nullptr, nullptr}};  // [children are leaves][with <r,Pr>]
   int occ_dual3 = 4;
@@ -192,6 +204,14 @@ struct spk_handle {
   double *d_pnorm = nullptr;
   // CUDA graphs of the fused operator evaluation, keyed by (input, output, gamma, sigma, pnorm slot)
   bool use_graphs = false;
+  // cut-level exchanges over peer memory (spk_peer.cuh): this rank's mailbox and every rank's mailbox as mapped here
+  double *mbox = nullptr;
+  double *peer_box[SPK_PEER_MAX] = {nullptr};
+  std::vector<void *> ipc_opened;
+  bool peer_ok = false;
+  long lenA = 0, lenB = 0;
+  bool graph_nccl = false;  // SPK_GRAPH_NCCL=1: capture the cut-level exchanges inside the evaluation's CUDA graph (one graph per evaluation)
+  bool use_pdl = true;  // SPK_NO_PDL=1: plain stream order between the level launches of the S1 sweeps
 #ifndef SPK_HOST_EMU
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
   std::map<std::tuple<const void *, void *, double, double, int, int>, GraphEntry> graphs;
@@ -393,7 +413,9 @@ static int fetch_scalars(spk_handle *h, int count) {
 
 // projection_S1! (implicit_l.jl:559-686) in place on arg = (x | u)
 static int op_proj_S1(spk_handle *h, double *arg) {
-  const SpkDims &D = h->D;
+  // (the modular kernels visit EVERY node: they read the per-stage table, which holds the same numbers as the per-node slots)
+  const SpkDims &D = h->D_tab;
+  const SpkPtrs &Ptab = h->P_tab;
   const int lanes = pow2_lanes(std::max(D.nx, D.nu));
   int block = SPK_EMU ? 1 : 128;
   const size_t per_group_b = (size_t)(D.d * D.nx + 3 * D.nu) * sizeof(double);
@@ -404,7 +426,7 @@ static int op_proj_S1(spk_handle *h, double *arg) {
     ProfScope ps(h, PC_S1_BWD);
     const long count = spk_level_count(D.d, t);
     const unsigned grid = (unsigned)((count + gpb - 1) / gpb);
-    SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_s1_bwd<LANES>, grid, block, gpb * per_group_b, h->stream, D, h->P, t,
+    SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_s1_bwd<LANES>, grid, block, gpb * per_group_b, h->stream, D, Ptab, t,
                                        (int)(t == D.N - 2), arg, h->ric_q, h->ric_d));
     COUNT_LAUNCH(h, PC_S1_BWD);
   }
@@ -412,7 +434,7 @@ static int op_proj_S1(spk_handle *h, double *arg) {
     ProfScope ps(h, PC_S1_FWD);
     const long count = spk_level_count(D.d, t);
     const unsigned grid = (unsigned)((count + gpb - 1) / gpb);
-    SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_s1_fwd<LANES>, grid, block, gpb * per_group_f, h->stream, D, h->P, t, arg,
+    SPK_LANES_SWITCH(lanes, SPK_LAUNCH(spk_k_s1_fwd<LANES>, grid, block, gpb * per_group_f, h->stream, D, Ptab, t, arg,
                                        h->ric_d));
     COUNT_LAUNCH(h, PC_S1_FWD);
   }
@@ -541,6 +563,8 @@ static int fused_setup(spk_handle *h) {
   h->k_fwd = spk_k_fwd_s1<0, 0, 0, 0>;
   h->k_dual = spk_k_dual<0, 0, 0>;
   h->k_dual2 = spk_k_dual2<0, 0, 0>;
+  h->k_bwd_top = spk_k_bwd_top<0, 0, 0, 0>;
+  h->k_fwd_top = spk_k_fwd_top<0, 0, 0, 0>;
   const char *gen = getenv("SPK_GENERIC_KERNELS");
 #ifndef SPK_HOST_EMU
   if (!(gen && gen[0] == '1'))
@@ -548,6 +572,7 @@ static int fused_setup(spk_handle *h) {
       const SpkShapeEntry &e = *getter();
       if (e.nx == D.nx && e.nu == D.nu && e.d == D.d) {
         Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd; h->k_dual = e.dual; h->k_dual2 = e.dual2;
+        h->k_bwd_top = e.bwd_top; h->k_fwd_top = e.fwd_top;
         h->shape_specialised = true;
         // register-resident dual kernel: Diagonal sqrt-costs, risk cone and branching within one warp
         const char *e3 = getenv("SPK_NO_DUAL3");
@@ -592,6 +617,23 @@ static int fused_setup(spk_handle *h) {
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, (const void *)h->k_bwd, Tb, h->fused_smem_bwd));
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, (const void *)h->k_fwd, Tf, h->fused_smem_fwd));
   h->occ_bwd = std::max(1, h->occ_bwd);
+  {  // top-of-tree kernels: their grid must be co-resident (software grid barrier)
+    // Measured (profiles/r02c_topk_ab.txt): with the level launches chained by programmatic dependent launch a level costs
+    // ~3.1 us, a level step behind the grid barrier ~4.6 us (N=10, nx=20: 65.6 -> 88.1 us per pass; N=13, nx=50: 185 -> 217 us),
+    // because the floor is the dependent chain INSIDE a level, not the launch.  The kernels stay as an opt-in (SPK_TOPK=1).
+    const char *nt = getenv("SPK_TOPK");
+    int ob = 0, of = 0;
+    RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
+    RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
+    RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, (const void *)h->k_bwd_top, Tb, h->fused_smem_bwd));
+    RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, (const void *)h->k_fwd_top, Tf, h->fused_smem_fwd));
+    h->top_cap_bwd = (long)h->num_sms * ob;
+    h->top_cap_fwd = (long)h->num_sms * of;
+    h->use_topk = (nt && nt[0] == '1') && ob >= 1 && of >= 1;
+    double *tb = nullptr;
+    SPK_TRY(dev_alloc(h, &tb, 2));
+    h->d_topbar = reinterpret_cast<unsigned *>(tb);
+  }
   if (h->k_dual3[1][0]) {
     RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_dual3, (const void *)h->k_dual3[1][0], 128, 0));
     h->occ_dual3 = std::max(1, h->occ_dual3);
@@ -634,6 +676,10 @@ static int fused_setup(spk_handle *h) {
 #endif
   h->fused_ok = true;
   {
+    const char *np = getenv("SPK_NO_PDL");
+    h->use_pdl = !(np && np[0] == '1');
+  }
+  {
     const char *mc = getenv("SPK_MAX_CTAS");
     h->max_ctas = mc ? atol(mc) : 0;
   }
@@ -644,6 +690,24 @@ static int fused_setup(spk_handle *h) {
   return SPK_OK;
 }
 
+#ifndef SPK_HOST_EMU
+// launch of a level kernel of the S1 sweeps, chained to the previous launch on the stream by programmatic dependent launch
+static cudaError_t launch_level(spk_handle *h, spk_fused_kernel_t k, unsigned grid, unsigned block, size_t smem, const SpkDims &D,
+                                const SpkFusedArgs &A) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, D, h->P, A);
+}
+#endif
+
 static unsigned fused_grid(const spk_handle *h, long count, int occ) {
   // persistent CTAs: one resident wave strides over the families of the level, so the per-thread index arithmetic is
   // paid once per kernel; with per-stage factors the level's matrices are also fetched only once per CTA
@@ -651,6 +715,31 @@ static unsigned fused_grid(const spk_handle *h, long count, int occ) {
   if (SPK_EMU) g = std::min(count, 3L);
   if (h->max_ctas > 0) g = std::min(g, h->max_ctas);
   return (unsigned)std::max(1L, g);
+}
+
+// One cut-level exchange (kind 0: the subtree roots' q; kind 1: their vbar2 and the residual maxima): a peer-memory kernel
+// (spk_peer.cuh) when the ranks' mailboxes are mapped, else an in-place NCCL all-gather issued by the host
+static int launch_exchange(spk_handle *h, int kind, double *vec, long vlen) {
+  ProfScope ps(h, PC_VEC);
+#ifndef SPK_HOST_EMU
+  if (h->peer_ok) {
+    SpkPeerArgs X;
+    X.rank = h->rank; X.world = h->world; X.kind = kind;
+    X.len = kind == 0 ? h->lenA : h->lenB;
+    X.off_payload = kind == 0 ? 0 : 2L * h->world * h->lenA;
+    X.off_flags = 2L * h->world * (h->lenA + h->lenB);
+    X.mine = h->mbox;
+    for (int r = 0; r < SPK_PEER_MAX; ++r) X.peer[r] = r < h->world ? h->peer_box[r] : nullptr;
+    X.gate = h->d_ctl ? &h->d_ctl->done : nullptr;
+    X.vec = vec; X.vlen = vlen; X.xi = h->d_scal;
+    spk_k_peer_exchange<<<1, 128, 0, h->stream>>>(X);
+    COUNT_LAUNCH(h, PC_VEC);
+    return rt_launch_check();
+  }
+#endif
+  std::string cerr;
+  if (!h->comm.allgather_inplace(vec, vlen, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+  return SPK_OK;
 }
 
 // `parts`: 1 = kernels up to the cut-level exchange, 2 = that exchange (all-gather of the subtree roots' q), 4 = the remaining
@@ -663,9 +752,10 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   A.gamma = gamma; A.sigma = sigma; A.inv_gamma = 1.0 / gamma; A.inv_sigma = 1.0 / sigma;
   A.z = zv_in; A.v = zv_in + D.nz; A.zbar = zv_out; A.vbar = zv_out + D.nz;
   A.q = h->ric_q; A.dd = h->ric_d; A.xi = h->d_scal; A.pnorm = pnorm_slot >= 0 ? h->d_pnorm : nullptr;
-  A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0; A.p_lo = 0; A.p_cnt = 0;
+  A.t = 0; A.children_are_leaves = 0; A.reset_xi = 0; A.p_lo = 0; A.p_cnt = 0; A.kshift = 0;
   A.gate = h->d_ctl ? &h->d_ctl->done : nullptr;
   A.vec2 = h->mm_vec2 ? 1 : 0;
+  A.topbar = h->d_topbar;
   fill_ranges(h, A);
   const long owned = A.r_prefix[A.n_ranges];
   std::string cerr;
@@ -687,12 +777,78 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   }
   // levels 0 .. t_top of both sweeps run in one single-CTA launch (single GPU, tensor-pipe kernels)
   const int t_top = (h->use_mm && h->world == 1) ? h->t_top : -1;
+  // levels 0 .. ts_b / ts_f of a sweep are narrower than one resident wave: one top-of-tree launch each (a second one for
+  // the backward sweep under the partition, where the cut-level exchange sits between two of its levels)
+  int ts_b = -1, ts_f = -1;
+#ifndef SPK_HOST_EMU
+  if (h->use_topk && t_top < 0) {
+    auto narrow = [&](int t, long cap) {
+      long lo, cnt;
+      level_range(h, t, lo, cnt);
+      return cnt <= cap && !(h->use_mm && cnt >= h->mm_min_count);
+    };
+    // (SPK_MAX_CTAS test switch: the top-of-tree grid is capped too, so its CTAs stride over up to 64 families per level,
+    // and wider levels keep exercising the steady-state loop of the per-level kernels)
+    const long cb = h->max_ctas > 0 ? std::min(h->top_cap_bwd, h->max_ctas * 64) : h->top_cap_bwd;
+    const long cf = h->max_ctas > 0 ? std::min(h->top_cap_fwd, h->max_ctas * 64) : h->top_cap_fwd;
+    while (ts_b + 1 <= D.N - 2 && narrow(ts_b + 1, cb)) ++ts_b;
+    while (ts_f + 1 <= D.N - 2 && narrow(ts_f + 1, cf)) ++ts_f;
+    if (ts_b < 1) ts_b = -1;  // a single level gains nothing
+    if (ts_f < 1) ts_f = -1;
+  }
+  auto launch_top = [&](bool bwd, int t_first, int t_last, int bar_idx) -> int {  // levels t_first .. t_last in execution order
+    SpkTopPlan plan;
+    plan.n = 0;
+    plan.bar = h->d_topbar + bar_idx;
+    long widest = 1;
+    for (int t = t_first; bwd ? t >= t_last : t <= t_last; t += bwd ? -1 : 1) {
+      const int k = plan.n++;
+      plan.t[k] = t; plan.leaves[k] = (t == D.N - 2);
+      level_range(h, t, plan.p_lo[k], plan.p_cnt[k]);
+      plan.kshift[k] = spk_level_first0(D.d, t) + plan.p_lo[k] - h->fac_start[t];
+      widest = std::max(widest, plan.p_cnt[k]);
+    }
+    SpkFusedArgs At = A;
+    At.reset_xi = (bwd && t_first == D.N - 2) ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    long grid = std::min(widest, bwd ? h->top_cap_bwd : h->top_cap_fwd);
+    if (h->max_ctas > 0) grid = std::min(grid, h->max_ctas);
+    cfg.gridDim = dim3((unsigned)std::max(1L, grid), 1, 1);
+    cfg.blockDim = dim3((unsigned)(bwd ? h->fused_threads_bwd : h->fused_threads_fwd), 1, 1);
+    cfg.dynamicSmemBytes = bwd ? h->fused_smem_bwd : h->fused_smem_fwd;
+    cfg.stream = h->stream;
+    // cooperative launch: the grid is gang-scheduled, so the software grid barrier cannot deadlock against kernels of
+    // other handles / streams that share the GPU (batched independent problems)
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RT_CHECK(cudaLaunchKernelEx(&cfg, bwd ? h->k_bwd_top : h->k_fwd_top, D, h->P, At, plan));
+    COUNT_LAUNCH(h, bwd ? PC_FUSED_BWD : PC_FUSED_FWD);
+    return SPK_OK;
+  };
+#endif
   for (int t = D.N - 2; t > t_top; --t) {  // 1. backward sweep
     const bool in_a = h->world <= 1 || t >= h->t_cut;  // levels down to the cut belong to the first kernel segment
+#ifndef SPK_HOST_EMU
+    if (t <= ts_b) {  // the narrow levels t .. stop in one launch
+      const int stop = (h->world > 1 && t >= h->t_cut) ? h->t_cut : 0;
+      if (in_a ? seg_a : seg_b) {
+        ProfScope ps(h, PC_FUSED_BWD);
+        SPK_TRY(launch_top(true, t, stop, in_a ? 0 : 2));
+      }
+      t = stop;
+      if (h->world > 1 && t == h->t_cut && (parts & 2))
+        SPK_TRY(launch_exchange(h, 0, h->ric_q + spk_level_first0(D.d, t) * D.nx, h->m_sub * D.nx));
+      continue;
+    }
+#endif
     if (in_a ? seg_a : seg_b) {
       ProfScope ps(h, PC_FUSED_BWD);
       A.t = t; A.children_are_leaves = (t == D.N - 2); A.reset_xi = (t == D.N - 2);
       level_range(h, t, A.p_lo, A.p_cnt);
+      A.kshift = spk_level_first0(D.d, t) + A.p_lo - h->fac_start[t];
 #ifndef SPK_HOST_EMU
       if (h->use_mm && A.p_cnt >= h->mm_min_count) {  // per-stage factors: the level is a chain of mat-mats on the fp64 tensor pipe
         // small levels: fewer warps (tiles) per CTA so that the tiles spread over the SMs (a DMMA chain is bound by
@@ -709,23 +865,21 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
 #endif
       {
         spk_fused_kernel_t kfn = h->k_bwd;
+#ifndef SPK_HOST_EMU
+        RT_CHECK(launch_level(h, kfn, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, D, A));
+#else
         SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_bwd), h->fused_threads_bwd, h->fused_smem_bwd, h->stream, D, h->P, A);
+#endif
       }
       COUNT_LAUNCH(h, PC_FUSED_BWD);
     }
-    if (h->world > 1 && t == h->t_cut && (parts & 2)) {  // the replicated levels above the cut need every subtree root's q
-      ProfScope ps(h, PC_VEC);
-      if (!h->comm.allgather_inplace(h->ric_q + spk_level_first0(D.d, t) * D.nx, h->m_sub * D.nx, h->stream, cerr))
-        return comm_fail(cerr);
-    }
+    if (h->world > 1 && t == h->t_cut && (parts & 2))  // the replicated levels above the cut need every subtree root's q
+      SPK_TRY(launch_exchange(h, 0, h->ric_q + spk_level_first0(D.d, t) * D.nx, h->m_sub * D.nx));
   }
   A.reset_xi = 0;
   if (!seg_b) {
-    if (h->world > 1 && (parts & 8)) {  // the second exchange on its own (between graph segments)
-      ProfScope ps(h, PC_VEC);
-      if (!h->comm.allgather_inplace(A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub, h->stream, cerr))
-        return comm_fail(cerr);
-    }
+    if (h->world > 1 && (parts & 8))  // the second exchange on its own (between graph segments)
+      SPK_TRY(launch_exchange(h, 1, A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub));
     return rt_launch_check();
   }
 #ifndef SPK_HOST_EMU
@@ -737,10 +891,17 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     COUNT_LAUNCH(h, PC_FUSED_BWD);
   }
 #endif
-  for (int t = t_top + 1; t <= D.N - 2; ++t) {  // 2. forward sweep
+#ifndef SPK_HOST_EMU
+  if (ts_f >= 1) {
+    ProfScope ps(h, PC_FUSED_FWD);
+    SPK_TRY(launch_top(false, 0, ts_f, 1));
+  }
+#endif
+  for (int t = std::max(t_top, ts_f) + 1; t <= D.N - 2; ++t) {  // 2. forward sweep
     ProfScope ps(h, PC_FUSED_FWD);
     A.t = t; A.children_are_leaves = (t == D.N - 2);
     level_range(h, t, A.p_lo, A.p_cnt);
+    A.kshift = spk_level_first0(D.d, t) + A.p_lo - h->fac_start[t];
 #ifndef SPK_HOST_EMU
     if (h->use_mm && A.p_cnt >= h->mm_min_count) {
       long cap = (long)h->num_sms * h->occ_fwd_mm;
@@ -754,11 +915,47 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
 #endif
     {
       spk_fused_kernel_t kfn = h->k_fwd;
+#ifndef SPK_HOST_EMU
+      RT_CHECK(launch_level(h, kfn, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, D, A));
+#else
       SPK_LAUNCH(kfn, fused_grid(h, A.p_cnt, h->occ_fwd), h->fused_threads_fwd, h->fused_smem_fwd, h->stream, D, h->P, A);
+#endif
     }
     COUNT_LAUNCH(h, PC_FUSED_FWD);
   }
   long pn_parts = owned;  // number of <r,Pr> partials in d_pnorm
+#ifndef SPK_HOST_EMU
+  if (h->use_dual2 && h->world > 1 && h->k_dual3[0][0] && h->k_dual3[1][0]) {
+    // 4c under the subtree partition: the register-resident kernel over FLAT owned-family indices -- one launch for all
+    // families with non-leaf children (the slices of every level at once) and one for the leaf parents (the last range)
+    ProfScope ps(h, PC_PROX_H);
+    const long fpc = 4L * (32 / spk_dual3_group(D.nx, D.nu, D.d));  // families per CTA (4 warps)
+    const int leaf_rng = A.n_ranges - 1;
+    const long F_all = A.r_prefix[A.n_ranges], F_nl = A.r_prefix[leaf_rng];
+    const long top = h->t_cut > 0 ? A.r_prefix[1] : 0;
+    const bool skip_top_pn = A.pnorm && h->rank != 0 && top > 0;  // <r, P r> of the replicated top is counted by rank 0 only
+    long pn_off = 0;
+    auto launch3 = [&](int part, long lo_arg, long cnt, bool with_pn) {
+      if (cnt <= 0) return;
+      SpkFusedArgs A2 = A;
+      A2.children_are_leaves = part;
+      A2.pnorm = with_pn ? A.pnorm + pn_off : nullptr;
+      const long g = (cnt + fpc - 1) / fpc;
+      spk_dual3_kernel_t k3 = h->k_dual3[part][with_pn ? 1 : 0];
+      k3<<<(unsigned)g, 128, 0, h->stream>>>(D, h->P, A2, lo_arg, cnt);
+      COUNT_LAUNCH(h, PC_PROX_H);
+      if (with_pn) pn_off += g;
+    };
+    if (skip_top_pn) {
+      launch3(0, -1, std::min(top, F_nl), false);
+      launch3(0, -1 - top, F_nl - top, true);
+    } else {
+      launch3(0, -1, F_nl, A.pnorm != nullptr);
+    }
+    launch3(1, A.r_start[leaf_rng], F_all - F_nl, A.pnorm != nullptr);
+    pn_parts = pn_off;
+  } else
+#endif
   if (h->use_dual2) {  // 4b. batched dual kernel: one launch per owned range, split where the children become leaves
     ProfScope ps(h, PC_PROX_H);
     const long leaf_parents0 = spk_level_first0(D.d, D.N - 2);  // first family whose children are leaves
@@ -806,11 +1003,8 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     SPK_LAUNCH(kfn, (unsigned)std::max(1L, g), T, h->fused_smem_dual, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_PROX_H);
   }
-  if (h->world > 1 && (parts & 8)) {  // v2 of the subtree roots is read by the replicated family above the cut in the next evaluation
-    ProfScope ps(h, PC_VEC);
-    if (!h->comm.allgather_inplace(A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub, h->stream, cerr))
-      return comm_fail(cerr);
-  }
+  if (h->world > 1 && (parts & 8))  // v2 of the subtree roots is read by the replicated family above the cut in the next evaluation
+    SPK_TRY(launch_exchange(h, 1, A.vbar + D.vo[1] + spk_level_first0(D.d, h->t_cut), h->m_sub));
   SPK_TRY(rt_launch_check());
   if (pnorm_slot >= 0) SPK_TRY(op_reduce(h, pn_parts, 2, h->d_pnorm, nullptr, pnorm_slot, 0));
   return SPK_OK;
@@ -855,7 +1049,7 @@ static int op_T_fused(spk_handle *h, const double *zv_in, double *zv_out, double
   if (h->world > 1 && pnorm_slot >= 0) h->slot_dirty[pnorm_slot] = 1;  // (a graph replay does not pass through op_reduce)
 #ifndef SPK_HOST_EMU
   if (h->use_graphs && !h->prof_on) {
-    if (h->world == 1) return graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 15);
+    if (h->world == 1 || h->graph_nccl || h->peer_ok) return graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 15);
     SPK_TRY(graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 1));
     SPK_TRY(op_T_fused_launch(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 2));
     SPK_TRY(graph_segment(h, zv_in, zv_out, gamma, sigma, pnorm_slot, 4));
@@ -1069,7 +1263,7 @@ static unsigned vec_grid(const spk_handle *h, long n) {
 }
 // should_terminate! on the device for one finished pass (CP: xi1, xi2 come out of the dual kernel in d_scal[0..1])
 static int launch_terminate(spk_handle *h, int xi_slot, int is_sp) {
-  if (h->world > 1) {
+  if (h->world > 1 && !h->peer_ok) {  // (the peer-memory exchange after the dual kernel already left the global maxima in d_scal[0..1])
     std::string cerr;
     if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
   }
@@ -1304,6 +1498,8 @@ int spk_destroy(spk_handle *h) {
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->sp_graph) cudaGraphExecDestroy(h->sp_graph);
   for (auto &s : h->prof_open) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+  for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+  if (h->mbox) cudaFree(h->mbox);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -1312,6 +1508,56 @@ int spk_destroy(spk_handle *h) {
   delete h;
   return SPK_OK;
 }
+
+#ifndef SPK_HOST_EMU
+// Mailbox of the peer-memory exchanges (spk_peer.cuh).  Between processes the ranks swap cudaIpc handles of their
+// mailboxes through one NCCL all-gather and map each other's; inside a device group the front handle links the pointers
+// after all sub-handles exist (group_link_peers).  Any failure on any rank leaves every rank on the NCCL path.
+static int peer_setup(spk_handle *h) {
+  const char *np = getenv("SPK_NO_PEER");
+  if (np && np[0] == '1') return SPK_OK;
+  if (h->world > SPK_PEER_MAX || h->world > 128) return SPK_OK;
+  h->lenA = h->m_sub * h->D.nx;
+  h->lenB = h->m_sub + 2;
+  const size_t bytes = (size_t)spk_peer_mailbox_doubles(h->world, h->lenA, h->lenB) * sizeof(double);
+  void *q = nullptr;
+  if (cudaMalloc(&q, bytes) != cudaSuccess) { cudaGetLastError(); return SPK_OK; }
+  h->mbox = (double *)q;
+  h->bytes += (int64_t)bytes;
+  RT_CHECK(cudaMemsetAsync(q, 0, bytes, h->stream));
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  h->peer_box[h->rank] = h->mbox;
+  if (h->in_group) return SPK_OK;  // same process: linked by the group front
+  // ---- one process per GPU: exchange IPC handles
+  double ok = 1.0;
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, q) != cudaSuccess) { cudaGetLastError(); ok = 0.0; memset(&mine, 0, sizeof(mine)); }
+  std::vector<cudaIpcMemHandle_t> all((size_t)h->world);
+  void *stage = nullptr;
+  RT_CHECK(cudaMalloc(&stage, sizeof(cudaIpcMemHandle_t) * h->world));
+  RT_CHECK(cudaMemcpyAsync((char *)stage + sizeof(mine) * h->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  std::string cerr;
+  if (!h->comm.allgather_bytes(stage, sizeof(mine), h->stream, cerr)) { cudaFree(stage); return fail(SPK_ERR_COMM, cerr); }
+  RT_CHECK(cudaMemcpyAsync(all.data(), stage, sizeof(mine) * h->world, cudaMemcpyDeviceToHost, h->stream));
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  cudaFree(stage);
+  for (int r = 0; r < h->world && ok > 0; ++r) {
+    if (r == h->rank) continue;
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0.0; break; }
+    h->ipc_opened.push_back(ptr);
+    h->peer_box[r] = (double *)ptr;
+  }
+  // all ranks or none
+  RT_CHECK(cudaMemcpyAsync(h->d_scal + 31, &ok, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (!h->comm.allreduce_sum(h->d_scal + 31, 1, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+  double sum = 0.0;
+  RT_CHECK(cudaMemcpyAsync(&sum, h->d_scal + 31, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  RT_CHECK(cudaStreamSynchronize(h->stream));
+  h->peer_ok = sum > h->world - 0.5;
+  return SPK_OK;
+}
+#endif
 
 static int create_impl(const spk_problem *p, spk_handle *h) {
   SpkDims &D = h->D;
@@ -1364,7 +1610,19 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(upload(h, &tmp, h->ls_host.data(), (long)h->ls_host.size())); h->P.ls = tmp;
   SPK_TRY(dev_alloc(h, &h->x0, nx)); h->P.x0 = h->x0;
 
-  // ---- factors: per-stage table, replicated to per-node slots in PER_NODE mode
+  // ---- subtree partition: levels < t_cut replicated, rank g owns m_sub subtrees below the cut
+  h->rank = p->rank; h->world = p->world_size > 1 ? p->world_size : 1;
+  if (h->world > 1) {
+    int tc = -1;
+    for (int t = 1; t <= D.N - 2; ++t)
+      if (spk_level_count(d, t) % h->world == 0) { tc = t; break; }
+    if (tc < 0) return fail(SPK_ERR_INVALID, "no tree level splits evenly over world_size ranks: report this tree at 1 GPU");
+    h->t_cut = tc;
+    h->m_sub = spk_level_count(d, tc) / h->world;
+  }
+
+  // ---- factors: per-stage table; in PER_NODE mode replicated into one slot per node of the families this rank computes
+  //      (all of them on a single GPU), packed level by level
   const SpkFactorTable &T = h->table;
   double *tABK, *tABKt, *tK, *tKt, *tG, *tR;
   SPK_TRY(upload(h, &tABK, T.ABK.data(), (long)T.ABK.size()));
@@ -1373,27 +1631,42 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(upload(h, &tKt, T.Kt.data(), (long)T.Kt.size()));
   SPK_TRY(upload(h, &tG, T.G.data(), (long)T.G.size()));
   SPK_TRY(upload(h, &tR, T.Rinv.data(), (long)T.Rinv.size()));
-  if (!D.per_node) {
-    h->P.ABK = tABK; h->P.ABKt = tABKt; h->P.K = tK; h->P.Kt = tKt; h->P.G = tG; h->P.Rinv = tR;
-  } else {
-    double *nABK, *nABKt, *nK, *nKt, *nG, *nR;
-    SPK_TRY(dev_alloc(h, &nABK, (n - 1) * D.abk_stride, false));
-    SPK_TRY(dev_alloc(h, &nABKt, (n - 1) * D.abk_stride, false));
-    SPK_TRY(dev_alloc(h, &nK, nnl * D.k_stride, false));
-    SPK_TRY(dev_alloc(h, &nKt, nnl * D.k_stride, false));
-    SPK_TRY(dev_alloc(h, &nG, nnl * D.k_stride, false));
-    SPK_TRY(dev_alloc(h, &nR, nnl * D.r_stride, false));
-    const int b = elem_block();
-    const unsigned g = SPK_EMU ? 64 : (unsigned)h->num_sms * 16;
-    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 0, D.abk_stride, n - 1, tABK, nABK);
-    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 0, D.abk_stride, n - 1, tABKt, nABKt);
-    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tK, nK);
-    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tKt, nKt);
-    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.k_stride, nnl, tG, nG);
-    SPK_LAUNCH(spk_k_replicate, g, b, 0, h->stream, D, 1, D.r_stride, nnl, tR, nR);
-    h->launches += 6;
-    SPK_TRY(rt_launch_check());
-    h->P.ABK = nABK; h->P.ABKt = nABKt; h->P.K = nK; h->P.Kt = nKt; h->P.G = nG; h->P.Rinv = nR;
+  h->P.ABK = tABK; h->P.ABKt = tABKt; h->P.K = tK; h->P.Kt = tKt; h->P.G = tG; h->P.Rinv = tR;
+  h->D_tab = D; h->D_tab.per_node = 0;
+  h->P_tab = h->P;
+  {
+    long packed = 0;
+    for (int t = 0; t <= D.N - 2; ++t) {
+      long lo, cnt;
+      level_range(h, t, lo, cnt);
+      h->fac_start[t] = packed;
+      packed += cnt;
+    }
+    if (D.per_node) {
+      double *nABK, *nABKt, *nK, *nKt, *nG, *nR;
+      SPK_TRY(dev_alloc(h, &nABK, packed * d * D.abk_stride, false));
+      SPK_TRY(dev_alloc(h, &nABKt, packed * d * D.abk_stride, false));
+      SPK_TRY(dev_alloc(h, &nK, packed * D.k_stride, false));
+      SPK_TRY(dev_alloc(h, &nKt, packed * D.k_stride, false));
+      SPK_TRY(dev_alloc(h, &nG, packed * D.k_stride, false));
+      SPK_TRY(dev_alloc(h, &nR, packed * D.r_stride, false));
+      const int b = elem_block();
+      for (int t = 0; t <= D.N - 2; ++t) {
+        long lo, cnt;
+        level_range(h, t, lo, cnt);
+        const long f0 = h->fac_start[t];
+        const unsigned g = SPK_EMU ? 8 : (unsigned)std::max(1L, std::min((long)h->num_sms * 16, (cnt * d * D.abk_stride + b - 1) / b));
+        SPK_LAUNCH(spk_k_replicate_level, g, b, 0, h->stream, d, 0, t, D.abk_stride, cnt * d, tABK, nABK + f0 * d * D.abk_stride);
+        SPK_LAUNCH(spk_k_replicate_level, g, b, 0, h->stream, d, 0, t, D.abk_stride, cnt * d, tABKt, nABKt + f0 * d * D.abk_stride);
+        SPK_LAUNCH(spk_k_replicate_level, g, b, 0, h->stream, d, 1, t, D.k_stride, cnt, tK, nK + f0 * D.k_stride);
+        SPK_LAUNCH(spk_k_replicate_level, g, b, 0, h->stream, d, 1, t, D.k_stride, cnt, tKt, nKt + f0 * D.k_stride);
+        SPK_LAUNCH(spk_k_replicate_level, g, b, 0, h->stream, d, 1, t, D.k_stride, cnt, tG, nG + f0 * D.k_stride);
+        SPK_LAUNCH(spk_k_replicate_level, g, b, 0, h->stream, d, 1, t, D.r_stride, cnt, tR, nR + f0 * D.r_stride);
+        h->launches += 6;
+      }
+      SPK_TRY(rt_launch_check());
+      h->P.ABK = nABK; h->P.ABKt = nABKt; h->P.K = nK; h->P.Kt = nKt; h->P.G = nG; h->P.Rinv = nR;
+    }
   }
 
   // ---- state (cpock.jl:83-103)
@@ -1423,17 +1696,21 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
     SPK_TRY(dev_alloc(h, &h->d_log, 3L * h->log_cap));
   }
   SPK_TRY(fused_setup(h));
-  h->rank = p->rank; h->world = p->world_size > 1 ? p->world_size : 1;
   if (h->world > 1) {
     if (!h->fused_ok) return fail(SPK_ERR_INVALID, "the subtree partition needs the fused kernels (problem too large for shared memory)");
-    int tc = -1;
-    for (int t = 1; t <= D.N - 2; ++t)
-      if (spk_level_count(d, t) % h->world == 0) { tc = t; break; }
-    if (tc < 0) return fail(SPK_ERR_INVALID, "no tree level splits evenly over world_size ranks: report this tree at 1 GPU");
-    h->t_cut = tc;
-    h->m_sub = spk_level_count(d, tc) / h->world;
     std::string cerr;
     if (!h->comm.init(h->rank, h->world, p->comm_id, cerr)) return fail(SPK_ERR_COMM, cerr);
+    // One eager round of the collectives of an operator evaluation: NCCL sets up its connections lazily on the first
+    // call (allocations, IPC), which must not happen inside a stream capture.  The buffers hold zeros at this point.
+    if (!h->comm.allgather_inplace(h->ric_q + spk_level_first0(d, h->t_cut) * nx, h->m_sub * nx, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+    if (!h->comm.allgather_inplace(h->zvbar + D.nz + D.vo[1] + spk_level_first0(d, h->t_cut), h->m_sub, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+    if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
+    SPK_TRY(rt_sync(h->stream));
+    const char *gn = getenv("SPK_GRAPH_NCCL");
+    h->graph_nccl = gn && gn[0] == '1';
+#ifndef SPK_HOST_EMU
+    SPK_TRY(peer_setup(h));
+#endif
   }
   if (h->world > 1 && h->alg == SPK_SP) {
     // Entries of (z|v) this rank counts in SuperMann's global sums and maxima: those of its owned families, and of the
@@ -1592,6 +1869,35 @@ int spk_create(const spk_problem *p, spk_handle **out) {
   h->D = grp->subs[0]->D;
   h->alg = grp->subs[0]->alg;
   h->world = G;
+#ifndef SPK_HOST_EMU
+  {  // peer-memory exchanges inside the process: enable peer access both ways and hand every sub-handle the mailboxes
+    bool all = true;
+    for (int g = 0; g < G; ++g) all = all && grp->subs[g]->mbox != nullptr;
+    if (all) {
+      std::vector<int> okv((size_t)G, 0);
+      int *okp = okv.data();
+      group_all(h, [grp, G, okp](spk_handle *s, int g) {
+        int ok = 1;
+        for (int r = 0; r < G && ok; ++r) {
+          if (r == g) continue;
+          int can = 0;
+          if (cudaDeviceCanAccessPeer(&can, s->device, grp->subs[r]->device) != cudaSuccess || !can) { ok = 0; break; }
+          const cudaError_t e = cudaDeviceEnablePeerAccess(grp->subs[r]->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+          cudaGetLastError();
+        }
+        okp[g] = ok;
+        return (int)SPK_OK;
+      });
+      for (int g = 0; g < G; ++g) all = all && okv[g];
+      if (all)
+        for (int g = 0; g < G; ++g) {
+          for (int r = 0; r < G; ++r) grp->subs[g]->peer_box[r] = grp->subs[r]->mbox;
+          grp->subs[g]->peer_ok = true;
+        }
+    }
+  }
+#endif
   *out = h;
   return SPK_OK;
 }
@@ -1794,6 +2100,19 @@ int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, dou
   return SPK_OK;
 }
 
+// a peer-memory exchange gave up waiting for a peer (spk_peer.cuh): report it instead of returning a wrong iterate
+static int peer_check(spk_handle *h) {
+#ifndef SPK_HOST_EMU
+  if (h->peer_ok) {
+    unsigned long long err = 0;
+    const double *w = h->mbox + 2L * h->world * (h->lenA + h->lenB) + 2L * h->world + 2;
+    SPK_TRY(rt_d2h(&err, w, sizeof(err), h->stream));
+    if (err) return fail(SPK_ERR_COMM, "peer-memory exchange timed out waiting for another rank");
+  }
+#endif
+  return SPK_OK;
+}
+
 struct LoopTimer {
   spk_handle *h;
   double t0 = 0;
@@ -1843,7 +2162,7 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
     h->res_0[0] = r0a; h->res_0[1] = r0b;  // spk_step leaves solve_model!'s res_0 alone
     const float t = timer.stop();
     if (ms) *ms = t;
-    return SPK_OK;
+    return peer_check(h);
   }
   for (int k = 0; k < K; ++k) {
     S.iter = k;
@@ -1857,7 +2176,7 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   h->last_xi2 = h->h_scal[1];
   const float t = timer.stop();
   if (ms) *ms = t;
-  return SPK_OK;
+  return peer_check(h);
 }
 
 // ---- persistent solver memory (checkpoint / resume), layout documented in include/spock_b200.h
@@ -2023,7 +2342,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
       result->k1_count = S.k1; result->k2_count = S.k2; result->fallback_count = S.fb;
       result->solve_ms = ms;
     }
-    return SPK_OK;
+    return peer_check(h);
   }
   while (iter < max_iter) {
     int bc = 0;
@@ -2050,7 +2369,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
     result->k1_count = S.k1; result->k2_count = S.k2; result->fallback_count = S.fb;
     result->solve_ms = ms;
   }
-  return SPK_OK;
+  return peer_check(h);
 }
 
 int spk_profile(spk_handle *h, int32_t enable, int32_t reset) {

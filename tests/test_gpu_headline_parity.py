@@ -137,3 +137,24 @@ def test_warm_started_second_solve_matches_oracle(cuda_lib, alg, tol):
 def test_nan_iterate_never_reports_convergence(cuda_lib, alg, host_loop, monkeypatch):
     monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
     check_nan_never_converges(cuda_lib, alg)
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(50, 20, 2, 9), (10, 10, 4, 5), (20, 20, 3, 5), (7, 3, 2, 7)])
+def test_top_of_tree_kernels_equal_level_launches(cuda_lib, nx, nu, d, N, monkeypatch):
+    """SPK_TOPK=1 (opt-in; measured slower than the PDL-chained level launches): all narrow levels of a sweep
+    in one cooperative launch with a grid barrier between levels -- bitwise the same iterate as one launch per level,
+    also with the grid capped so that a CTA strides over several families per level step."""
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    rng = np.random.default_rng(5)
+    o = Oracle(flat, CP)
+    z0, v0 = 0.3 * rng.standard_normal(o.nz), 0.3 * rng.standard_normal(o.nv)
+    out = {}
+    for topk, cap in (("0", "0"), ("1", "0"), ("1", "3")):
+        monkeypatch.setenv("SPK_TOPK", topk)
+        monkeypatch.setenv("SPK_MAX_CTAS", cap)
+        _, res = _run_pair(cuda_lib, flat, CP, 6, z0=z0, v0=v0)
+        out[(topk, cap)] = res
+        _run_pair(cuda_lib, flat, SP, 3, z0=z0, v0=v0)
+    for key in (("1", "0"), ("1", "3")):
+        for (za, va, xa), (zb, vb, xb) in zip(out[("0", "0")], out[key]):
+            assert np.array_equal(za, zb) and np.array_equal(va, vb) and xa == xb
