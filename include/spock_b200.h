@@ -166,6 +166,14 @@ int spk_set_state(spk_handle *h, const double *state);
 int spk_estimate_L_norm(spk_handle *h, int32_t iters, double *L_norm);
 int spk_set_L_norm(spk_handle *h, double L_norm);
 
+/* SuperMann variants that the reference's source contains but does not execute.  Default 0 =
+ * the reference as shipped (parity mode).  SPK_SP_LINESEARCH: tau <- beta tau after a failed K1 / K2 test -- sp.jl:439 discards
+ * the result of perform_linesearch!, so the reference re-evaluates the same candidate nine times.  SPK_SP_K0: the blind update
+ * K0 (sp.jl:72-106), whose test ends in "&& false" (sp.jl:80).  With an option set the loop is driven from the host. */
+#define SPK_SP_LINESEARCH 1
+#define SPK_SP_K0 2
+int spk_set_sp_options(spk_handle *h, int32_t options);
+
 /* Residuals of the last pass without a full D2H of the iterate: out[0] = xi1, out[1] = xi2 */
 int spk_get_residuals(spk_handle *h, double out[2]);
 

@@ -85,6 +85,7 @@ def _load(omp: bool):
         lib.spo_solve.restype = C.c_int
         lib.spo_solve.argtypes = [C.c_void_p, dp, C.c_double, C.c_int, dp, dp, C.c_double, C.c_double, C.c_int,
                                   C.POINTER(_Result), dp, dp, dp, ip, C.c_int]
+        lib.spo_set_sp_options.argtypes = [C.c_void_p, C.c_int]
         lib.spo_step.restype = C.c_int
         lib.spo_step.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         _LIBS[key] = lib
@@ -229,6 +230,10 @@ class Oracle:
         k = res.passes
         out = {f: getattr(res, f) for f, _ in _Result._fields_}
         return out, {"xi": xi[:k], "xi1": xi1[:k], "xi2": xi2[:k], "backtrack_count": bc[:k]}
+
+    def set_sp_options(self, linesearch: bool = False, k0: bool = False):
+        """SuperMann variants present but not executed in the reference (sp.jl:439, sp.jl:80); default = as shipped."""
+        self.lib.spo_set_sp_options(self.h, (1 if linesearch else 0) | (2 if k0 else 0))
 
     def step(self, K, gamma=0.0, sigma=0.0):
         self.lib.spo_step(self.h, int(K), gamma, sigma)

@@ -20,6 +20,7 @@
 #define AA_M 3 /* ANDERSON_BUFFER_SIZE, anderson.jl:6, spock.jl:108 */
 
 struct spo_model {
+  int sp_options; /* SPO_SP_LINESEARCH | SPO_SP_K0; 0 = the reference as shipped */
   int N, d, nx, nu, ny, nt, alg;
   long n, nnl, nl, nz, nv;
   long zo[5];  /* x,u,s,tau,y   (implicit_l.jl:106-158) */
@@ -849,6 +850,8 @@ typedef struct {
   double r_safe;
   int iter, broyden_k;
   int k1, k2, fb;
+  double eta; /* sp.jl:381 eta = r_safe */
+  int k0;
 } sp_locals;
 
 /* one pass of cp.jl:205-228; returns should_terminate! */
@@ -883,7 +886,16 @@ static int sp_pass(spo_model *m, sp_locals *L, double gamma, double sigma, doubl
   anderson(m, L->broyden_k);
   double tau = 1.0, rtilde_norm = INFINITY;
   int backtrack_count = 0, loop = 1;
-  /* K0 is disabled: should_perform_k0 ends in "&& false" (sp.jl:80) */
+  const double c0 = 0.99, beta = 0.5; /* sp.jl:364,369 */
+  /* K0 is disabled in the reference: should_perform_k0 ends in "&& false" (sp.jl:80).  SPO_SP_K0 restores the test
+   * as written before the "&& false": the blind update of perform_k0! (:83-106). */
+  if ((m->sp_options & SPO_SP_K0) && rnorm <= c0 * L->eta) {
+    L->eta = rnorm;
+    for (long i = 0; i < nz; ++i) m->z[i] += m->dz[i];
+    for (long i = 0; i < nv; ++i) m->v[i] += m->dv[i];
+    loop = 0; /* (update_candidate_residual! :406 only computes rtilde_norm, which nobody reads afterwards) */
+    L->k0++;
+  }
   while (loop && backtrack_count <= MAX_BACKTRACK_COUNT) { /* :411-441 */
     for (long i = 0; i < nz; ++i) m->sw[i] = m->z[i] + tau * m->dz[i];
     for (long i = 0; i < nv; ++i) m->su[i] = m->v[i] + tau * m->dv[i];
@@ -910,7 +922,9 @@ static int sp_pass(spo_model *m, sp_locals *L, double gamma, double sigma, doubl
       L->k2++;
       continue;
     }
-    /* perform_linesearch!(tau, beta) returns tau*beta but the result is discarded (sp.jl:439) */
+    /* perform_linesearch!(tau, beta) returns tau*beta but the result is discarded (sp.jl:439);
+     * SPO_SP_LINESEARCH assigns it (the evident intent: tau = perform_linesearch!(tau, beta)) */
+    if (m->sp_options & SPO_SP_LINESEARCH) tau = tau * beta;
     backtrack_count += 1;
   }
   if (loop) { /* :443-446 plain CP update */
@@ -939,7 +953,7 @@ int spo_solve(spo_model *m, const double *x0, double tol, int verbose_log, const
     gamma = sigma;
   }
   if (max_iter <= 0) max_iter = (m->alg == SPO_ALG_SP) ? 1000 : 5000; /* sp.jl:360 / cp.jl:190 */
-  sp_locals L = {INFINITY, 0, 0, 0, 0, 0};
+  sp_locals L = {INFINITY, 0, 0, 0, 0, 0, INFINITY, 0};
   int iter = 0, passes = 0, converged = 0;
   double xi = NAN, xi1 = NAN, xi2 = NAN;
   while (iter < max_iter) {
@@ -970,13 +984,15 @@ int spo_solve(spo_model *m, const double *x0, double tol, int verbose_log, const
   return 0;
 }
 
+void spo_set_sp_options(spo_model *m, int options) { m->sp_options = options; }
+
 int spo_step(spo_model *m, int K, double gamma, double sigma) {
   if (!(sigma > 0) || !(gamma > 0)) {
     sigma = 0.99 / sqrt(m->L_norm);
     gamma = sigma;
   }
   static sp_locals L; /* parity helper: SP locals restart like a fresh run_sp! on every call */
-  L = (sp_locals){INFINITY, 0, 0, 0, 0, 0};
+  L = (sp_locals){INFINITY, 0, 0, 0, 0, 0, INFINITY, 0};
   double xi, xi1, xi2;
   int bc;
   for (int k = 0; k < K; ++k) {

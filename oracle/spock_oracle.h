@@ -92,6 +92,13 @@ int spo_solve(spo_model *m, const double *x0, double tol, int verbose_log, const
               double gamma, double sigma, int max_iter, spo_result *res, double *log_xi, double *log_xi1,
               double *log_xi2, int *log_bc, int log_cap);
 
+/* SuperMann variants the reference's source contains but does not execute; 0 = as shipped.
+ * SPO_SP_LINESEARCH: tau <- beta*tau after a failed K1/K2 test (sp.jl:439 discards the result of perform_linesearch!).
+ * SPO_SP_K0: the blind update K0, whose test ends in "&& false" (sp.jl:80). */
+#define SPO_SP_LINESEARCH 1
+#define SPO_SP_K0 2
+void spo_set_sp_options(spo_model *m, int options);
+
 /* exactly K passes without looking at the termination flag (parity helper; still evaluates should_terminate!
  * because it has side effects on delta_z/delta_v/res_0) */
 int spo_step(spo_model *m, int K, double gamma, double sigma);

@@ -139,6 +139,7 @@ struct spk_handle {
   SpkDims D;
   SpkPtrs P;
   int alg = SPK_CP;
+  int sp_options = 0;  // SPK_SP_LINESEARCH | SPK_SP_K0 (spk_set_sp_options); 0 = the reference as shipped
   double L_norm = 10.0;
   int device = 0;
   spk_stream_t stream = 0;
@@ -1073,7 +1074,8 @@ struct LoopState {
   double gamma, sigma, tol;
   int verbose_log;
   double r_safe = INFINITY;
-  int iter = 0, broyden_k = 0, k1 = 0, k2 = 0, fb = 0;
+  double eta = INFINITY;  // sp.jl:381
+  int iter = 0, broyden_k = 0, k1 = 0, k2 = 0, fb = 0, k0 = 0;
 };
 
 // should_terminate! (cp.jl:54-123 / sp.jl:270-344).  Leaves xi1, xi2 (and xi in LOG mode) in d_scal[0..2].
@@ -1186,39 +1188,61 @@ static int sp_pass_launch(spk_handle *h, LoopState &S, int *bc) {
   S.broyden_k += 1;                                                                    // spock.jl:212-224
   SPK_TRY(anderson(h, S.broyden_k));  // its last fetch also brought slot 4 (launched earlier on the stream)
   const double rnorm = std::sqrt(h->h_scal[4]);
-  // tau is always 1: perform_linesearch!'s result is discarded (sp.jl:439), so the up-to-9 "backtracks" recompute
-  // the same candidate.  It is evaluated once; a failed K1/K2 test reports backtrack_count = 9 like the reference.
-  const double tau = 1.0;
-  SPK_TRY(op_axpby(h, nr, 1.0, h->zv, tau, h->dir, h->wu));                            // generate_candidate_update! :118-131
-  if (h->fused_ok) {
-    SPK_TRY(op_T_fused(h, h->wu, h->wubar, S.gamma, S.sigma, 5));
-    SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
-  } else {
-    SPK_TRY(op_T(h, h->wu, h->wubar, S.gamma, S.sigma));                               // update_candidate_residual! :133-164
-    SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
-    SPK_TRY(op_pdot(h, h->rwu, h->rwu, S.gamma, S.sigma, 5));
-  }
-  SPK_TRY(fetch_scalars(h, 6));
-  const double rtilde_norm = std::sqrt(h->h_scal[5]);
+  // Reference as shipped (sp_options == 0): tau is always 1 because perform_linesearch!'s result is discarded (sp.jl:439), so
+  // the up-to-9 "backtracks" recompute the same candidate; it is evaluated once and a failed K1/K2 test reports
+  // backtrack_count = 9 like the reference.  SPK_SP_LINESEARCH assigns tau <- beta tau (up to 9 different candidates);
+  // SPK_SP_K0 restores the blind update whose test ends in "&& false" (sp.jl:80-106).
+  const double c0 = 0.99, beta = 0.5;  // sp.jl:364,369
+  const int MAX_BACKTRACK_COUNT = 8;
+  double tau = 1.0;
   int backtrack_count = 0;
-  if (rnorm <= S.r_safe && rtilde_norm <= c1 * rnorm) {                                // K1 :166-191
-    std::swap(h->zv, h->wu);
-    S.r_safe = rtilde_norm + std::pow(q, (double)S.iter);
-    S.k1++;
-  } else {
-    SPK_TRY(op_axpby(h, nr, 1.0, h->rwu, -tau, h->dir, h->ws_rho));                    // :419-424
+  bool loop = true;
+  if ((h->sp_options & SPK_SP_K0) && rnorm <= c0 * S.eta) {                              // K0 :72-106
+    S.eta = rnorm;
+    SPK_TRY(op_axpby(h, nr, 1.0, h->zv, 1.0, h->dir, h->zv));
+    loop = false;
+    S.k0++;
+  }
+  while (loop && backtrack_count <= MAX_BACKTRACK_COUNT) {                               // :411-441
+    SPK_TRY(op_axpby(h, nr, 1.0, h->zv, tau, h->dir, h->wu));                            // generate_candidate_update! :118-131
+    if (h->fused_ok) {
+      SPK_TRY(op_T_fused(h, h->wu, h->wubar, S.gamma, S.sigma, 5));
+      SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
+    } else {
+      SPK_TRY(op_T(h, h->wu, h->wubar, S.gamma, S.sigma));                               // update_candidate_residual! :133-164
+      SPK_TRY(op_axpby(h, nr, 1.0, h->wu, -1.0, h->wubar, h->rwu));
+      SPK_TRY(op_pdot(h, h->rwu, h->rwu, S.gamma, S.sigma, 5));
+    }
+    SPK_TRY(fetch_scalars(h, 6));
+    const double rtilde_norm = std::sqrt(h->h_scal[5]);
+    if (rnorm <= S.r_safe && rtilde_norm <= c1 * rnorm) {                                // K1 :166-191
+      std::swap(h->zv, h->wu);
+      S.r_safe = rtilde_norm + std::pow(q, (double)S.iter);
+      S.k1++;
+      loop = false;
+      continue;
+    }
+    SPK_TRY(op_axpby(h, nr, 1.0, h->rwu, -tau, h->dir, h->ws_rho));                      // :419-424
     SPK_TRY(op_pdot(h, h->rwu, h->ws_rho, S.gamma, S.sigma, 6));
     SPK_TRY(fetch_scalars(h, 7));
     double rho = h->h_scal[6];
-    if (rho >= sigma_k2 * rnorm * rtilde_norm) {                                       // K2 :193-222
+    if (rho >= sigma_k2 * rnorm * rtilde_norm) {                                         // K2 :193-222
       rho /= rtilde_norm * rtilde_norm;
       SPK_TRY(op_axpby(h, nr, 1.0, h->zv, -(lambda_sp * rho), h->rwu, h->zv));
       S.k2++;
-    } else {                                                                           // fallback :443-446
-      backtrack_count = 9;
-      std::swap(h->zv, h->zvbar);
-      S.fb++;
+      loop = false;
+      continue;
     }
+    if (h->sp_options & SPK_SP_LINESEARCH) {
+      tau *= beta;                                                                       // :224-230 with the result assigned
+      backtrack_count += 1;
+    } else {
+      backtrack_count = MAX_BACKTRACK_COUNT + 1;  // the remaining 8 candidates are identical
+    }
+  }
+  if (loop) {                                                                            // fallback :443-446
+    std::swap(h->zv, h->zvbar);
+    S.fb++;
   }
   *bc = backtrack_count;
   return launch_termination(h, S);
@@ -2151,7 +2175,7 @@ int spk_step(spk_handle *h, int32_t K, double gamma, double sigma, float *ms) {
   S.gamma = gamma; S.sigma = sigma; S.tol = 0.0; S.verbose_log = 0;
   SPK_TRY(ctl_begin(h, 0.0, 0, 1));  // also clears the device-side `done` flag that gates the fused kernels
   LoopTimer timer(h);
-  if (h->dev_loop && h->alg == SPK_SP) {  // SuperMann without host decisions (spk_sp.cuh)
+  if (h->dev_loop && h->alg == SPK_SP && !h->sp_options) {  // SuperMann without host decisions (spk_sp.cuh)
     for (int k = 0; k < K; ++k) {
       SPK_TRY(sp_pass_device(h, gamma, sigma));
       if (h->prof_on && h->prof_open.size() > 8192) prof_harvest(h);
@@ -2263,6 +2287,14 @@ int spk_set_L_norm(spk_handle *h, double L_norm) {
   return SPK_OK;
 }
 
+int spk_set_sp_options(spk_handle *h, int32_t options) {
+  if (!h || (options & ~3)) return fail(SPK_ERR_INVALID, "unknown SuperMann option");
+  if (h->group)
+    for (spk_handle *s : h->group->subs) spk_set_sp_options(s, options);
+  h->sp_options = options;
+  return SPK_OK;
+}
+
 int spk_get_residuals(spk_handle *h, double out[2]) {
   if (!h || !out) return fail(SPK_ERR_INVALID, "NULL argument");
   if (h->group) h = h->group->subs[0];  // the residual pair is global on every rank
@@ -2298,7 +2330,7 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
   SPK_TRY(ctl_begin(h, tol, verbose_log, 0));
   LoopTimer timer(h);
   // Device-resident loop: CP (SILENT; LOG needs the xi vector, cp.jl:82-86) and SP (both modes, sp.jl:304)
-  if (h->dev_loop && (h->alg == SPK_SP || !verbose_log)) {
+  if (h->dev_loop && (h->alg == SPK_SP || !verbose_log) && !(h->alg == SPK_SP && h->sp_options)) {
     const int batch = poll_batch(h);
     int launched = 0;
     while (launched < max_iter) {

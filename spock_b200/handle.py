@@ -92,6 +92,10 @@ class Handle:
             raise ValueError("state has the wrong length")
         check(self.lib, self.lib.spk_set_state(self._h, dptr(state)))
 
+    def set_sp_options(self, linesearch: bool = False, k0: bool = False):
+        """SuperMann variants present but not executed in the reference (sp.jl:439, sp.jl:80); default = as shipped."""
+        check(self.lib, self.lib.spk_set_sp_options(self._h, (1 if linesearch else 0) | (2 if k0 else 0)))
+
     def estimate_L_norm(self, iters: int = 0, apply: bool = False) -> float:
         """||L||^2 by power iteration on the device; apply=True makes it the value behind the default step sizes."""
         out = C.c_double()

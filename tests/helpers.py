@@ -262,3 +262,31 @@ def check_nan_never_converges(lib, alg):
     o = Oracle(flat, alg)
     ro, _ = o.solve(x0, tol=1e-3, max_iter=12)
     assert ro["converged"] == 0 and ro["passes"] == 12
+
+
+def check_sp_options(lib, flat, K=12):
+    """SuperMann variants behind spk_set_sp_options (working line search tau <- beta tau, sp.jl:439; K0 blind update, sp.jl:80)
+    against the oracle's restatement of the same variants: iterate after K passes and the branch counts of a solve."""
+    x0 = 0.1 * np.ones(flat.nx)
+    for ls, k0 in ((True, False), (False, True), (True, True)):
+        h, o = Handle(flat, SP, factor_mode=1, lib=lib), Oracle(flat, SP)
+        h.set_sp_options(linesearch=ls, k0=k0)
+        o.set_sp_options(linesearch=ls, k0=k0)
+        h.set_x0(x0)
+        o.set_x0(x0)
+        h.step(K)
+        o.step(K)
+        z, v = h.get_iterate()
+        assert relerr(z, o.z) < 1e-9 and relerr(v, o.v) < 1e-9, (ls, k0, relerr(z, o.z), relerr(v, o.v))
+        h.close()
+        h, o = Handle(flat, SP, factor_mode=0, lib=lib), Oracle(flat, SP)
+        h.set_sp_options(linesearch=ls, k0=k0)
+        o.set_sp_options(linesearch=ls, k0=k0)
+        rh, lh = h.solve(x0, tol=5e-2)
+        ro, lo = o.solve(x0, tol=5e-2)
+        assert rh["converged"] == ro["converged"] == 1
+        if ro["passes"] <= 30:
+            assert rh["passes"] == ro["passes"]
+            assert (rh["k1_count"], rh["k2_count"], rh["fallback_count"]) == (ro["k1_count"], ro["k2_count"], ro["fallback_count"])
+            assert np.array_equal(lh["backtrack_count"], lo["backtrack_count"])
+        h.close()

@@ -19,7 +19,7 @@ from oracle.oracle import CP, SP, Oracle
 from spock_b200.examples import get_random_system_specs, get_server_heat_specs
 from spock_b200.handle import Handle
 from spock_b200.problem import flatten_problem
-from tests.helpers import (check_nan_never_converges, check_soc_branches, check_soc_edge_vectors,
+from tests.helpers import (check_nan_never_converges, check_soc_branches, check_sp_options, check_soc_edge_vectors,
                            check_warm_started_second_solve, relerr)
 
 pytestmark = pytest.mark.gpu
@@ -158,3 +158,10 @@ def test_top_of_tree_kernels_equal_level_launches(cuda_lib, nx, nu, d, N, monkey
     for key in (("1", "0"), ("1", "3")):
         for (za, va, xa), (zb, vb, xb) in zip(out[("0", "0")], out[key]):
             assert np.array_equal(za, zb) and np.array_equal(va, vb) and xa == xb
+
+
+@pytest.mark.parametrize("name", ["heat_N7_d2_nx5", "l2ball_N4_d3_nx3"])
+def test_supermann_options_match_oracle(cuda_lib, name):
+    """working line search / K0 (non-default; the reference ships with both switched off, sp.jl:439 and sp.jl:80)"""
+    from tests.helpers import flat_of
+    check_sp_options(cuda_lib, flat_of(name))

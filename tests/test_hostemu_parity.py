@@ -6,7 +6,7 @@ import pytest
 
 from oracle.oracle import CP, SP, Oracle
 from spock_b200.handle import Handle
-from tests.helpers import (SMALL_PROBLEMS, check_k_steps, check_nan_never_converges, check_operators, check_soc_branches,
+from tests.helpers import (SMALL_PROBLEMS, check_k_steps, check_nan_never_converges, check_operators, check_soc_branches, check_sp_options,
                            check_soc_edge_vectors, check_warm_started_second_solve, flat_of, golden_cp, golden_sp, relerr)
 
 
@@ -196,3 +196,10 @@ def test_warm_started_second_solve_matches_oracle(emu_lib, alg, tol, host_loop, 
 def test_nan_iterate_never_reports_convergence(emu_lib, alg, host_loop, monkeypatch):
     monkeypatch.setenv("SPK_HOST_LOOP", host_loop)
     check_nan_never_converges(emu_lib, alg)
+
+
+@pytest.mark.parametrize("name", ["heat_N7_d2_nx5", "l2ball_N4_d3_nx3"])
+def test_supermann_options_match_oracle(emu_lib, name):
+    """working line search / K0 (non-default; the reference ships with both switched off, sp.jl:439 and sp.jl:80)"""
+    from tests.helpers import flat_of
+    check_sp_options(emu_lib, flat_of(name))
