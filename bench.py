@@ -288,8 +288,9 @@ def unit_name(workload):
 
 # ------------------------------------------------------------------------------------------------ latency workloads
 
-def closed_loop(solver, dyn, nx, d, steps=20):
-    """examples/server_heat/mpc_simulation.jl:38-54: solve, apply u_1, draw the disturbance, advance the state."""
+def closed_loop(solver, dyn, nx, d, steps=20, after_step=None):
+    """examples/server_heat/mpc_simulation.jl:38-54: solve, apply u_1, draw the disturbance, advance the state.
+    after_step(w): hook between two solves (shift-initialisation of the warm start)."""
     rng = np.random.default_rng(1)
     x0 = 0.1 * np.ones(nx)
     lat, passes = [], []
@@ -300,6 +301,10 @@ def closed_loop(solver, dyn, nx, d, steps=20):
         passes.append(k)
         w = int(rng.integers(1, d + 1)) - 1
         x0 = dyn.A[w] @ x0 + dyn.B[w] @ u
+        if after_step is not None:
+            t0 = time.perf_counter()
+            after_step(w)
+            lat[-1] += time.perf_counter() - t0
     return lat, passes, x0
 
 
@@ -391,6 +396,47 @@ def bench_latency(args, lib):
                      "us_per_launch": 1000.0 * float(np.mean(dev_ms)) * args.steps / max(launches, 1)},
         "details": info,
     }
+    if not args.no_extras and args.workload == "config4":
+        # (1) shift-initialised warm starts (spk_shift_iterate) instead of the reference's unshifted re-solve
+        model = build_model(*spec, SolverOptions(SP, None, factor_mode=1 if args.factor_mode == "per_stage" else 0))
+
+        def solver2(x0):
+            solve_model_(model, x0, tol=1e-3, quiet=True)
+            return model.solver_state.z[model.solver_state_internal.u_inds[:nu]].copy(), model.last_result["passes"]
+        lat2, passes2, xf2 = closed_loop(solver2, spec[2], nx, d, after_step=lambda w: model.handle.shift_iterate(w))
+        info["shift_initialisation"] = {"latency_s_per_mpc_step": [round(x, 6) for x in lat2], "passes_per_mpc_step": passes2,
+                                        "closed_loop_ms": 1000.0 * sum(lat2), "x_norm_final": float(np.linalg.norm(xf2))}
+        model.handle.close()
+        # (2) independent MPC problems sharing the GPU: one cold-start solve of B models, batched (spk_solve_batch: the
+        #     device-resident loops overlap on their own streams) against one after the other
+        from spock_b200.handle import Handle, solve_batch
+        from spock_b200.problem import flatten_problem
+
+        flat = flatten_problem(*spec)
+        B = 16
+        x0s = [0.1 * np.ones(nx) * (1.0 + 0.02 * k) for k in range(B)]
+        out = {}
+        for mode in ("sequential", "batched"):
+            hs = [Handle(flat, 2, factor_mode=1 if args.factor_mode == "per_stage" else 0) for _ in range(B)]
+            for h in hs:  # warm the graphs up on a throw-away solve, then restart cold
+                h.solve(x0s[0], tol=1e-3)
+                h.set_iterate(np.zeros(h.nz), np.zeros(h.nv))
+            hs = [Handle(flat, 2, factor_mode=1 if args.factor_mode == "per_stage" else 0) for _ in range(B)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if mode == "batched":
+                res = solve_batch(hs, x0s, tol=1e-3)
+                passes_b = [r["passes"] for r in res]
+            else:
+                passes_b = [h.solve(x, tol=1e-3)[0]["passes"] for h, x in zip(hs, x0s)]
+            torch.cuda.synchronize()
+            out[mode] = {"seconds": time.perf_counter() - t0, "passes": passes_b}
+            for h in hs:
+                h.close()
+        info["batched_independent_problems"] = {"models": B, "what": "one cold-start SuperMann solve to 1e-3 per model",
+                                                "sequential_s": out["sequential"]["seconds"], "batched_s": out["batched"]["seconds"],
+                                                "solves_per_s_batched": B / out["batched"]["seconds"],
+                                                "same_passes": out["sequential"]["passes"] == out["batched"]["passes"]}
     if not args.no_extras:
         cb = cpu_latency(args.workload, 1, max(1, min(args.steps, 3)), 1)
         line["cpu_baseline"] = {"value": cb["value"], "unit": unit_name(args.workload), "cores": 1, "kind": "port", "sample": cb["sample"],

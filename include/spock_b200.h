@@ -151,6 +151,16 @@ int spk_solve(spk_handle *h, const double *x0, double tol, int32_t max_iter, dou
               int32_t verbose_log, const double *z0, const double *v0, spk_result *result, double *log_xi,
               double *log_xi1, double *log_xi2, int32_t *log_backtrack, int32_t log_cap);
 
+/* MPC serving (examples/server_heat/mpc_simulation.jl:38-183).
+ * spk_shift_iterate: shift-initialisation of the next receding-horizon solve -- after the first input has been applied and
+ * the disturbance observed (`child` = 0-based ordinal of the realised child of the root), every node of the new problem
+ * takes the warm-start values of the corresponding node one stage deeper in that child's subtree; the last stage keeps
+ * its values.  (The reference re-solves from the unshifted iterate; this is an optional better initial guess.)
+ * spk_solve_batch: solve_model! (SILENT, default step sizes, warm start) for n independent models that share the GPU --
+ * the device-resident loops of all handles run concurrently on their own streams.  x0s = n vectors of nx, back to back. */
+int spk_shift_iterate(spk_handle *h, int32_t child);
+int spk_solve_batch(spk_handle **handles, int32_t n, const double *x0s, double tol, int32_t max_iter, spk_result *results);
+
 /* Solver memory that persists ACROSS solves besides (z, v): checkpoint / resume and bit-exact warm starts (MPC).
  * CP (model.jl:80-125): [z_old | v_old]                                                          -> nz+nv doubles.
  * SP (model.jl:137-226, spock.jl:160-202): [z_old|v_old], [rz_old|rv_old], [delta_z|delta_v], the Anderson columns

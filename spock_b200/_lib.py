@@ -24,7 +24,7 @@ EXPORTS = [
     "spk_set_x0", "spk_set_iterate", "spk_get_iterate", "spk_apply", "spk_dot", "spk_get_factors", "spk_step",
     "spk_solve", "spk_get_residuals", "spk_profile", "spk_profile_get", "spk_launch_count", "spk_device_bytes",
     "spk_comm_unique_id", "spk_owned_ranges", "spk_state_size", "spk_get_state", "spk_set_state",
-    "spk_estimate_L_norm", "spk_set_L_norm", "spk_gather_iterate", "spk_set_sp_options",
+    "spk_estimate_L_norm", "spk_set_L_norm", "spk_gather_iterate", "spk_set_sp_options", "spk_shift_iterate", "spk_solve_batch",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -94,6 +94,8 @@ def bind(path: str) -> C.CDLL:
     lib.spk_set_L_norm.argtypes = [vp, C.c_double]
     lib.spk_gather_iterate.argtypes = [vp]
     lib.spk_set_sp_options.argtypes = [vp, C.c_int32]
+    lib.spk_shift_iterate.argtypes = [vp, C.c_int32]
+    lib.spk_solve_batch.argtypes = [C.POINTER(vp), C.c_int32, _dp, C.c_double, C.c_int32, C.POINTER(SpkResult)]
     for name in EXPORTS:
         if name not in ("spk_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -420,6 +420,41 @@ SPK_KERNEL void spk_k_axpby(long n, double a, const double *x, double b, const d
     out[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
 }
 
+// Shift-initialisation of a receding-horizon warm start (the reference's closed loop,
+// examples/server_heat/mpc_simulation.jl:38-54, re-solves from the previous (z, v) unshifted): after the first input has
+// been applied and the disturbance `w` (ordinal of the realised child of the root) observed, the new problem's node at
+// (stage t, position p) is the old problem's node at (stage t+1, position w d^t + p).  Every entry of (z | v) keyed by a node
+// takes the old value of its source node where that source has such an entry; the last stage keeps its old values.
+SPK_KERNEL void spk_k_shift(SpkDims D, int w, const double *__restrict__ oldzv, double *__restrict__ zv) {
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D.n) return;
+  int t = 0;
+  long first = 0, cnt = 1;  // first0 and node count of level t
+  while (j >= first + cnt) { first += cnt; cnt *= D.d; ++t; }
+  if (t > D.N - 2) return;                          // leaves have no deeper source
+  const long s = first + cnt + (long)w * cnt + (j - first);  // source node (0-based) on level t+1
+  const double *oz = oldzv, *ov = oldzv + D.nz;
+  double *z = zv, *v = zv + D.nz;
+  for (int k = 0; k < D.nx; ++k) z[j * D.nx + k] = oz[s * D.nx + k];
+  z[D.zo[2] + j] = oz[D.zo[2] + s];
+  if (j >= 1) {
+    z[D.zo[3] + j - 1] = oz[D.zo[3] + s - 1];
+    for (int k = 0; k < D.nx; ++k) v[D.vo[2] + (j - 1) * D.nx + k] = ov[D.vo[2] + (s - 1) * D.nx + k];
+    for (int k = 0; k < D.nu; ++k) v[D.vo[3] + (j - 1) * D.nu + k] = ov[D.vo[3] + (s - 1) * D.nu + k];
+    v[D.vo[4] + j - 1] = ov[D.vo[4] + s - 1];
+    v[D.vo[5] + j - 1] = ov[D.vo[5] + s - 1];
+  }
+  if (s < D.nnl) {                                   // entries keyed by a non-leaf node (j is non-leaf since t <= N-2)
+    for (int k = 0; k < D.nu; ++k) z[D.zo[1] + j * D.nu + k] = oz[D.zo[1] + s * D.nu + k];
+    for (int k = 0; k < D.ny; ++k) {
+      z[D.zo[4] + j * D.ny + k] = oz[D.zo[4] + s * D.ny + k];
+      v[D.vo[0] + j * D.ny + k] = ov[D.vo[0] + s * D.ny + k];
+    }
+    v[D.vo[1] + j] = ov[D.vo[1] + s];
+    for (int k = 0; k < D.nx + D.nu; ++k) v[D.vo[6] + j * (D.nx + D.nu) + k] = ov[D.vo[6] + s * (D.nx + D.nu) + k];
+  }
+}
+
 // x[idx] += a
 SPK_KERNEL void spk_k_add_scalar(double *x, long idx, double a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) x[idx] += a;

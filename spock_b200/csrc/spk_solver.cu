@@ -550,6 +550,23 @@ typedef void (*spk_fused_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs);
 typedef void (*spk_dual2_kernel_t)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long);
 #endif
 
+#ifndef SPK_HOST_EMU
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION, shared by every handle of the process (the
+// runtime-size instantiations serve all unspecialised shapes): only ever raise it
+static cudaError_t set_max_smem(const void *fn, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> cur;  // (function, device): the attribute is per device
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t &c = cur[std::make_pair(fn, dev)];
+  if (bytes <= c) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) c = bytes;
+  return e;
+}
+#endif
+
 static int fused_setup(spk_handle *h) {
   const SpkDims &D = h->D;
   h->fused_ok = false;
@@ -610,11 +627,11 @@ static int fused_setup(spk_handle *h) {
   h->fused_smem_dual = (size_t)spk_dual_warp_doubles(D) * h->dual_warps * sizeof(double);
 #ifndef SPK_HOST_EMU
   if (std::max(h->fused_smem_bwd, h->fused_smem_fwd) > 227 * 1024 || h->fused_smem_dual > 200 * 1024) return SPK_OK;
-  RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
-  RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
-  RT_CHECK(cudaFuncSetAttribute((const void *)h->k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_dual));
+  RT_CHECK(set_max_smem((const void *)h->k_bwd, h->fused_smem_bwd));
+  RT_CHECK(set_max_smem((const void *)h->k_fwd, h->fused_smem_fwd));
+  RT_CHECK(set_max_smem((const void *)h->k_dual, h->fused_smem_dual));
   if (h->use_dual2)
-    RT_CHECK(cudaFuncSetAttribute((const void *)h->k_dual2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dual2_smem));
+    RT_CHECK(set_max_smem((const void *)h->k_dual2, h->dual2_smem));
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd, (const void *)h->k_bwd, Tb, h->fused_smem_bwd));
   RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd, (const void *)h->k_fwd, Tf, h->fused_smem_fwd));
   h->occ_bwd = std::max(1, h->occ_bwd);
@@ -624,8 +641,8 @@ static int fused_setup(spk_handle *h) {
     // because the floor is the dependent chain INSIDE a level, not the launch.  The kernels stay as an opt-in (SPK_TOPK=1).
     const char *nt = getenv("SPK_TOPK");
     int ob = 0, of = 0;
-    RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_bwd));
-    RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem_fwd));
+    RT_CHECK(set_max_smem((const void *)h->k_bwd_top, h->fused_smem_bwd));
+    RT_CHECK(set_max_smem((const void *)h->k_fwd_top, h->fused_smem_fwd));
     RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, (const void *)h->k_bwd_top, Tb, h->fused_smem_bwd));
     RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, (const void *)h->k_fwd_top, Tf, h->fused_smem_fwd));
     h->top_cap_bwd = (long)h->num_sms * ob;
@@ -656,13 +673,13 @@ static int fused_setup(spk_handle *h) {
       SPK_TRY(upload(h, &h->d_frag_bwd, fb.data(), (long)fb.size()));
       SPK_TRY(upload(h, &h->d_frag_fwd, ff.data(), (long)ff.size()));
       for (int k = 0; k < 2; ++k)
-        RT_CHECK(cudaFuncSetAttribute((const void *)h->k_bwd_mm[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-      RT_CHECK(cudaFuncSetAttribute((const void *)h->k_fwd_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
+        RT_CHECK(set_max_smem((const void *)h->k_bwd_mm[k], sb));
+      RT_CHECK(set_max_smem((const void *)h->k_fwd_mm, sf));
       RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_bwd_mm, (const void *)h->k_bwd_mm[1], 256, sb));
       RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_fwd_mm, (const void *)h->k_fwd_mm, 256, sf));
       h->occ_bwd_mm = std::max(1, h->occ_bwd_mm);
       h->occ_fwd_mm = std::max(1, h->occ_fwd_mm);
-      RT_CHECK(cudaFuncSetAttribute((const void *)h->k_top_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sb, sf)));
+      RT_CHECK(set_max_smem((const void *)h->k_top_mm, std::max(sb, sf)));
       const char *nt = getenv("SPK_NO_TOP");
       h->t_top = -1;
       // (measured: with large fragment tables -- nx = 50: 93-168 KB per level -- a level in the single-CTA kernel costs
@@ -2284,6 +2301,97 @@ int spk_set_L_norm(spk_handle *h, double L_norm) {
   if (h->group)
     for (spk_handle *s : h->group->subs) s->L_norm = L_norm;
   h->L_norm = L_norm;
+  return SPK_OK;
+}
+
+int spk_shift_iterate(spk_handle *h, int32_t child) {
+  if (!h) return fail(SPK_ERR_INVALID, "NULL handle");
+  if (h->world > 1 || h->group) return fail(SPK_ERR_INVALID, "spk_shift_iterate is single-GPU");
+  if (child < 0 || child >= h->D.d) return fail(SPK_ERR_INVALID, "child ordinal out of range");
+  const long nr = h->D.nz + h->D.nv;
+  SPK_TRY(rt_d2d(h->zvbar, h->zv, sizeof(double) * nr, h->stream));  // zvbar is scratch between evaluations
+  const int b = elem_block();
+  SPK_LAUNCH(spk_k_shift, grid_for(h->D.n, b), b, 0, h->stream, h->D, (int)child, h->zvbar, h->zv);
+  COUNT_LAUNCH(h, PC_VEC);
+  SPK_TRY(rt_launch_check());
+  return rt_sync(h->stream);
+}
+
+// solve_model! for several independent models at once (MPC serving: many small problems share one GPU).  Every handle
+// runs its device-resident loop on its own stream; the host launches a few passes of each, then polls each, so the
+// latency-bound kernels of the different problems overlap on the device.  Handles that cannot run the device-resident
+// loop (LOG mode, SuperMann options, several GPUs) are solved one after the other.
+int spk_solve_batch(spk_handle **hs, int32_t n, const double *x0s, double tol, int32_t max_iter, spk_result *results) {
+  if (!hs || n < 0 || !x0s) return fail(SPK_ERR_INVALID, "NULL argument");
+  std::vector<int> launched((size_t)n, 0), maxit((size_t)n, 0);
+  std::vector<char> active((size_t)n, 0);
+  std::vector<double> gam((size_t)n, 0.0), sig((size_t)n, 0.0);
+  size_t x0_off = 0;
+  for (int k = 0; k < n; ++k) {
+    spk_handle *h = hs[k];
+    if (!h) return fail(SPK_ERR_INVALID, "NULL handle in batch");
+    const double *x0 = x0s + x0_off;  // back to back: the models may have different nx
+    x0_off += (size_t)h->D.nx;
+    const bool dev = !h->group && h->world == 1 && h->dev_loop && !(h->alg == SPK_SP && h->sp_options);
+    if (!dev) {
+      SPK_TRY(spk_solve(h, x0, tol, max_iter, 0.0, 0.0, 0, nullptr, nullptr, results ? results + k : nullptr, nullptr, nullptr,
+                        nullptr, nullptr, 0));
+      continue;
+    }
+    h->gathered = false;
+    SPK_TRY(spk_set_x0(h, x0));
+    h->res_0[0] = h->res_0[1] = -INFINITY;
+    default_steps(h, gam[k], sig[k]);
+    maxit[k] = max_iter > 0 ? max_iter : (h->alg == SPK_SP ? 1000 : 5000);
+    SPK_TRY(ctl_begin(h, tol, 0, 0));
+#ifndef SPK_HOST_EMU
+    cudaEventRecord(h->ev_a, h->stream);
+#endif
+    active[k] = 1;
+  }
+  bool any = true;
+  while (any) {
+    any = false;
+    for (int k = 0; k < n; ++k) {  // queue a few passes of every unfinished problem ...
+      if (!active[k]) continue;
+      spk_handle *h = hs[k];
+      LoopState S;
+      S.gamma = gam[k]; S.sigma = sig[k]; S.tol = tol; S.verbose_log = 0;
+      const int nb = std::min(poll_batch(h), maxit[k] - launched[k]);
+      for (int b = 0; b < nb; ++b, ++launched[k]) {
+        if (h->alg == SPK_SP) {
+          SPK_TRY(sp_pass_device(h, gam[k], sig[k]));
+        } else {
+          SPK_TRY(cp_pass_launch(h, S));
+          SPK_TRY(launch_terminate(h, 0, 0));
+        }
+      }
+    }
+    for (int k = 0; k < n; ++k) {  // ... then look at each one's control block
+      if (!active[k]) continue;
+      spk_handle *h = hs[k];
+      SPK_TRY(ctl_poll(h));
+      if (!h->h_ctl.done && launched[k] < maxit[k]) { any = true; continue; }
+      const SpkCtl &c = h->h_ctl;
+      const int passes = c.passes, converged = c.done ? 1 : 0;
+      if (h->alg == SPK_CP && ((launched[k] - passes) & 1)) std::swap(h->zv, h->zvbar);  // gated passes did not move the iterate
+      ctl_end(h);
+      float ms = 0.f;
+#ifndef SPK_HOST_EMU
+      cudaEventRecord(h->ev_b, h->stream);
+      cudaEventSynchronize(h->ev_b);
+      cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+#endif
+      if (results) {
+        spk_result &r = results[k];
+        r.passes = passes; r.printed_iter = converged ? passes - 1 : passes; r.converged = converged;
+        r.xi1 = c.xi1; r.xi2 = c.xi2; r.xi = NAN;
+        r.k1_count = c.k1; r.k2_count = c.k2; r.fallback_count = c.fb;
+        r.solve_ms = ms;
+      }
+      active[k] = 0;
+    }
+  }
   return SPK_OK;
 }
 

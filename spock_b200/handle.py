@@ -96,6 +96,10 @@ class Handle:
         """SuperMann variants present but not executed in the reference (sp.jl:439, sp.jl:80); default = as shipped."""
         check(self.lib, self.lib.spk_set_sp_options(self._h, (1 if linesearch else 0) | (2 if k0 else 0)))
 
+    def shift_iterate(self, child: int):
+        """Shift-initialisation of the next receding-horizon solve (`child`: 0-based ordinal of the realised child of the root)."""
+        check(self.lib, self.lib.spk_shift_iterate(self._h, int(child)))
+
     def estimate_L_norm(self, iters: int = 0, apply: bool = False) -> float:
         """||L||^2 by power iteration on the device; apply=True makes it the value behind the default step sizes."""
         out = C.c_double()
@@ -212,6 +216,18 @@ class Handle:
         n = C.c_int64()
         check(self.lib, self.lib.spk_device_bytes(self._h, C.byref(n)))
         return int(n.value)
+
+
+def solve_batch(handles, x0s, tol=1e-3, max_iter=0):
+    """solve_model! for several independent models at once (their device-resident loops overlap on the GPU).
+    x0s: one initial state per handle.  Returns the list of result dicts."""
+    lib = handles[0].lib
+    n = len(handles)
+    arr = (C.c_void_p * n)(*[h._h for h in handles])
+    x = np.ascontiguousarray(np.concatenate([_f64(x0) for x0 in x0s]))
+    res = (SpkResult * n)()
+    check(lib, lib.spk_solve_batch(arr, n, dptr(x), float(tol), int(max_iter), res))
+    return [{f: getattr(res[k], f) for f, _ in SpkResult._fields_} for k in range(n)]
 
 
 def tree_maps(N: int, d: int, lib=None):

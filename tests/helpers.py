@@ -290,3 +290,79 @@ def check_sp_options(lib, flat, K=12):
             assert (rh["k1_count"], rh["k2_count"], rh["fallback_count"]) == (ro["k1_count"], ro["k2_count"], ro["fallback_count"])
             assert np.array_equal(lh["backtrack_count"], lo["backtrack_count"])
         h.close()
+
+
+def check_shift_iterate(lib, flat, w):
+    """spk_shift_iterate against an independent derivation by tree PATHS: the node reached from the root by the child
+    ordinals (c1, .., ct) takes the values of the node reached by (w, c1, .., ct); entries whose source does not exist
+    (last stage; non-leaf-keyed entries whose source is a leaf) keep their values."""
+    from spock_b200.handle import tree_maps
+
+    h = Handle(flat, CP, lib=lib)
+    nx, nu, ny, d, n, nnl = flat.nx, flat.nu, flat.ny, flat.d, flat.n, flat.n_non_leaf
+    cf, anc, _, _ = tree_maps(flat.N, d, lib=lib)
+    rng = np.random.default_rng(3)
+    z0, v0 = rng.standard_normal(h.nz), rng.standard_normal(h.nv)
+    h.set_iterate(z0, v0)
+    h.shift_iterate(w)
+    z, v = h.get_iterate()
+    zo, vo = h.z_off, h.v_off
+
+    def path(j):  # child ordinals from the root to node j (1-based)
+        p = []
+        while j > 1:
+            a = int(anc[j - 1])
+            p.append(j - int(cf[a - 1]))
+            j = a
+        return p[::-1]
+
+    def node(p):
+        j = 1
+        for c in p:
+            if j > nnl:
+                return None
+            j = int(cf[j - 1]) + c
+        return j
+
+    ez, ev = z0.copy(), v0.copy()
+    for j in range(1, n + 1):
+        s = node([w] + path(j))
+        if s is None:
+            continue
+        j0, s0 = j - 1, s - 1
+        ez[j0 * nx:(j0 + 1) * nx] = z0[s0 * nx:(s0 + 1) * nx]
+        ez[zo[2] + j0] = z0[zo[2] + s0]
+        if j > 1:
+            ez[zo[3] + j0 - 1] = z0[zo[3] + s0 - 1]
+            ev[vo[2] + (j0 - 1) * nx: vo[2] + j0 * nx] = v0[vo[2] + (s0 - 1) * nx: vo[2] + s0 * nx]
+            ev[vo[3] + (j0 - 1) * nu: vo[3] + j0 * nu] = v0[vo[3] + (s0 - 1) * nu: vo[3] + s0 * nu]
+            ev[vo[4] + j0 - 1], ev[vo[5] + j0 - 1] = v0[vo[4] + s0 - 1], v0[vo[5] + s0 - 1]
+        if s <= nnl:
+            ez[zo[1] + j0 * nu: zo[1] + (j0 + 1) * nu] = z0[zo[1] + s0 * nu: zo[1] + (s0 + 1) * nu]
+            ez[zo[4] + j0 * ny: zo[4] + (j0 + 1) * ny] = z0[zo[4] + s0 * ny: zo[4] + (s0 + 1) * ny]
+            ev[vo[0] + j0 * ny: vo[0] + (j0 + 1) * ny] = v0[vo[0] + s0 * ny: vo[0] + (s0 + 1) * ny]
+            ev[vo[1] + j0] = v0[vo[1] + s0]
+            ev[vo[6] + j0 * (nx + nu): vo[6] + (j0 + 1) * (nx + nu)] = v0[vo[6] + s0 * (nx + nu): vo[6] + (s0 + 1) * (nx + nu)]
+    assert np.array_equal(z, ez) and np.array_equal(v, ev)
+    h.close()
+
+
+def check_solve_batch(lib, flats, algs, tol=1e-3):
+    """spk_solve_batch (independent models sharing the GPU) == one spk_solve per model: same passes, same iterate; and a
+    second, warm-started batch from the persisted state."""
+    from spock_b200.handle import solve_batch
+
+    x0s = [0.1 * np.ones(f.nx) * (1 + 0.1 * k) for k, f in enumerate(flats)]
+    x1s = [0.9 * x for x in x0s]
+    hb = [Handle(f, a, factor_mode=k % 2, lib=lib) for k, (f, a) in enumerate(zip(flats, algs))]
+    hs = [Handle(f, a, factor_mode=k % 2, lib=lib) for k, (f, a) in enumerate(zip(flats, algs))]
+    for xs in (x0s, x1s):
+        rb = solve_batch(hb, xs, tol=tol)
+        for k, h in enumerate(hs):
+            r, _ = h.solve(xs[k], tol=tol)
+            assert rb[k]["converged"] == r["converged"] == 1
+            assert rb[k]["passes"] == r["passes"], (k, rb[k]["passes"], r["passes"])
+            (zb, vb), (zs, vs) = hb[k].get_iterate(), h.get_iterate()
+            assert relerr(zb, zs) < 1e-12 and relerr(vb, vs) < 1e-12
+    for h in hb + hs:
+        h.close()

@@ -203,3 +203,15 @@ def test_supermann_options_match_oracle(emu_lib, name):
     """working line search / K0 (non-default; the reference ships with both switched off, sp.jl:439 and sp.jl:80)"""
     from tests.helpers import flat_of
     check_sp_options(emu_lib, flat_of(name))
+
+
+@pytest.mark.parametrize("name,w", [("heat_N7_d2_nx5", 1), ("heat_N4_d3_nx3", 2), ("l2ball_N4_d3_nx3", 0), ("fixture_N3_d2", 1)])
+def test_shift_initialisation(emu_lib, name, w):
+    from tests.helpers import check_shift_iterate, flat_of
+    check_shift_iterate(emu_lib, flat_of(name), w)
+
+
+def test_batched_independent_problems(emu_lib):
+    from tests.helpers import check_solve_batch, flat_of
+    names = ["heat_N7_d2_nx5", "random_N5_d2_nx6_nu3", "heat_N4_d3_nx3", "heat_N7_d2_nx5", "l2ball_N4_d3_nx3"]
+    check_solve_batch(emu_lib, [flat_of(n) for n in names], [CP, CP, CP, SP, SP])
