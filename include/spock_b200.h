@@ -94,6 +94,11 @@ typedef struct {
    * fans out to all devices; spk_get_iterate assembles the complete (z, v) in the caller's host vectors.  0 or 1: `device`. */
   int32_t n_devices;
   const int32_t *devices;
+  /* non-uniform risk measures (get_nonuniform_rms_avar_v2, risk_measures.jl:127-136; rms[i].E / .F / .b of implicit_l.jl:219,427
+   * and the per-node ls_matrix of cpock.jl:71-81): 0 or 1 = one (E, F, b) for all nodes; n_non_leaf = E, F, b hold one entry
+   * per non-leaf node, back to back (node i at offsets (i-1)*ny*d and (i-1)*ny).  ny and the sub-cone list stay uniform,
+   * as in the reference (implicit_l.jl:14,19). */
+  int32_t n_rms;
 } spk_problem;
 
 typedef struct {

@@ -48,6 +48,7 @@ struct SpkProblem
   algorithm::Int32; L_norm::Float64; factor_mode::Int32; device::Int32
   rank::Int32; world_size::Int32; comm_id::Ptr{UInt8}
   n_devices::Int32; devices::Ptr{Int32}
+  n_rms::Int32
 end
 
 struct SpkResult
@@ -125,17 +126,20 @@ function spk_build(scen_tree, cost, dynamics, rms, constraints, algorithm :: Int
   @assert length(sQ) == length(sR)
   dense = !(eltype(sQ) <: LA.Diagonal)
   A = reduce(vcat, [vec(Matrix{Float64}(a)) for a in dynamics.A]); B = reduce(vcat, [vec(Matrix{Float64}(b)) for b in dynamics.B])
-  rm = rms[1]                      # uniform risk measures (implicit_l.jl:14, 19)
+  rm = rms[1]                      # ny and the sub-cone list are uniform (implicit_l.jl:14, 19); E, F, b may differ per node
   ct = Int32[spk_cone_code(c) for c in rm.K.subcones]; cd = Int32[MOI.dimension(c) for c in rm.K.subcones]
-  E, F, b = vec(Matrix{Float64}(rm.E)), vec(Matrix{Float64}(rm.F)), Vector{Float64}(rm.b)
+  uniform_rms = all(r -> r.E == rm.E && r.F == rm.F && r.b == rm.b, rms)
+  rl = uniform_rms ? rms[1:1] : rms          # get_nonuniform_rms_avar_v2 (risk_measures.jl:127-136): one entry per non-leaf node
+  E = reduce(vcat, [vec(Matrix{Float64}(r.E)) for r in rl]); F = reduce(vcat, [vec(Matrix{Float64}(r.F)) for r in rl])
+  b = reduce(vcat, [Vector{Float64}(r.b) for r in rl])
   fQ, fR, fQN = spk_flat(sQ), spk_flat(sR), spk_flat(sQN)
   devs = haskey(ENV, "SPOCK_B200_DEVICES") ? Int32[parse(Int32, s) for s in split(ENV["SPOCK_B200_DEVICES"], ",")] : Int32[]
   fmode = get(ENV, "SPOCK_B200_FACTORS", "per_node") == "per_stage" ? 1 : 0
   keep = Any[A, B, fQ, fR, fQN, E, F, b, ct, cd, devs]
   p = SpkProblem(scen_tree.N, d, nx, nu, pointer(A), pointer(B), dense, length(sQ), pointer(fQ), pointer(fR),
-                 length(sQN), pointer(fQN), length(b), pointer(E), pointer(F), pointer(b), length(ct), pointer(ct),
+                 length(sQN), pointer(fQN), length(rm.b), pointer(E), pointer(F), pointer(b), length(ct), pointer(ct),
                  pointer(cd), constraints.x_min, constraints.x_max, constraints.u_min, constraints.u_max,
-                 algorithm, 0.0, fmode, -1, 0, 1, C_NULL, length(devs), isempty(devs) ? C_NULL : pointer(devs))
+                 algorithm, 0.0, fmode, -1, 0, 1, C_NULL, length(devs), isempty(devs) ? C_NULL : pointer(devs), length(rl))
   h = Ref{Ptr{Cvoid}}(C_NULL)
   GC.@preserve keep spk_check(ccall((:spk_create, SPK_LIB), Cint, (Ref{SpkProblem}, Ref{Ptr{Cvoid}}), p, h))
   sz = zeros(Int64, 5); spk_check(ccall((:spk_sizes, SPK_LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], sz))

@@ -32,7 +32,7 @@ class _Problem(C.Structure):
         ("n_cones", C.c_int), ("cone_type", C.POINTER(C.c_int)), ("cone_dim", C.POINTER(C.c_int)),
         ("ls_matrix", C.POINTER(C.c_double)),
         ("x_min", C.c_double), ("x_max", C.c_double), ("u_min", C.c_double), ("u_max", C.c_double),
-        ("algorithm", C.c_int), ("L_norm", C.c_double),
+        ("algorithm", C.c_int), ("L_norm", C.c_double), ("n_rms", C.c_int),
     ]
 
 
@@ -113,14 +113,19 @@ class Oracle:
         self.lib = _load(n_threads > 1)
         self.flat = flat
         self.algorithm = algorithm
-        ls = np.ascontiguousarray(kernel_projector(flat.E2d, flat.F2d).T).reshape(-1)
+        n_rms = int(getattr(flat, "n_rms", 1))
+        if n_rms > 1:  # one projector per non-leaf node (cpock.jl:71-81,125-128 loops over the nodes)
+            ls = np.concatenate([np.ascontiguousarray(kernel_projector(np.asarray(r.E, float), np.asarray(r.F, float)).T).reshape(-1)
+                                 for r in flat.rms_list])
+        else:
+            ls = np.ascontiguousarray(kernel_projector(flat.E2d, flat.F2d).T).reshape(-1)
         self._keep = [ls, flat.cone_type.astype(np.int32), flat.cone_dim.astype(np.int32)]
         ip = C.POINTER(C.c_int)
         p = _Problem(
             flat.N, flat.d, flat.nx, flat.nu, flat.ny, _dp(flat.A), _dp(flat.B), flat.cost_dense, flat.n_sqrtQ,
             _dp(flat.sqrtQ), _dp(flat.sqrtR), flat.n_sqrtQN, _dp(flat.sqrtQN), _dp(flat.E), _dp(flat.F), _dp(flat.b),
             len(flat.cone_type), self._keep[1].ctypes.data_as(ip), self._keep[2].ctypes.data_as(ip), _dp(ls),
-            flat.x_min, flat.x_max, flat.u_min, flat.u_max, algorithm, float(L_norm),
+            flat.x_min, flat.x_max, flat.u_min, flat.u_max, algorithm, float(L_norm), n_rms,
         )
         self.h = self.lib.spo_create(C.byref(p), int(n_threads))
         if not self.h:

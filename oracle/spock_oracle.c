@@ -21,6 +21,7 @@
 
 struct spo_model {
   int sp_options; /* SPO_SP_LINESEARCH | SPO_SP_K0; 0 = the reference as shipped */
+  long n_rms;     /* 1 = uniform risk measures; nnl = per-node b and ls_matrix (get_nonuniform_rms_avar_v2) */
   int N, d, nx, nu, ny, nt, alg;
   long n, nnl, nl, nz, nv;
   long zo[5];  /* x,u,s,tau,y   (implicit_l.jl:106-158) */
@@ -303,8 +304,9 @@ spo_model *spo_create(const spo_problem *p, int n_threads) {
   m->sqrtQN = dcopy(p->sqrtQN, (long)p->n_sqrtQN * (p->cost_dense ? nx * nx : nx));
   m->E = dcopy(p->E, (long)ny * d);
   m->F = dcopy(p->F, (long)ny * d);
-  m->b = dcopy(p->b, ny);
-  m->ls = dcopy(p->ls_matrix, (long)(ny + 2 * d) * (ny + 2 * d));
+  m->n_rms = p->n_rms > 1 ? p->n_rms : 1; /* rms[i].b (implicit_l.jl:219,427), ls_matrix[i] (cpock.jl:125-128) */
+  m->b = dcopy(p->b, (long)m->n_rms * ny);
+  m->ls = dcopy(p->ls_matrix, (long)m->n_rms * (ny + 2 * d) * (ny + 2 * d));
   m->n_cones = p->n_cones;
   m->cone_type = (int *)calloc((size_t)p->n_cones, sizeof(int));
   m->cone_dim = (int *)calloc((size_t)p->n_cones, sizeof(int));
@@ -401,7 +403,7 @@ void spo_L(spo_model *m, const double *z, double *v) {
   PAR_FOR
   for (long i = 1; i <= nnl; ++i) {
     double dot_p = 0.0;
-    for (int k = 0; k < ny; ++k) dot_p += m->b[k] * z[zo[4] + (i - 1) * ny + k];
+    for (int k = 0; k < ny; ++k) dot_p += m->b[(m->n_rms > 1 ? (i - 1) * ny : 0) + k] * z[zo[4] + (i - 1) * ny + k];
     v[vo[1] + i - 1] = z[zo[2] + i - 1] - dot_p;
   }
   /* v3 :226-235, v4 :239-248, v5 :253-260, v6 :265-272 */
@@ -462,7 +464,7 @@ void spo_Lt(spo_model *m, double *z, const double *v) {
       for (int k = 0; k < nu; ++k) ui[k] += tmpx[k];
     }
     /* y :423-429 */
-    for (int k = 0; k < ny; ++k) z[zo[4] + (i - 1) * ny + k] = v[(i - 1) * ny + k] - m->b[k] * v[vo[1] + i - 1];
+    for (int k = 0; k < ny; ++k) z[zo[4] + (i - 1) * ny + k] = v[(i - 1) * ny + k] - m->b[(m->n_rms > 1 ? (i - 1) * ny : 0) + k] * v[vo[1] + i - 1];
     /* tau :432-437 */
     for (long j = c0; j < c0 + d; ++j) {
       const long j_ind = j - 1;
@@ -597,7 +599,7 @@ void spo_projection_S2(spo_model *m, double *z2) {
     for (int k = 0; k < ny; ++k) ls_b[k] = z2[y_offset + (i - 1) * ny + k];          /* :712 */
     for (int k = 0; k < d; ++k) ls_b[ny + k] = z2[(ch1 - 1) - 1 + k];                /* :713 */
     for (int k = 0; k < d; ++k) ls_b[ny + d + k] = z2[tau_offset + (ch1 - 1) - 1 + k]; /* :714 */
-    gemv_n(m->ls, nls, nls, ls_b, ls_b2);                                            /* :717 */
+    gemv_n(m->ls + (m->n_rms > 1 ? (i - 1) * (long)nls * nls : 0), nls, nls, ls_b, ls_b2);                                            /* :717 */
     for (int k = 0; k < ny; ++k) z2[y_offset + (i - 1) * ny + k] = ls_b2[k];         /* :721 */
     for (int k = 0; k < d; ++k) z2[(ch1 - 1) - 1 + k] = ls_b2[ny + k];               /* :723 */
     for (int k = 0; k < d; ++k) z2[tau_offset + (ch1 - 1) - 1 + k] = ls_b2[ny + d + k]; /* :725 */

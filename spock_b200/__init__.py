@@ -8,7 +8,7 @@ from .model import (AA, CP, CPOCK, LOG, RB, SILENT, SP, SPOCK, AlgorithmOptions,
                     VERBOSE_LEVEL, L_, L_transpose_, build_model, prox_f_, prox_h_conj_, solve_model, solve_model_,
                     spock_dot, spock_mul_, spock_norm)
 from .problem import (ConvexCone, Cost, Diagonal, Dynamics, Nonnegatives, Nonpositives, Reals, RiskMeasure,  # noqa: F401
-                      SecondOrderCone, UniformRectangle, Zeros, flatten_problem, get_uniform_rms_avar_v2,
+                      SecondOrderCone, UniformRectangle, Zeros, flatten_problem, get_nonuniform_rms_avar_v2, get_uniform_rms_avar_v2,
                       get_uniform_rms_l2ball_v2, get_uniform_rms_tv_v2, get_uniform_rms_v2)
 from .scenario_tree import ScenarioTree, generate_scenario_tree_uniform_branching_factor_v2  # noqa: F401
 

@@ -719,8 +719,9 @@ SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   const long cfirst = (long)d * i0 + 1;
   double in[CAP];
   const double v2i = A.v[D.vo[1] + i0];
+  const double *__restrict__ bi = spk_b(D, P, i0), *__restrict__ lsi = spk_ls(D, P, i0);
   _Pragma("unroll") for (int k = 0; k < (NY_ > 0 ? NY_ : ny); ++k)
-    in[k] = A.z[D.zo[4] + i0 * ny + k] - gamma * (A.v[i0 * ny + k] - P.b[k] * v2i);
+    in[k] = A.z[D.zo[4] + i0 * ny + k] - gamma * (A.v[i0 * ny + k] - bi[k] * v2i);
   _Pragma("unroll") for (int c = 0; c < (NY_ > 0 ? DD_ : d); ++c) {
     const long j0 = cfirst + c;
     const double lt = (j0 < D.nnl) ? A.v[D.vo[1] + j0] : 0.5 * A.v[D.vo[8] + (j0 - D.nnl)] + 0.5 * A.v[D.vo[9] + (j0 - D.nnl)];
@@ -729,7 +730,7 @@ SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   }
   _Pragma("unroll") for (int k = 0; k < (NY_ > 0 ? CAP : nls); ++k) {
     double acc = 0.0;
-    _Pragma("unroll") for (int m = 0; m < (NY_ > 0 ? CAP : nls); ++m) acc += P.ls[k + (long)m * nls] * in[m];
+    _Pragma("unroll") for (int m = 0; m < (NY_ > 0 ? CAP : nls); ++m) acc += lsi[k + (long)m * nls] * in[m];
     if (k < ny) A.zbar[D.zo[4] + i0 * ny + k] = acc;
     else if (k < ny + d) A.zbar[D.zo[2] + cfirst + (k - ny)] = acc;
     else A.zbar[D.zo[3] + cfirst + (k - ny - d) - 1] = acc;
@@ -844,8 +845,8 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
       }
       double bwy = 0.0, bdy = 0.0;  // every lane computes b'wy (ny is tiny) so that no broadcast is needed
       for (int k = 0; k < ny; ++k) {
-        bwy += P.b[k] * wy[k];
-        bdy += P.b[k] * dy[k];
+        bwy += spk_b(D, P, i0)[k] * wy[k];
+        bdy += spk_b(D, P, i0)[k] * dy[k];
       }
       const double v2old = A.v[D.vo[1] + i0];
       const double w2 = (v2old + sigma * (ws_i - bwy)) / sigma;  // L! :214-222
@@ -975,7 +976,7 @@ SPK_KERNEL void spk_k_dual(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
       for (int c = 0; c < d; ++c) lt += spk_cost_row(spk_sqrtR(D, P, cfirst + c), D.cost_dense, nu, k, dv4 + c * nu);
       SPK_Z(du[k], lt);
     }
-    for (int k = lane; k < ny; k += WL) SPK_Z(dy[k], dv1[k] - P.b[k] * dv2);  // y_i :423-429
+    for (int k = lane; k < ny; k += WL) SPK_Z(dy[k], dv1[k] - spk_b(D, P, i0)[k] * dv2);  // y_i :423-429
     if (lane == 0) SPK_Z(ds_i, dv2);                                          // s_i :440-442
     if (leaves)
       for (int idx = lane; idx < d * nx; idx += WL) {  // x_leaf :376-396
@@ -1102,7 +1103,7 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
     for (int e = tid; e < f * ny; e += T) S[M.W1 + e] = (S[M.v1 + e] + sigma * S[M.wy + e]) / sigma;
     for (int ff = tid; ff < f; ff += T) {
       double bwy = 0.0;
-      for (int k = 0; k < ny; ++k) bwy += P.b[k] * S[M.wy + ff * ny + k];
+      for (int k = 0; k < ny; ++k) bwy += spk_b(D, P, i0 + ff)[k] * S[M.wy + ff * ny + k];
       S[M.W2 + ff] = (S[M.v2 + ff] + sigma * (S[M.ws + ff] - bwy)) / sigma;
     }
     for (int e = tid; e < f * nxu; e += T) {
@@ -1192,7 +1193,7 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
     }
     for (int ff = tid; ff < f; ff += T) {  // v2 (:849-851)
       double bdy = 0.0;
-      for (int k = 0; k < ny; ++k) bdy += P.b[k] * S[M.dy + ff * ny + k];
+      for (int k = 0; k < ny; ++k) bdy += spk_b(D, P, i0 + ff)[k] * S[M.dy + ff * ny + k];
       const double w2 = S[M.W2 + ff];
       SPK_FIN(M.W2 + ff, S[M.v2 + ff], S[M.ds + ff] - bdy, (w2 >= 0 ? w2 : 0.0), D.vo[1] + i0 + ff);
     }
@@ -1271,7 +1272,7 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
     }
     for (int e = tid; e < f * ny; e += T) {  // y_i :423-429
       const int ff = e / ny, k = e - ff * ny;
-      SPK_Z(S[M.dy + e], S[M.W1 + e] - P.b[k] * S[M.W2 + ff]);
+      SPK_Z(S[M.dy + e], S[M.W1 + e] - spk_b(D, P, i0 + ff)[k] * S[M.W2 + ff]);
     }
     for (int ff = tid; ff < f; ff += T) SPK_Z(S[M.ds + ff], S[M.W2 + ff]);  // s_i :440-442
     for (int fc = tid; fc < fd; fc += T) {
@@ -1470,7 +1471,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
       off += D.cone_dim[c];
     }
   }
-  const double b_k = lane < ny ? P.b[lane] : 0.0;
+  const double b_k = lane < ny ? spk_b(D, P, i0)[lane] : 0.0;
   // ---------------------------------------------------------------- w = 2 zbar - z, delta = zbar - z (in place)
 #define SPK_WD3(w_, d_) { const double old_ = (w_), nb_ = (d_); (w_) = 2.0 * nb_ - old_; (d_) = nb_ - old_; }
 #pragma unroll

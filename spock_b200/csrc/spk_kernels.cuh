@@ -82,7 +82,7 @@ SPK_D double spk_Lt_entry(const SpkDims &D, const SpkPtrs &P, const double *__re
     const long idx = e - D.zo[4];
     const long i0 = idx / D.ny;
     const int k = (int)(idx - i0 * D.ny);
-    val = v[idx] - P.b[k] * v[D.vo[1] + i0];
+    val = v[idx] - spk_b(D, P, i0)[k] * v[D.vo[1] + i0];
   }
   return val;
 }
@@ -103,7 +103,7 @@ SPK_D double spk_L_entry(const SpkDims &D, const SpkPtrs &P, const double *__res
   } else if (e < D.vo[2]) {  // v2 :214-222
     const long i0 = e - D.vo[1];
     double dot_p = 0.0;
-    for (int k = 0; k < D.ny; ++k) dot_p += P.b[k] * z[D.zo[4] + i0 * D.ny + k];
+    for (int k = 0; k < D.ny; ++k) dot_p += spk_b(D, P, i0)[k] * z[D.zo[4] + i0 * D.ny + k];
     val = z[D.zo[2] + i0] - dot_p;
   } else if (e < D.vo[3]) {  // v3 :226-235
     const long idx = e - D.vo[2];
@@ -272,7 +272,7 @@ SPK_KERNEL void spk_k_s2(SpkDims D, SpkPtrs P, double *__restrict__ arg) {
   for (int k = 0; k < nls; ++k) outv[k] = 0.0;
   for (int m = 0; m < nls; ++m) {  // :717
     const double xm = in[m];
-    for (int k = 0; k < nls; ++k) outv[k] += P.ls[k + (long)m * nls] * xm;
+    for (int k = 0; k < nls; ++k) outv[k] += spk_ls(D, P, i0)[k + (long)m * nls] * xm;
   }
   for (int k = 0; k < ny; ++k) arg[D.zo[4] + i0 * ny + k] = outv[k];                  // :721
   for (int c = 0; c < d; ++c) arg[D.zo[2] + (long)d * i0 + 1 + c] = outv[ny + c];     // :723

@@ -1496,6 +1496,7 @@ static int check_problem(const spk_problem *p) {
     if (!p->comm_id) return fail(SPK_ERR_INVALID, "world_size > 1 needs comm_id (spk_comm_unique_id)");
     if (p->rank < 0 || p->rank >= p->world_size) return fail(SPK_ERR_INVALID, "rank out of range");
   }
+  if (p->n_rms < 0) return fail(SPK_ERR_INVALID, "n_rms must not be negative");
   if (p->n_devices > 1) {
     if (!p->devices) return fail(SPK_ERR_INVALID, "n_devices > 1 needs the devices array");
     if (p->world_size > 1) return fail(SPK_ERR_INVALID, "n_devices > 1 (one process) and world_size > 1 (one process per GPU) are exclusive");
@@ -1630,7 +1631,24 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
 
   std::string err;
   if (!spk_offline_factors(p->N, d, nx, nu, p->A, p->B, h->table, err)) return fail(SPK_ERR_INVALID, err);
-  if (!spk_kernel_projector(ny, d, p->E, p->F, h->ls_host, err)) return fail(SPK_ERR_INVALID, err);
+  // kernel projector (cpock.jl:71-81,125-128): one for all nodes, or one per non-leaf node with non-uniform risk measures
+  const long n_rms = p->n_rms > 1 ? p->n_rms : 1;
+  if (n_rms != 1 && n_rms != nnl) return fail(SPK_ERR_INVALID, "n_rms must be 1 (uniform risk measures) or n_non_leaf");
+  D.rms_per_node = n_rms > 1 ? 1 : 0;
+  {
+    const size_t nls2 = (size_t)D.nls * D.nls;
+    h->ls_host.resize(nls2 * n_rms);
+    std::vector<double> one;
+    const double *prevE = nullptr, *prevF = nullptr;
+    for (long i = 0; i < n_rms; ++i) {
+      const double *Ei = p->E + (size_t)i * ny * d, *Fi = p->F + (size_t)i * ny * d;
+      // consecutive nodes often share (E, F): reuse the projector instead of recomputing it
+      if (!(prevE && memcmp(prevE, Ei, sizeof(double) * ny * d) == 0 && memcmp(prevF, Fi, sizeof(double) * ny * d) == 0))
+        if (!spk_kernel_projector(ny, d, Ei, Fi, one, err)) return fail(SPK_ERR_INVALID, err);
+      std::copy(one.begin(), one.end(), h->ls_host.begin() + nls2 * i);
+      prevE = Ei; prevF = Fi;
+    }
+  }
   D.abk_stride = h->table.abk_stride; D.k_stride = h->table.k_stride; D.r_stride = h->table.r_stride;
 
   // ---- problem data
@@ -1647,7 +1665,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(upload(h, &tmp, p->sqrtQ, p->n_sqrtQ * qsz)); h->P.sqrtQ = tmp;
   SPK_TRY(upload(h, &tmp, p->sqrtR, p->n_sqrtQ * rsz)); h->P.sqrtR = tmp;
   SPK_TRY(upload(h, &tmp, p->sqrtQN, p->n_sqrtQN * qsz)); h->P.sqrtQN = tmp;
-  SPK_TRY(upload(h, &tmp, p->b, ny)); h->P.b = tmp;
+  SPK_TRY(upload(h, &tmp, p->b, n_rms * ny)); h->P.b = tmp;
   SPK_TRY(upload(h, &tmp, h->ls_host.data(), (long)h->ls_host.size())); h->P.ls = tmp;
   SPK_TRY(dev_alloc(h, &h->x0, nx)); h->P.x0 = h->x0;
 
@@ -2137,7 +2155,10 @@ int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, dou
     if (K) std::copy(T.K.begin() + t * T.k_stride, T.K.begin() + t * T.k_stride + (size_t)D.nu * D.nx, K);
     if (Rinv) std::copy(T.Rinv.begin() + t * T.r_stride, T.Rinv.begin() + t * T.r_stride + (size_t)D.nu * D.nu, Rinv);
   }
-  if (ls) std::copy(h->ls_host.begin(), h->ls_host.end(), ls);
+  if (ls) {
+    const size_t nls2 = (size_t)D.nls * D.nls, off = (D.rms_per_node && i0 < D.nnl) ? nls2 * (size_t)i0 : 0;
+    std::copy(h->ls_host.begin() + off, h->ls_host.begin() + off + nls2, ls);
+  }
   return SPK_OK;
 }
 

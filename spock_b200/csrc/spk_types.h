@@ -18,6 +18,7 @@ struct SpkDims {
   int cone_type[SPK_MAX_CONES], cone_dim[SPK_MAX_CONES];
   double x_min, x_max, u_min, u_max;
   int cost_dense, n_sqrtQ, n_sqrtQN;
+  int rms_per_node;        // 1: b (ny) and the kernel projector ls (nls*nls) differ per non-leaf node (get_nonuniform_rms_avar_v2)
   int per_node;            // factor mode: 1 = one factor slot per node, 0 = per (stage, mode)
   long abk_stride;         // doubles per ABK slot (nx*nx rounded up to an even count: 16-byte aligned slots)
   long k_stride, r_stride; // doubles per K/Kt/G slot and per Rinv slot
@@ -78,5 +79,11 @@ SPK_HD long long spk_bits_nn(double a) {
 #endif
 }
 SPK_HD double spk_max_nn(double a, double b) { return spk_bits_nn(a) >= spk_bits_nn(b) ? a : b; }
+
+// risk vector b_i and kernel projector ls_matrix[i] of non-leaf node i0 (uniform risk measures: one copy for all nodes)
+SPK_HD const double *spk_b(const SpkDims &D, const SpkPtrs &P, long i0) { return D.rms_per_node ? P.b + i0 * D.ny : P.b; }
+SPK_HD const double *spk_ls(const SpkDims &D, const SpkPtrs &P, long i0) {
+  return D.rms_per_node ? P.ls + i0 * (long)D.nls * D.nls : P.ls;
+}
 
 SPK_HD double spk_clip(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }  // constraints.jl:28-30

@@ -130,6 +130,22 @@ def get_uniform_rms_avar_v2(p, alpha, d, N) -> UniformRiskMeasures:
     return get_uniform_rms_v2(E, F, b, ConvexCone([Nonnegatives(2 * d), Zeros(1)]), d, N)
 
 
+def get_nonuniform_rms_avar_v2(d, N, rng=None):
+    """risk_measures.jl:127-136: a different AV@R at every non-leaf node -- E = [a_i I; -I; 1'] with a_i = rand(),
+    b = [p_i; 0; 1] with p_i = rand_probvec2(d).  The reference draws from the unseeded global RNG; here `rng` is a
+    numpy Generator (default_rng(0) if None) so that the problem is reproducible."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    out = []
+    for _ in range((d ** (N - 1) - 1) // (d - 1)):
+        a = float(rng.random())
+        p = rng.random(d)
+        p = p / p.sum()
+        E = np.vstack([a * np.eye(d), -np.eye(d), np.ones((1, d))])
+        out.append(RiskMeasure(E, np.zeros((2 * d + 1, d)), np.concatenate([p, np.zeros(d), [1.0]]),
+                               ConvexCone([Nonnegatives(2 * d), Zeros(1)])))
+    return out
+
+
 def get_uniform_rms_tv_v2(p, r, d, N) -> UniformRiskMeasures:
     """risk_measures.jl:138-147 (total-variation ambiguity set)."""
     E = np.vstack([0.5 * np.eye(d), -0.5 * np.eye(d), np.zeros((d, d))])
@@ -211,6 +227,8 @@ class FlatProblem:
     # kept for host-side use (not passed to C)
     E2d: np.ndarray = field(repr=False, default=None)
     F2d: np.ndarray = field(repr=False, default=None)
+    n_rms: int = 1                                      # 1 = uniform risk measures, n_non_leaf = one (E, F, b) per node
+    rms_list: list = field(repr=False, default=None)    # the per-node RiskMeasure objects when n_rms > 1
 
     @property
     def n(self) -> int:
@@ -278,10 +296,15 @@ def flatten_problem(scen_tree: ScenarioTree, cost: Cost, dynamics: Dynamics, rms
         raise ValueError("number of dynamics modes must equal the branching factor")
     n, nl = scen_tree.n, scen_tree.n_leaf_nodes
     rm = rms[0]
-    ny = len(rm.b)  # implicit_l.jl:20: uniform risk measures assumed
-    for k in (len(rms) // 2, len(rms) - 1):
-        if rms[k] is not rm and not (np.array_equal(rms[k].E, rm.E) and np.array_equal(rms[k].b, rm.b)):
-            raise NotImplementedError("non-uniform risk measures are not supported yet")
+    ny = len(rm.b)  # implicit_l.jl:20: one ny for all nodes, like the reference
+    uniform = isinstance(rms, UniformRiskMeasures) or all(
+        r is rm or (np.array_equal(r.E, rm.E) and np.array_equal(r.F, rm.F) and np.array_equal(r.b, rm.b)) for r in rms)
+    if not uniform:
+        if len(rms) != scen_tree.n_non_leaf_nodes:
+            raise ValueError("one risk measure per non-leaf node expected")
+        for r in rms:
+            if len(r.b) != ny or [(c.type_id, c.dimension) for c in r.K.subcones] != [(c.type_id, c.dimension) for c in rm.K.subcones]:
+                raise NotImplementedError("risk measures must share ny and the sub-cone list (implicit_l.jl:14,19)")
     E = np.asarray(rm.E, float)
     F = np.asarray(rm.F, float)
     if E.shape != (ny, d) or F.shape[0] != ny:
@@ -311,7 +334,11 @@ def flatten_problem(scen_tree: ScenarioTree, cost: Cost, dynamics: Dynamics, rms
         cost_dense=int(dense),
         n_sqrtQ=len(sQ), sqrtQ=pack(sQ, dq, nx), sqrtR=pack(sR, dr, nu),
         n_sqrtQN=len(sQN), sqrtQN=pack(sQN, dqn, nx),
-        E=_colmajor(E), F=_colmajor(F), b=np.asarray(rm.b, float).copy(),
+        E=_colmajor(E) if uniform else np.concatenate([_colmajor(np.asarray(r.E, float)) for r in rms]),
+        F=_colmajor(F) if uniform else np.concatenate([_colmajor(np.asarray(r.F, float)) for r in rms]),
+        b=np.asarray(rm.b, float).copy() if uniform else np.concatenate([np.asarray(r.b, float) for r in rms]),
+        n_rms=1 if uniform else len(rms),
+        rms_list=None if uniform else list(rms),
         cone_type=np.array([c.type_id for c in rm.K.subcones], dtype=np.int32),
         cone_dim=np.array([c.dimension for c in rm.K.subcones], dtype=np.int32),
         x_min=float(constraints.x_min), x_max=float(constraints.x_max),

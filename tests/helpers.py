@@ -42,7 +42,18 @@ def _per_node_cost_specs():
     return scen_tree, cost, dynamics, rms, constraints
 
 
+def _nonuniform_rms_specs(N=5, d=2, nx=4, nu=3):
+    """A different AV@R (own alpha and reference probabilities) at every non-leaf node: get_nonuniform_rms_avar_v2
+    (risk_measures.jl:127-136) -- per-node b (implicit_l.jl:219,427) and per-node kernel projector (cpock.jl:71-81,125-128)."""
+    from spock_b200.problem import get_nonuniform_rms_avar_v2
+
+    scen_tree, cost, dynamics, _, constraints = get_random_system_specs(N, d, nx, nu)
+    return scen_tree, cost, dynamics, get_nonuniform_rms_avar_v2(d, N, np.random.default_rng(42)), constraints
+
+
 SMALL_PROBLEMS = {
+    "nonuniform_avar_N5_d2_nx4": _nonuniform_rms_specs,
+    "nonuniform_avar_N4_d3_nx3": lambda: _nonuniform_rms_specs(4, 3, 3, 2),
     "pernode_cost_tv_N4_d2_nx3": _per_node_cost_specs,
     "fixture_N3_d2": lambda: get_test_fixture_specs(),
     "heat_N7_d2_nx5": lambda: get_server_heat_specs(7, 5, 2),

@@ -177,3 +177,18 @@ def test_batched_independent_problems(cuda_lib):
     from tests.helpers import check_solve_batch, flat_of
     names = ["heat_N7_d2_nx5", "random_N5_d2_nx6_nu3", "heat_N4_d3_nx3", "heat_N7_d2_nx5", "l2ball_N4_d3_nx3"]
     check_solve_batch(cuda_lib, [flat_of(n) for n in names], [CP, CP, CP, SP, SP])
+
+
+@pytest.mark.parametrize("nx,nu,d,N", [(10, 10, 2, 8), (50, 20, 2, 7), (10, 10, 4, 5)])
+def test_nonuniform_risk_measures_on_specialised_shapes(cuda_lib, nx, nu, d, N):
+    """get_nonuniform_rms_avar_v2 (risk_measures.jl:127-136): per-node b and per-node kernel projector through the
+    shape-specialised kernels (spk_k_s2t<ny,d>, spk_k_dual3) and the modular operators, against the oracle."""
+    from spock_b200.problem import get_nonuniform_rms_avar_v2
+    from tests.helpers import check_operators
+
+    scen_tree, cost, dynamics, _, constraints = get_random_system_specs(N, d, nx, nu)
+    flat = flatten_problem(scen_tree, cost, dynamics, get_nonuniform_rms_avar_v2(d, N, np.random.default_rng(7)), constraints)
+    assert flat.n_rms == flat.n_non_leaf
+    check_operators(cuda_lib, flat, 0, seed=2)
+    _run_pair(cuda_lib, flat, CP, 30)
+    _run_pair(cuda_lib, flat, SP, 8)

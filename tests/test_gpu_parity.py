@@ -38,6 +38,7 @@ def test_operators_medium(cuda_lib, spec):
     ("l2ball_N4_d3_nx3", CP, 200), ("random_N3_d4_nx35_nu17", CP, 100), ("pernode_cost_tv_N4_d2_nx3", CP, 150),
     ("pernode_cost_tv_N4_d2_nx3", SP, 15),
     ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
+    ("nonuniform_avar_N5_d2_nx4", CP, 150), ("nonuniform_avar_N4_d3_nx3", CP, 100), ("nonuniform_avar_N5_d2_nx4", SP, 15),
 ])
 @pytest.mark.parametrize("factor_mode", [0, 1])
 def test_k_step_iterates(cuda_lib, name, alg, K, factor_mode):

@@ -37,6 +37,7 @@ def test_offline_factors(emu_lib, name):
     ("fixture_N3_d2", CP, 200), ("heat_N7_d2_nx5", CP, 300), ("heat_N4_d3_nx3", CP, 200),
     ("l2ball_N4_d3_nx3", CP, 200), ("pernode_cost_tv_N4_d2_nx3", CP, 150), ("pernode_cost_tv_N4_d2_nx3", SP, 15),
     ("heat_N7_d2_nx5", SP, 30), ("fixture_N3_d2", SP, 20), ("l2ball_N4_d3_nx3", SP, 15),
+    ("nonuniform_avar_N5_d2_nx4", CP, 150), ("nonuniform_avar_N4_d3_nx3", CP, 100), ("nonuniform_avar_N5_d2_nx4", SP, 15),
 ])
 @pytest.mark.parametrize("host_loop", ["0", "1"])
 def test_k_step_iterates(emu_lib, name, alg, K, host_loop, monkeypatch):
