@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libspock_b200.so")
+# (SPOCK_B200_LIB: development builds of the same library under csrc/_variants/, used for A/B timing of kernel variants)
+LIB_PATH = os.environ.get("SPOCK_B200_LIB") or os.path.join(HERE, "csrc", "libspock_b200.so")
 
 SPK_OK = 0
 CP, SP = 1, 2

@@ -270,7 +270,8 @@ SPK_D int spk_child_mode_dev(int d, int c) {  // mode of child ordinal c: (j0 + 
 SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
   const long SA = spk_slices(T, D.nx), SB = spk_slices(T, D.nu), nw = (T + 31) / 32;
   const long raw = 2L * D.nu + 2L * D.nx + (long)D.d * D.nu + 4L * D.d * D.nx;  // zu, zx, v7, v4c, v3c, qraw, v14c, v11c
-  return 2 + (long)D.d * D.abk_stride + 2 * D.k_stride + D.r_stride + (long)D.d * D.nx + D.nu + D.nx + SA * D.nx + SB * D.nu +
+  // (partial sums of the ABK' mat-vec: up to 2 SA + 1 slices -- the row-pair mapping of the large shapes slices finer)
+  return 2 + (long)D.d * D.abk_stride + 2 * D.k_stride + D.r_stride + (long)D.d * D.nx + D.nu + D.nx + (2 * SA + 1) * D.nx + SB * D.nu +
          nw * 3L * D.nu + raw + 4;
 }
 
@@ -289,7 +290,7 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
   const long count = A.p_cnt, first0 = spk_level_first0(d, t) + A.p_lo;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   double *mABKt = smem + 2, *mG = mABKt + (long)d * D.abk_stride, *mKt = mG + D.k_stride, *mRinv = mKt + D.k_stride;
-  double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *partA = tx + nx, *partB = partA + (long)SA * nx,
+  double *qc = mRinv + D.r_stride, *tu = qc + (long)d * nx, *tx = tu + nu, *partA = tx + nx, *partB = partA + (long)(2 * SA + 1) * nx,
          *wrhs = partB + (long)SB * nu + (long)warp * 3 * nu, *wdv = wrhs + nu, *wdmt = wdv + nu;
   // raw staging of the next family's vector entries (asynchronous copies)
   double *rzu = partB + (long)SB * nu + (long)((T + WL - 1) / WL) * 3 * nu, *rzx = rzu + nu, *rv7 = rzx + nx, *rv4 = rv7 + nx + nu,
@@ -338,6 +339,16 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
   // soon as it is consumed instead of after the whole family (see spk_k_fwd_s1).
   constexpr bool SPLIT = !SPK_EMU && NX_ > 0 && D_ <= 4 && NX_ * NX_ * 8 >= 16 * 1024 && NX_ * spk_cslices(T_, NX_) <= T_;
   uint64_t *cbar = reinterpret_cast<uint64_t *>(rv11 + (long)d * nx);  // SPLIT: D_ barriers in the 4 spare doubles behind the staging
+  // PAIR: row-pair mapping of the ABK' mat-vec (even nx: rows 2p, 2p+1 of a column are one aligned 16-byte word)
+#ifndef SPK_NO_PAIR
+  constexpr bool PAIR = SPLIT && NX_ % 2 == 0;
+#else
+  constexpr bool PAIR = false;
+#endif
+  constexpr int NP = NX_ > 0 ? NX_ / 2 : 1;
+  constexpr int SA2 = PAIR ? (T_ / NP < NX_ ? T_ / NP : NX_) : 1, PER2 = PAIR ? (NX_ + SA2 - 1) / SA2 : 1;
+  const int pair_p = tid % NP, pair_sl = tid / NP, pair_m0 = pair_sl * PER2;
+  const bool pair_on = PAIR && tid < NP * SA2;
   if constexpr (SPLIT) {
     if (tid == 0)
       for (int c = 0; c < D_; ++c) spk_mbar_init(cbar + c, 1);
@@ -412,7 +423,41 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
         acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_child_mode_dev(d, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
       partB[o] = acc;
     }
-    if constexpr (SPLIT) {  // child by child; one work item per thread (nx * SA <= T)
+    if constexpr (PAIR) {
+      // child by child, TWO output rows per thread: one 16-byte shared-memory read feeds two FMAs and the q entry is read
+      // once for both (half the LDS instructions of the one-row mapping, two independent accumulator chains)
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < D_; ++c) {
+        if (fresh) {
+          spk_mbar_wait(cbar + c, (cph >> c) & 1u);
+          cph ^= 1u << c;
+        }
+        if (pair_on) {
+          const double *Mp = mABKt + (long)c * D.abk_stride + (long)pair_m0 * NX_ + 2 * pair_p;
+          const double *xq = qc + c * NX_ + pair_m0;
+#pragma unroll
+          for (int j = 0; j < PER2; ++j) {
+            if (pair_m0 + j < NX_) {
+              const double2 mm = *reinterpret_cast<const double2 *>(Mp + j * NX_);
+              const double xv = xq[j];
+              a0 += mm.x * xv;
+              a1 += mm.y * xv;
+            }
+          }
+          if (c == D_ - 1) {
+            partA[pair_sl * NX_ + 2 * pair_p] = a0;
+            partA[pair_sl * NX_ + 2 * pair_p + 1] = a1;
+          }
+        }
+        SPK_SYNCTHREADS();  // ABK_c' is consumed (after the last child: partA, partB complete)
+        if (more && tid == 0) fetch_child(i0 + gridDim.x, c);
+      }
+      if (fresh) {
+        spk_mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+    } else if constexpr (SPLIT) {  // child by child; one work item per thread (nx * SA <= T)
       const bool activeA = tid < NX_ * cSA;
       double accA = 0.0;
 #pragma unroll
@@ -460,9 +505,29 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
     }
     SPK_SYNCWARP();
     // ---- P4: + G d + K'(d - ubar) (:610-632)
-    for (int o = tid; o < nx * SA; o += T) {
-      const SpkItem it = (o == tid) ? itA : spk_make_item(o, nx, SA, nx, nu);
-      partA[o] += spk_dot_any<PER_AU>(mG + it.r, nx, wdv, it.k0, it.k1, nu) + spk_dot_any<PER_AU>(mKt + it.r, nx, wdmt, it.k0, it.k1, nu);
+    if constexpr (PAIR) {  // the same row-pair mapping: slice pair_sl of the nu columns of G and K'
+      constexpr int PERU2 = (NU_ + SA2 - 1) / SA2;
+      if (pair_on) {
+        const int k0 = pair_sl * PERU2;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < PERU2; ++j) {
+          if (k0 + j < NU_) {
+            const double2 g2 = *reinterpret_cast<const double2 *>(mG + (long)(k0 + j) * NX_ + 2 * pair_p);
+            const double2 k2 = *reinterpret_cast<const double2 *>(mKt + (long)(k0 + j) * NX_ + 2 * pair_p);
+            const double dv_ = wdv[k0 + j], dm_ = wdmt[k0 + j];
+            a0 += g2.x * dv_ + k2.x * dm_;
+            a1 += g2.y * dv_ + k2.y * dm_;
+          }
+        }
+        partA[pair_sl * NX_ + 2 * pair_p] += a0;
+        partA[pair_sl * NX_ + 2 * pair_p + 1] += a1;
+      }
+    } else {
+      for (int o = tid; o < nx * SA; o += T) {
+        const SpkItem it = (o == tid) ? itA : spk_make_item(o, nx, SA, nx, nu);
+        partA[o] += spk_dot_any<PER_AU>(mG + it.r, nx, wdv, it.k0, it.k1, nu) + spk_dot_any<PER_AU>(mKt + it.r, nx, wdmt, it.k0, it.k1, nu);
+      }
     }
     SPK_SYNCTHREADS();
     // the matrices are consumed: start the next family's transfer before finishing this one
@@ -476,7 +541,7 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
     // ---- P5: q_i (:634-636)
     for (int r = tid; r < nx; r += T) {
       double acc = 0.0;
-      for (int sl = 0; sl < SA; ++sl) acc += partA[sl * nx + r];
+      for (int sl = 0; sl < (PAIR ? SA2 : SA); ++sl) acc += partA[sl * nx + r];
       A.q[i0 * nx + r] = acc - tx[r];
     }
     SPK_SYNCTHREADS();  // work buffers are reused by the next family
@@ -545,6 +610,7 @@ SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
   constexpr bool SPLIT = !SPK_EMU && NX_ > 0 && cS == 2 && (HC * NX_) % 2 == 0 && (HC * NU_) % 2 == 0 &&
                          ((NX_ - HC) * NX_) % 2 == 0 && ((NX_ - HC) * NU_) % 2 == 0 &&
                          NX_ * NX_ * 8 >= 16 * 1024;  // measured: no gain (slightly slower) with a few KB per family
+  // (a row-pair / 16-byte-read mapping like the backward kernel's was measured neutral here: this kernel is DRAM-bound)
   if (SPLIT && tid == 0) spk_mbar_init(bar + 1, 1);
   SPK_SYNCTHREADS();
   uint32_t phase = 0;
