@@ -57,6 +57,7 @@ extern thread_local std::vector<unsigned char> spk_emu_smem;
 
 typedef int spk_stream_t;
 typedef double spk_event_t;  // wall-clock ms
+struct double2 { double x, y; };
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
