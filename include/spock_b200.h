@@ -134,6 +134,9 @@ int spk_get_iterate(spk_handle *h, double *z, double *v);
 
 /* One operator application on host vectors (lengths as listed at spk_op).  `scalar` is gamma / sigma. */
 int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double scalar);
+/* spock_mul!(model, C, trans, B, alpha, beta), implicit_l.jl:451-481: C <- alpha * op(L) B + beta * C on host vectors;
+ * trans != 0: op(L) = L' (B has nv entries, C nz), else L (B nz, C nv). */
+int spk_mul(spk_handle *h, int32_t trans, const double *B, double alpha, double beta, double *C);
 /* spock_dot(model, a_z, a_v, b_z, b_v, gamma, sigma), implicit_l.jl:485 */
 int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b_z, const double *b_v, double gamma,
             double sigma, double *out);

@@ -220,8 +220,10 @@ function L_transpose!(model :: MODEL_B200, z :: AbstractArray{TF, 1}, v :: Abstr
   out = zeros(model.solver_state.nz); spk_apply!(model, 1, Vector{Float64}(v), out); copyto!(z, out)
 end
 function spock_mul!(model :: MODEL_B200, C :: AbstractArray{TF, 1}, trans :: Bool, B :: AbstractArray{TF, 1}, alpha :: TF, beta :: TF) where {TF <: Real}   # :451-481
-  out = zeros(length(C)); spk_apply!(model, trans ? 1 : 0, Vector{Float64}(B), out)
-  @. C = alpha * out + beta * C
+  Cv = Vector{Float64}(C)
+  spk_check(ccall((:spk_mul, SPK_LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Float64, Float64, Ptr{Float64}),
+                  model.solver_state_internal.handle, trans ? 1 : 0, Vector{Float64}(B), alpha, beta, Cv))
+  copyto!(C, Cv)
 end
 function spock_dot(model :: MODEL_B200, a_z, a_v, b_z, b_v, gamma, sigma)                                         # :485-516
   out = Ref{Float64}(0.0)

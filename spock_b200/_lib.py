@@ -25,7 +25,7 @@ EXPORTS = [
     "spk_set_x0", "spk_set_iterate", "spk_get_iterate", "spk_apply", "spk_dot", "spk_get_factors", "spk_step",
     "spk_solve", "spk_get_residuals", "spk_profile", "spk_profile_get", "spk_launch_count", "spk_device_bytes",
     "spk_comm_unique_id", "spk_owned_ranges", "spk_state_size", "spk_get_state", "spk_set_state",
-    "spk_estimate_L_norm", "spk_set_L_norm", "spk_gather_iterate", "spk_set_sp_options", "spk_shift_iterate", "spk_solve_batch",
+    "spk_estimate_L_norm", "spk_set_L_norm", "spk_gather_iterate", "spk_set_sp_options", "spk_shift_iterate", "spk_solve_batch", "spk_mul",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -77,6 +77,7 @@ def bind(path: str) -> C.CDLL:
     lib.spk_set_iterate.argtypes = [vp, _dp, _dp]
     lib.spk_get_iterate.argtypes = [vp, _dp, _dp]
     lib.spk_apply.argtypes = [vp, C.c_int32, _dp, _dp, C.c_double]
+    lib.spk_mul.argtypes = [vp, C.c_int32, _dp, C.c_double, C.c_double, _dp]
     lib.spk_dot.argtypes = [vp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
     lib.spk_get_factors.argtypes = [vp, C.c_int64, _dp, _dp, _dp, _dp, _dp]
     lib.spk_step.argtypes = [vp, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_float)]

@@ -2114,6 +2114,24 @@ int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double s
   }
 }
 
+// spock_mul!(model, C, trans, B, alpha, beta): C <- alpha * op(L) B + beta * C (implicit_l.jl:451-481)
+int spk_mul(spk_handle *h, int32_t trans, const double *B, double alpha, double beta, double *C) {
+  if (!h || !B || !C) return fail(SPK_ERR_INVALID, "NULL argument");
+  if (h->group) return group_first(h, [=](spk_handle *s) { return spk_mul(s, trans, B, alpha, beta, C); });
+  const long nz = h->D.nz, nv = h->D.nv;
+  double *tz = h->zvbar, *tv = h->zvbar + nz, *cz = h->xi12, *cv = h->xi12 + nz;  // scratch (see spk_apply)
+  if (trans) {  // C (nz) <- alpha L'B + beta C, B (nv)
+    SPK_TRY(rt_h2d(tv, B, sizeof(double) * nv, h->stream));
+    SPK_TRY(rt_h2d(cz, C, sizeof(double) * nz, h->stream));
+    SPK_TRY(op_Lt(h, tv, alpha, beta, cz, cz));
+    return rt_d2h(C, cz, sizeof(double) * nz, h->stream);
+  }
+  SPK_TRY(rt_h2d(tz, B, sizeof(double) * nz, h->stream));
+  SPK_TRY(rt_h2d(cv, C, sizeof(double) * nv, h->stream));
+  SPK_TRY(op_L(h, tz, alpha, beta, cv, cv));
+  return rt_d2h(C, cv, sizeof(double) * nv, h->stream);
+}
+
 int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b_z, const double *b_v, double gamma,
             double sigma, double *out) {
   if (!h || !a_z || !a_v || !b_z || !b_v || !out) return fail(SPK_ERR_INVALID, "NULL argument");

@@ -133,6 +133,13 @@ class Handle:
     def Lt(self, v):
         return self.apply(OP_LT, v)
 
+    def mul(self, C_vec, trans: bool, B, alpha: float, beta: float):
+        """spock_mul!: C <- alpha * op(L) B + beta * C, in place on the numpy vector C_vec."""
+        B = _f64(B)
+        if B.shape != ((self.nv,) if trans else (self.nz,)) or C_vec.shape != ((self.nz,) if trans else (self.nv,)):
+            raise ValueError("z or v has the wrong length")
+        check(self.lib, self.lib.spk_mul(self._h, int(bool(trans)), dptr(B), float(alpha), float(beta), dptr(C_vec)))
+
     def prox_f(self, arg, gamma):
         return self.apply(OP_PROX_F, arg, gamma)
 

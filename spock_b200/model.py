@@ -155,7 +155,7 @@ def L_transpose_(model, z, v):
 
 
 def spock_mul_(model, C, trans: bool, B, alpha: float, beta: float):
-    C[:] = alpha * (model.handle.Lt(B) if trans else model.handle.L(B)) + beta * C
+    model.handle.mul(C, trans, B, alpha, beta)
 
 
 def spock_dot(model, a_z, a_v, b_z, b_v, gamma, sigma):

@@ -92,6 +92,11 @@ def check_operators(lib, flat, factor_mode, seed=0, tol=1e-12):
         for g in (0.1, 0.313):
             assert relerr(h.prox_f(z, g), o.prox_f(z, g)) <= tol
             assert relerr(h.prox_h_conj(v, g), o.prox_h_conj(v, g)) <= tol
+        for trans, Bv, Cv in ((True, v, z), (False, z, v)):  # spock_mul! with alpha, beta (implicit_l.jl:451-481)
+            got = np.array(Cv, copy=True)
+            h.mul(got, trans, Bv, -0.7, 1.3)
+            want = -0.7 * (o.Lt(Bv) if trans else o.L(Bv)) + 1.3 * Cv
+            assert relerr(got, want) <= tol
         a, b = h.dot(z, v, 2 * z, -v, 0.3, 0.2), o.dot(z, v, 2 * z, -v, 0.3, 0.2)
         assert abs(a - b) <= 1e-11 * max(1.0, abs(b))
     # adjointness <Lz, v> = <z, L'v>
