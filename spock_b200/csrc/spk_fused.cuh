@@ -1437,7 +1437,11 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   if (!valid) f = fam_cnt - 1;
   // fam_lo >= 0: families fam_lo .. fam_lo + fam_cnt - 1; fam_lo < 0: flat owned-family indices (-1 - fam_lo) + f over the
   // rank's owned ranges (subtree partition: one launch covers the slices of all levels)
+#ifndef SPK_DUAL3_NO_FLAT
   const long i0 = fam_lo >= 0 ? fam_lo + f : spk_owned_family(A, (-1 - fam_lo) + f);
+#else
+  const long i0 = fam_lo + f;
+#endif
   const long cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
   double my_xi1 = 0.0, my_xi2 = 0.0, my_pn = 0.0;
 #define SPK_XON(r) ((NX % G == 0) || (r) < RX - 1 || lane + G * (r) < NX)

@@ -61,5 +61,33 @@ def report(path):
             print(f"{w:80s} {vals[idx[w]]:>16s} {units[idx[w]]}")
 
 
+def traffic(path, workload, factor_mode, launches_scale, out_json, how):
+    """DRAM bytes (read + write) of the captured launch -> profiles/*traffic*.json, the file bench.py reads `roofline.traffic`
+    from.  launches_scale: factor from the captured launch to all launches of that kernel in one pass."""
+    import json
+    import os
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def val(name):
+        v, u = float(vals[idx[name]].replace(",", "")), units[idx[name]].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1)
+    r, w = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    rec = {"workload": workload, "factor_mode": factor_mode, "kernel": vals[idx["Kernel Name"]].split("(")[0],
+           "dram_bytes_read_launch": r, "dram_bytes_write_launch": w, "launch_to_pass_scale": float(launches_scale),
+           "dram_bytes_per_pass": (r + w) * float(launches_scale), "commit": commit, "ncu_report": os.path.basename(path), "how": how}
+    recs = json.load(open(out_json)) if os.path.exists(out_json) else []
+    recs = [x for x in recs if not (x["workload"] == workload and x["factor_mode"] == factor_mode)] + [rec]
+    json.dump(recs, open(out_json, "w"), indent=1)
+    print(json.dumps(rec))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:8])
+    else:
+        {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
