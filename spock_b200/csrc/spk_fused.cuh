@@ -1413,7 +1413,10 @@ SPK_D double spk_warp_max_nonneg(double v) {
 }
 
 // PN: also accumulate <r, P r> (SuperMann only; Chambolle-Pock needs just the residual maxima)
-template <int NX, int NU, int DD, bool LEAVES, bool UC, bool PN>
+// FLAT (subtree partition only): the launch covers flat owned-family indices over the rank's owned ranges instead of one
+// contiguous node range.  A template parameter, not a run-time branch: merely having the range-table lookup in the kernel
+// cost the single-GPU instantiation 9 % (0.951 -> 1.038 ms per pass at config 3, same-box A/B).
+template <int NX, int NU, int DD, bool LEAVES, bool UC, bool PN, bool FLAT = false>
 __launch_bounds__(128, SPK_DUAL3_MINB)
 __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, long fam_cnt) {
   if (A.gate && *A.gate) return;
@@ -1435,13 +1438,8 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   long f = ((long)blockIdx.x * wpb + warp) * FPW + wlane / G;
   const bool valid = f < fam_cnt;
   if (!valid) f = fam_cnt - 1;
-  // fam_lo >= 0: families fam_lo .. fam_lo + fam_cnt - 1; fam_lo < 0: flat owned-family indices (-1 - fam_lo) + f over the
-  // rank's owned ranges (subtree partition: one launch covers the slices of all levels)
-#ifndef SPK_DUAL3_NO_FLAT
-  const long i0 = fam_lo >= 0 ? fam_lo + f : spk_owned_family(A, (-1 - fam_lo) + f);
-#else
-  const long i0 = fam_lo + f;
-#endif
+  // FLAT: fam_lo = first flat owned-family index of the launch
+  const long i0 = FLAT ? spk_owned_family(A, fam_lo + f) : fam_lo + f;
   const long cfirst = (long)DD * i0 + 1, lfirst = cfirst - D.nnl;
   double my_xi1 = 0.0, my_xi2 = 0.0, my_pn = 0.0;
 #define SPK_XON(r) ((NX % G == 0) || (r) < RX - 1 || lane + G * (r) < NX)

@@ -14,6 +14,8 @@ extern "C" const SpkShapeEntry *SPK_CAT(spk_shape_entry_, SPK_SHAPE_NX, SPK_SHAP
 #define SPK_D3(LV, UC) {spk_k_dual3<NX, NU, DD, LV, UC, false>, spk_k_dual3<NX, NU, DD, LV, UC, true>}
       {{SPK_D3(false, false), SPK_D3(false, true)}, {SPK_D3(true, false), SPK_D3(true, true)}},
 #undef SPK_D3
+      {{spk_k_dual3<NX, NU, DD, false, false, false, true>, spk_k_dual3<NX, NU, DD, false, false, true, true>},
+       {spk_k_dual3<NX, NU, DD, false, true, false, true>, spk_k_dual3<NX, NU, DD, false, true, true, true>}},
       {spk_k_bwd_mm<NX, NU, DD, false>, spk_k_bwd_mm<NX, NU, DD, true>}, spk_k_fwd_mm<NX, NU, DD>, spk_k_top_mm<NX, NU, DD>,
       spk_k_bwd_top<NX, NU, DD, SPK_SHAPE_TB>, spk_k_fwd_top<NX, NU, DD, SPK_SHAPE_TF>};
   return &e;

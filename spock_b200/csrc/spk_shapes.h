@@ -14,6 +14,7 @@ struct SpkShapeEntry {
   spk_fused_kernel_t bwd, fwd, dual;
   spk_dual2_kernel_t dual2;
   spk_dual3_kernel_t dual3[2][2][2];  // [children are leaves][uniform cost diagonals][with <r,Pr>]
+  spk_dual3_kernel_t dual3_flat[2][2];  // non-leaf children, flat owned-family indices (subtree partition): [uniform cost][with <r,Pr>]
   spk_mm_kernel_t bwd_mm[2], fwd_mm;  // per-stage factors on the fp64 tensor pipe; bwd_mm[children are leaves]
   spk_mm_top_kernel_t top_mm;         // levels with <= 64 families, both sweeps, one CTA
   spk_top_kernel_t bwd_top, fwd_top;  // all narrow levels of a sweep in one launch (grid barrier between levels)

@@ -183,6 +183,7 @@ struct spk_handle {
   unsigned *d_topbar = nullptr;
   void (*k_dual2)(SpkDims, SpkPtrs, SpkFusedArgs, int, long, long) = nullptr;
   void (*k_dual3[2][2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {{nullptr, nullptr}, {nullptr, nullptr}};  // [children are leaves][with <r,Pr>]
+  void (*k_dual3_flat[2])(SpkDims, SpkPtrs, SpkFusedArgs, long, long) = {nullptr, nullptr};  // flat owned-family indices, [with <r,Pr>]
   int occ_dual3 = 4;
   // per-stage factors on the fp64 tensor pipe (spk_mm.cuh)
   bool use_mm = false, mm_vec2 = false;
@@ -598,6 +599,7 @@ static int fused_setup(spk_handle *h) {
         if (!D.cost_dense && D.ny <= spk_dual3_group(D.nx, D.nu, D.d) && D.d <= 32 && !(e3 && e3[0] == '1') && (uc || (D.n_sqrtQ > 1 && D.n_sqrtQN > 1))) {
           for (int lv = 0; lv < 2; ++lv)
             for (int pn = 0; pn < 2; ++pn) h->k_dual3[lv][pn] = e.dual3[lv][uc ? 1 : 0][pn];
+          for (int pn = 0; pn < 2; ++pn) h->k_dual3_flat[pn] = e.dual3_flat[uc ? 1 : 0][pn];
         }
         const char *emm = getenv("SPK_NO_MM");
         if (!D.per_node && !D.cost_dense && !(emm && emm[0] == '1')) {
@@ -943,7 +945,7 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
   }
   long pn_parts = owned;  // number of <r,Pr> partials in d_pnorm
 #ifndef SPK_HOST_EMU
-  if (h->use_dual2 && h->world > 1 && h->k_dual3[0][0] && h->k_dual3[1][0]) {
+  if (h->use_dual2 && h->world > 1 && h->k_dual3_flat[0] && h->k_dual3[1][0]) {
     // 4c under the subtree partition: the register-resident kernel over FLAT owned-family indices -- one launch for all
     // families with non-leaf children (the slices of every level at once) and one for the leaf parents (the last range)
     ProfScope ps(h, PC_PROX_H);
@@ -953,22 +955,22 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
     const long top = h->t_cut > 0 ? A.r_prefix[1] : 0;
     const bool skip_top_pn = A.pnorm && h->rank != 0 && top > 0;  // <r, P r> of the replicated top is counted by rank 0 only
     long pn_off = 0;
-    auto launch3 = [&](int part, long lo_arg, long cnt, bool with_pn) {
+    auto launch3 = [&](int part, long lo_arg, long cnt, bool with_pn) {  // part 0: lo_arg = first FLAT index; part 1: first node
       if (cnt <= 0) return;
       SpkFusedArgs A2 = A;
       A2.children_are_leaves = part;
       A2.pnorm = with_pn ? A.pnorm + pn_off : nullptr;
       const long g = (cnt + fpc - 1) / fpc;
-      spk_dual3_kernel_t k3 = h->k_dual3[part][with_pn ? 1 : 0];
+      spk_dual3_kernel_t k3 = part == 0 ? h->k_dual3_flat[with_pn ? 1 : 0] : h->k_dual3[part][with_pn ? 1 : 0];
       k3<<<(unsigned)g, 128, 0, h->stream>>>(D, h->P, A2, lo_arg, cnt);
       COUNT_LAUNCH(h, PC_PROX_H);
       if (with_pn) pn_off += g;
     };
     if (skip_top_pn) {
-      launch3(0, -1, std::min(top, F_nl), false);
-      launch3(0, -1 - top, F_nl - top, true);
+      launch3(0, 0, std::min(top, F_nl), false);
+      launch3(0, top, F_nl - top, true);
     } else {
-      launch3(0, -1, F_nl, A.pnorm != nullptr);
+      launch3(0, 0, F_nl, A.pnorm != nullptr);
     }
     launch3(1, A.r_start[leaf_rng], F_all - F_nl, A.pnorm != nullptr);
     pn_parts = pn_off;
