@@ -96,8 +96,7 @@ long even_up(long k) { return (k + 1) & ~1L; }
 
 }  // namespace
 
-bool spk_offline_factors(int N, int d, int nx, int nu, const double *A, const double *B, SpkFactorTable &T,
-                         std::string &err) {
+void spk_table_init(int N, int d, int nx, int nu, SpkFactorTable &T) {
   T.N = N; T.d = d; T.nx = nx; T.nu = nu;
   T.abk_stride = even_up((long)nx * nx);
   T.k_stride = even_up((long)nx * nu);
@@ -110,7 +109,12 @@ bool spk_offline_factors(int N, int d, int nx, int nu, const double *A, const do
   T.Kt = T.K;
   T.G = T.K;
   T.Rinv.assign((size_t)std::max(S, 0) * T.r_stride, 0.0);
+}
 
+bool spk_offline_factors(int N, int d, int nx, int nu, const double *A, const double *B, SpkFactorTable &T,
+                         std::string &err) {
+  spk_table_init(N, d, nx, nu, T);
+  const int S = N - 1;
   std::vector<Mat> Am(d), Bm(d);
   for (int w = 0; w < d; ++w) {
     Am[w] = Mat::from(A + (size_t)w * nx * nx, nx, nx);

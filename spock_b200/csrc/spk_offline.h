@@ -1,4 +1,5 @@
-// spk_offline.h -- offline factors of the hot path, computed once per spk_create on the host in fp64.
+// spk_offline.h -- offline factors of the hot path on the HOST in fp64: the cross-check (SPK_HOST_OFFLINE=1) of the device
+// versions in spk_offline_dev.cuh, which spk_create uses by default.
 //
 // Replaces `ricatti_offline` (src/model_dynamics/implicit_l.jl:46-97) and the kernel-projector construction
 // (src/models/cpock.jl:71-81,125-128).  On the trees the reference can generate every node of a stage has the
@@ -23,6 +24,8 @@ struct SpkFactorTable {
 // mode (0-based) of the child with ordinal c: Julia w(j) = (j % d) + 1 and j = 2 + c (mod d)
 inline int spk_child_mode(int d, int c) { return (c + 2) % d; }
 
+// dimensions, padded strides and zero-filled vectors of the table (the device version of the recursion fills them by D2H)
+void spk_table_init(int N, int d, int nx, int nu, SpkFactorTable &out);
 bool spk_offline_factors(int N, int d, int nx, int nu, const double *A, const double *B, SpkFactorTable &out,
                          std::string &err);
 

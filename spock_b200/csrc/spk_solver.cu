@@ -17,6 +17,7 @@
 #include "spk_fused.cuh"
 #include "spk_kernels.cuh"
 #include "spk_offline.h"
+#include "spk_offline_dev.cuh"
 #include "spk_peer.cuh"
 #include "spk_sp.cuh"
 
@@ -1632,13 +1633,17 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   h->L_norm = p->L_norm > 0 ? p->L_norm : (p->algorithm == SPK_SP ? 3.28 : 10.0);  // spock.jl:64 / cpock.jl:63
 
   std::string err;
-  if (!spk_offline_factors(p->N, d, nx, nu, p->A, p->B, h->table, err)) return fail(SPK_ERR_INVALID, err);
-  // kernel projector (cpock.jl:71-81,125-128): one for all nodes, or one per non-leaf node with non-uniform risk measures
+  // The offline phase (Riccati recursion, kernel projectors) runs on the device (spk_offline_dev.cuh); SPK_HOST_OFFLINE=1
+  // selects the host versions (spk_offline.cpp), which the tests use as the cross-check.
+  const char *ho = getenv("SPK_HOST_OFFLINE");
+  const bool host_offline = ho && ho[0] == '1';
   const long n_rms = p->n_rms > 1 ? p->n_rms : 1;
   if (n_rms != 1 && n_rms != nnl) return fail(SPK_ERR_INVALID, "n_rms must be 1 (uniform risk measures) or n_non_leaf");
   D.rms_per_node = n_rms > 1 ? 1 : 0;
-  {
-    const size_t nls2 = (size_t)D.nls * D.nls;
+  const size_t nls2 = (size_t)D.nls * D.nls;
+  if (host_offline) {
+    if (!spk_offline_factors(p->N, d, nx, nu, p->A, p->B, h->table, err)) return fail(SPK_ERR_INVALID, err);
+    // kernel projector (cpock.jl:71-81,125-128): one for all nodes, or one per non-leaf node with non-uniform risk measures
     h->ls_host.resize(nls2 * n_rms);
     std::vector<double> one;
     const double *prevE = nullptr, *prevF = nullptr;
@@ -1650,6 +1655,8 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
       std::copy(one.begin(), one.end(), h->ls_host.begin() + nls2 * i);
       prevE = Ei; prevF = Fi;
     }
+  } else {
+    spk_table_init(p->N, d, nx, nu, h->table);
   }
   D.abk_stride = h->table.abk_stride; D.k_stride = h->table.k_stride; D.r_stride = h->table.r_stride;
 
@@ -1668,7 +1675,33 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(upload(h, &tmp, p->sqrtR, p->n_sqrtQ * rsz)); h->P.sqrtR = tmp;
   SPK_TRY(upload(h, &tmp, p->sqrtQN, p->n_sqrtQN * qsz)); h->P.sqrtQN = tmp;
   SPK_TRY(upload(h, &tmp, p->b, n_rms * ny)); h->P.b = tmp;
-  SPK_TRY(upload(h, &tmp, h->ls_host.data(), (long)h->ls_host.size())); h->P.ls = tmp;
+  if (host_offline) {
+    SPK_TRY(upload(h, &tmp, h->ls_host.data(), (long)h->ls_host.size())); h->P.ls = tmp;
+  } else {  // kernel projectors on the device: one thread per risk measure (spk_k_projector)
+    double *dE = nullptr, *dF = nullptr, *rows = nullptr, *dls = nullptr, *flag = nullptr;
+    SPK_TRY(dev_alloc(h, &dls, (long)(nls2 * n_rms), false));
+    SPK_TRY(dev_alloc(h, &flag, 1));
+    void *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;  // temporaries: freed right after the kernel
+    const size_t eb = sizeof(double) * (size_t)n_rms * ny * d, rb = sizeof(double) * (size_t)n_rms * 2 * d * D.nls;
+    SPK_TRY(rt_malloc(&t1, eb));
+    if (rt_malloc(&t2, eb) != SPK_OK) { rt_free(t1); return SPK_ERR_ALLOC; }
+    if (rt_malloc(&t3, rb) != SPK_OK) { rt_free(t1); rt_free(t2); return SPK_ERR_ALLOC; }
+    dE = (double *)t1; dF = (double *)t2; rows = (double *)t3;
+    int rc = rt_h2d(dE, p->E, eb, h->stream);
+    if (rc == SPK_OK) rc = rt_h2d(dF, p->F, eb, h->stream);
+    if (rc == SPK_OK) {
+      const int b = SPK_EMU ? 1 : 128;
+      SPK_LAUNCH(spk_k_projector, grid_for(n_rms, b), b, 0, h->stream, ny, d, n_rms, dE, dF, rows, dls, reinterpret_cast<int *>(flag));
+      h->launches++;
+      rc = rt_launch_check();
+    }
+    int bad = 0;
+    if (rc == SPK_OK) rc = rt_d2h(&bad, flag, sizeof(int), h->stream);
+    rt_free(t1); rt_free(t2); rt_free(t3);
+    SPK_TRY(rc);
+    if (bad) return fail(SPK_ERR_INVALID, "kernel projector: the risk measure has E = F = 0");
+    h->P.ls = dls;
+  }
   SPK_TRY(dev_alloc(h, &h->x0, nx)); h->P.x0 = h->x0;
 
   // ---- subtree partition: levels < t_cut replicated, rank g owns m_sub subtrees below the cut
@@ -1684,14 +1717,43 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
 
   // ---- factors: per-stage table; in PER_NODE mode replicated into one slot per node of the families this rank computes
   //      (all of them on a single GPU), packed level by level
-  const SpkFactorTable &T = h->table;
+  SpkFactorTable &T = h->table;
   double *tABK, *tABKt, *tK, *tKt, *tG, *tR;
-  SPK_TRY(upload(h, &tABK, T.ABK.data(), (long)T.ABK.size()));
-  SPK_TRY(upload(h, &tABKt, T.ABKt.data(), (long)T.ABKt.size()));
-  SPK_TRY(upload(h, &tK, T.K.data(), (long)T.K.size()));
-  SPK_TRY(upload(h, &tKt, T.Kt.data(), (long)T.Kt.size()));
-  SPK_TRY(upload(h, &tG, T.G.data(), (long)T.G.size()));
-  SPK_TRY(upload(h, &tR, T.Rinv.data(), (long)T.Rinv.size()));
+  if (host_offline) {
+    SPK_TRY(upload(h, &tABK, T.ABK.data(), (long)T.ABK.size()));
+    SPK_TRY(upload(h, &tABKt, T.ABKt.data(), (long)T.ABKt.size()));
+    SPK_TRY(upload(h, &tK, T.K.data(), (long)T.K.size()));
+    SPK_TRY(upload(h, &tKt, T.Kt.data(), (long)T.Kt.size()));
+    SPK_TRY(upload(h, &tG, T.G.data(), (long)T.G.size()));
+    SPK_TRY(upload(h, &tR, T.Rinv.data(), (long)T.Rinv.size()));
+  } else {  // ricatti_offline on the device (spk_k_riccati), then a host copy of the small table for spk_get_factors and the
+            // fragment tables of the tensor-pipe kernels
+    double *tP = nullptr, *ws = nullptr, *flag = nullptr;
+    SPK_TRY(dev_alloc(h, &tABK, (long)T.ABK.size()));
+    SPK_TRY(dev_alloc(h, &tABKt, (long)T.ABKt.size()));
+    SPK_TRY(dev_alloc(h, &tK, (long)T.K.size()));
+    SPK_TRY(dev_alloc(h, &tKt, (long)T.Kt.size()));
+    SPK_TRY(dev_alloc(h, &tG, (long)T.G.size()));
+    SPK_TRY(dev_alloc(h, &tR, (long)T.Rinv.size()));
+    SPK_TRY(dev_alloc(h, &tP, (long)T.P.size()));
+    SPK_TRY(dev_alloc(h, &ws, spk_riccati_ws_doubles(d, nx, nu)));
+    SPK_TRY(dev_alloc(h, &flag, 1));
+    SpkRiccatiArgs R;
+    R.N = p->N; R.d = d; R.nx = nx; R.nu = nu;
+    R.abk_stride = T.abk_stride; R.k_stride = T.k_stride; R.r_stride = T.r_stride;
+    R.A = h->P.A; R.B = h->P.B;
+    R.P = tP; R.ABK = tABK; R.ABKt = tABKt; R.K = tK; R.Kt = tKt; R.G = tG; R.Rinv = tR; R.ws = ws;
+    R.fail = reinterpret_cast<int *>(flag);
+    SPK_LAUNCH(spk_k_riccati, 1, SPK_EMU ? 1 : 256, 0, h->stream, R);
+    h->launches++;
+    SPK_TRY(rt_launch_check());
+    int bad = 0;
+    SPK_TRY(rt_d2h(&bad, flag, sizeof(int), h->stream));
+    if (bad) return fail(SPK_ERR_INVALID, "Riccati recursion: I + sum B'PB is not positive definite at stage " + std::to_string(bad - 1));
+    auto back = [&](std::vector<double> &dst, const double *src) { return dst.empty() ? (int)SPK_OK : rt_d2h(dst.data(), src, sizeof(double) * dst.size(), h->stream); };
+    SPK_TRY(back(T.ABK, tABK)); SPK_TRY(back(T.ABKt, tABKt)); SPK_TRY(back(T.K, tK)); SPK_TRY(back(T.Kt, tKt));
+    SPK_TRY(back(T.G, tG)); SPK_TRY(back(T.Rinv, tR)); SPK_TRY(back(T.P, tP));
+  }
   h->P.ABK = tABK; h->P.ABKt = tABKt; h->P.K = tK; h->P.Kt = tKt; h->P.G = tG; h->P.Rinv = tR;
   h->D_tab = D; h->D_tab.per_node = 0;
   h->P_tab = h->P;
@@ -2177,7 +2239,11 @@ int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, dou
   }
   if (ls) {
     const size_t nls2 = (size_t)D.nls * D.nls, off = (D.rms_per_node && i0 < D.nnl) ? nls2 * (size_t)i0 : 0;
-    std::copy(h->ls_host.begin() + off, h->ls_host.begin() + off + nls2, ls);
+    if (!h->ls_host.empty()) {
+      std::copy(h->ls_host.begin() + off, h->ls_host.begin() + off + nls2, ls);
+    } else {  // computed on the device (spk_k_projector): fetch this node's projector
+      SPK_TRY(rt_d2h(ls, h->P.ls + off, sizeof(double) * nls2, h->stream));
+    }
   }
   return SPK_OK;
 }

@@ -382,3 +382,19 @@ def check_solve_batch(lib, flats, algs, tol=1e-3):
             assert relerr(zb, zs) < 1e-12 and relerr(vb, vs) < 1e-12
     for h in hb + hs:
         h.close()
+
+
+def check_offline_device_vs_host(lib, flat, monkeypatch):
+    """The offline phase on the device (spk_k_riccati, spk_k_projector: spk_offline_dev.cuh) against the host versions
+    (SPK_HOST_OFFLINE=1, spk_offline.cpp) and, through the oracle, against ricatti_offline / the kernel projector of the
+    reference (implicit_l.jl:46-97, cpock.jl:71-81,125-128)."""
+    out = []
+    for host in ("1", "0"):
+        monkeypatch.setenv("SPK_HOST_OFFLINE", host)
+        h = Handle(flat, CP, lib=lib)
+        nodes = sorted({1, 2, max(1, flat.n_non_leaf // 2), flat.n_non_leaf, flat.n_non_leaf + 1, flat.n})
+        out.append([h.factors(i) for i in nodes])
+        h.close()
+    for fh, fd in zip(*out):
+        for a, b in zip(fh, fd):
+            assert relerr(b, a) < 1e-12 or np.max(np.abs(a)) == 0.0

@@ -192,3 +192,10 @@ def test_nonuniform_risk_measures_on_specialised_shapes(cuda_lib, nx, nu, d, N):
     check_operators(cuda_lib, flat, 0, seed=2)
     _run_pair(cuda_lib, flat, CP, 30)
     _run_pair(cuda_lib, flat, SP, 8)
+
+
+@pytest.mark.parametrize("name", ["fixture_N3_d2", "heat_N4_d3_nx3", "l2ball_N4_d3_nx3", "random_N5_d2_nx6_nu3", "nonuniform_avar_N5_d2_nx4",
+                                  "pernode_cost_tv_N4_d2_nx3", "random_N3_d4_nx35_nu17"])
+def test_offline_phase_on_device_equals_host(cuda_lib, name, monkeypatch):
+    from tests.helpers import check_offline_device_vs_host, flat_of
+    check_offline_device_vs_host(cuda_lib, flat_of(name), monkeypatch)

@@ -216,3 +216,10 @@ def test_batched_independent_problems(emu_lib):
     from tests.helpers import check_solve_batch, flat_of
     names = ["heat_N7_d2_nx5", "random_N5_d2_nx6_nu3", "heat_N4_d3_nx3", "heat_N7_d2_nx5", "l2ball_N4_d3_nx3"]
     check_solve_batch(emu_lib, [flat_of(n) for n in names], [CP, CP, CP, SP, SP])
+
+
+@pytest.mark.parametrize("name", ["fixture_N3_d2", "heat_N4_d3_nx3", "l2ball_N4_d3_nx3", "random_N5_d2_nx6_nu3", "nonuniform_avar_N5_d2_nx4",
+                                  "pernode_cost_tv_N4_d2_nx3", "random_N3_d4_nx35_nu17"])
+def test_offline_phase_on_device_equals_host(emu_lib, name, monkeypatch):
+    from tests.helpers import check_offline_device_vs_host, flat_of
+    check_offline_device_vs_host(emu_lib, flat_of(name), monkeypatch)
