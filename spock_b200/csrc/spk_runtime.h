@@ -32,6 +32,24 @@ typedef cudaEvent_t spk_event_t;
 
 #define SPK_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// the same launch chained to the previous one on the stream by programmatic dependent launch (the kernel must execute
+// griddepcontrol.wait before it touches anything the previous kernel wrote); `pdl` false = plain stream order
+template <class... KArgs, class... Args>
+static inline cudaError_t spk_launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define SPK_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) (void)spk_launch_pdl((pdl), kernel, (grid), (block), (smem), (stream), __VA_ARGS__)
 
 #else
 // ------------------------------------------------------------------------------------------------ host emulation (tests only)
@@ -79,6 +97,8 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
       }                                                                        \
     }                                                                          \
   } while (0)
+
+#define SPK_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) SPK_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
 
 #endif
 

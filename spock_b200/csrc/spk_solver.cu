@@ -1311,7 +1311,7 @@ static int launch_terminate(spk_handle *h, int xi_slot, int is_sp) {
     std::string cerr;
     if (!h->comm.allreduce_max(h->d_scal, 2, h->stream, cerr)) return fail(SPK_ERR_COMM, cerr);
   }
-  SPK_LAUNCH(spk_k_terminate, 1, 1, 0, h->stream, h->d_ctl, h->d_scal, xi_slot, is_sp, h->d_log);
+  SPK_LAUNCH_PDL(h->use_pdl, spk_k_terminate, 1, 1, 0, h->stream, h->d_ctl, h->d_scal, xi_slot, is_sp, h->d_log);
   COUNT_LAUNCH(h, PC_VEC);
   return rt_launch_check();
 }
@@ -1337,29 +1337,29 @@ static int sp_pass_device_launch(spk_handle *h, double gamma, double sigma) {
   SPK_TRY(op_T_fused_launch(h, h->zv, h->zvbar, gamma, sigma, 4));                       // :389-390 and <r, P r>
   {
     ProfScope ps(h, PC_VEC);
-    SPK_LAUNCH(spk_k_sp_a, g, T, 0, h->stream, nr, V, c, scal, part, tick);
-    SPK_LAUNCH(spk_k_sp_b, g, T, 0, h->stream, nr, V, c, part, tick);
-    SPK_LAUNCH(spk_k_sp_c, g, T, 0, h->stream, nr, V, c, part, tick);
-    SPK_LAUNCH(spk_k_sp_d, g, T, 0, h->stream, nr, V, c, part, tick);
-    SPK_LAUNCH(spk_k_sp_e, g, T, 0, h->stream, nr, V, c);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_a, g, T, 0, h->stream, nr, V, c, scal, part, tick);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_b, g, T, 0, h->stream, nr, V, c, part, tick);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_c, g, T, 0, h->stream, nr, V, c, part, tick);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_d, g, T, 0, h->stream, nr, V, c, part, tick);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_e, g, T, 0, h->stream, nr, V, c);
     for (int k = 0; k < 5; ++k) COUNT_LAUNCH(h, PC_VEC);
   }
   SPK_TRY(op_T_fused_launch(h, h->wu, h->wubar, gamma, sigma, 5));                       // :133-164
   {
     ProfScope ps(h, PC_VEC);
-    SPK_LAUNCH(spk_k_sp_f_decide, 1, 1, 0, h->stream, c, scal);
-    SPK_LAUNCH(spk_k_sp_f, g, T, 0, h->stream, nr, V, c);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_f_decide, 1, 1, 0, h->stream, c, scal);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_f, g, T, 0, h->stream, nr, V, c);
     // K2: rho = <r~, P (r~ - d)> (spock_dot :485-516), only when K1 failed
-    SPK_LAUNCH(kLt, gz, T, 0, h->stream, D, h->P, h->ws_rho + nz, -gamma, 1.0, h->ws_rho, nop, h->rwu, scal + 6, 0, nop, c, &c->need_k2,
+    SPK_LAUNCH_PDL(h->use_pdl, kLt, gz, T, 0, h->stream, D, h->P, h->ws_rho + nz, -gamma, 1.0, h->ws_rho, nop, h->rwu, scal + 6, 0, nop, c, &c->need_k2,
                part, tick);
-    SPK_LAUNCH(kL, gv, T, 0, h->stream, D, h->P, h->ws_rho, -sigma, 1.0, h->ws_rho + nz, nop, h->rwu + nz, scal + 6, 1, nop, c,
+    SPK_LAUNCH_PDL(h->use_pdl, kL, gv, T, 0, h->stream, D, h->P, h->ws_rho, -sigma, 1.0, h->ws_rho + nz, nop, h->rwu + nz, scal + 6, 1, nop, c,
                &c->need_k2, part, tick);
-    SPK_LAUNCH(spk_k_sp_g_decide, 1, 1, 0, h->stream, c, scal);
-    SPK_LAUNCH(spk_k_sp_g, g, T, 0, h->stream, nr, V, c);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_g_decide, 1, 1, 0, h->stream, c, scal);
+    SPK_LAUNCH_PDL(h->use_pdl, spk_k_sp_g, g, T, 0, h->stream, nr, V, c);
     // should_terminate! (sp.jl:270-344): xi1 = ||L'dv - dz/gamma||_inf, xi2 = ||L dz - dv/sigma||_inf
-    SPK_LAUNCH(kLt, gz, T, 0, h->stream, D, h->P, h->dzv + nz, 1.0, -1.0 / gamma, h->dzv, nop, nodp, nop, 0, scal + 10, c, always, part,
+    SPK_LAUNCH_PDL(h->use_pdl, kLt, gz, T, 0, h->stream, D, h->P, h->dzv + nz, 1.0, -1.0 / gamma, h->dzv, nop, nodp, nop, 0, scal + 10, c, always, part,
                tick);
-    SPK_LAUNCH(kL, gv, T, 0, h->stream, D, h->P, h->dzv, 1.0, -1.0 / sigma, h->dzv + nz, nop, nodp, nop, 0, scal + 11, c, always, part,
+    SPK_LAUNCH_PDL(h->use_pdl, kL, gv, T, 0, h->stream, D, h->P, h->dzv, 1.0, -1.0 / sigma, h->dzv + nz, nop, nodp, nop, 0, scal + 11, c, always, part,
                tick);
     for (int k = 0; k < 8; ++k) COUNT_LAUNCH(h, PC_VEC);
   }

@@ -101,6 +101,8 @@ SPK_HD int spk_sp_slot(int j, int rot) { return (j + 2 * rot) % 3; }
 //      columns (anderson.jl:13-65, rotating slots instead of shifting) and the first Gram-Schmidt dots (:78-91)
 SPK_SP_KERNEL spk_k_sp_a(long nr, SpkSpVecs V, SpkCtl *c, const double *scal, double *partial,
                                                                unsigned *ticket) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const int rot = c->rot + 1;  // this pass's rotation; stored by the epilogue after every block has read the old value
   double *mr0 = V.MR[spk_sp_slot(0, rot)], *mp0 = V.MP[spk_sp_slot(0, rot)], *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -138,6 +140,8 @@ SPK_SP_KERNEL spk_k_sp_a(long nr, SpkSpVecs V, SpkCtl *c, const double *scal, do
 }
 // ---- KB: Q1 -= rho2 Q2 (anderson.jl:78-91, j = 2) and the dots for j = 3
 SPK_SP_KERNEL spk_k_sp_b(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const int rot = c->rot;
   double *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -168,6 +172,8 @@ SPK_SP_KERNEL spk_k_sp_b(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsig
 }
 // ---- KC: Q1 -= rho3 Q3, ||Q1|| (anderson.jl:68-76 / :93-98)
 SPK_SP_KERNEL spk_k_sp_c(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const int rot = c->rot;
   double *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -193,6 +199,8 @@ SPK_SP_KERNEL spk_k_sp_c(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsig
 }
 // ---- KD: Q1 /= R11, Q'r (anderson.jl:111), then gamma = R^{-1} Q'r (:113)
 SPK_SP_KERNEL spk_k_sp_d(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsigned *ticket) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const int rot = c->rot;
   double *q0 = V.AQ[spk_sp_slot(0, rot)];
@@ -220,6 +228,8 @@ SPK_SP_KERNEL spk_k_sp_d(long nr, SpkSpVecs V, SpkCtl *c, double *partial, unsig
 }
 // ---- KE: d = -r - MP gamma (anderson.jl:116-122), candidate (w,u) = (z,v) + d (sp.jl:118-131, tau = 1)
 SPK_SP_KERNEL spk_k_sp_e(long nr, SpkSpVecs V, const SpkCtl *c) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const int rot = c->rot;
   const double *p0 = V.MP[spk_sp_slot(0, rot)], *p1 = V.MP[spk_sp_slot(1, rot)], *p2 = V.MP[spk_sp_slot(2, rot)];
@@ -235,6 +245,8 @@ SPK_SP_KERNEL spk_k_sp_e(long nr, SpkSpVecs V, const SpkCtl *c) {
 }
 // ---- SF (one thread): the K1 test (sp.jl:166-191)
 SPK_KERNEL void spk_k_sp_f_decide(SpkCtl *c, const double *scal) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const double c1 = 0.99, q = 0.99;  // sp.jl:366-372
   const double rt = sqrt(scal[5]);
@@ -251,6 +263,8 @@ SPK_KERNEL void spk_k_sp_f_decide(SpkCtl *c, const double *scal) {
 }
 // ---- KF: candidate residual (sp.jl:133-164) and, unless K1 holds, r~ - d for the K2 inner product (:419-424)
 SPK_SP_KERNEL spk_k_sp_f(long nr, SpkSpVecs V, const SpkCtl *c) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const bool k2 = c->need_k2 != 0;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -262,6 +276,8 @@ SPK_SP_KERNEL spk_k_sp_f(long nr, SpkSpVecs V, const SpkCtl *c) {
 }
 // ---- SG (one thread): K2 test or fallback (sp.jl:193-222, :443-446)
 SPK_KERNEL void spk_k_sp_g_decide(SpkCtl *c, double *scal) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const double sigma_k2 = 0.1, lambda_sp = 1.0;
   if (c->need_k2) {
@@ -280,6 +296,8 @@ SPK_KERNEL void spk_k_sp_g_decide(SpkCtl *c, double *scal) {
 }
 // ---- KG: the accepted update and delta = (z,v) - (z,v)_old for should_terminate! and the next Anderson step
 SPK_SP_KERNEL spk_k_sp_g(long nr, SpkSpVecs V, const SpkCtl *c) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const int branch = c->branch;
   const double coef = c->coef;
@@ -304,6 +322,8 @@ SPK_SP_KERNEL spk_k_Lop_ctl(SpkDims D, SpkPtrs P, const double *__restrict__ x, 
                                                                   const double *__restrict__ dot_with, double *dot_out, int dot_accumulate,
                                                                   double *absmax, const SpkCtl *c, const int *run_if, double *partial,
                                                                   unsigned *ticket) {
+  spk_pdl_trigger();
+  spk_pdl_wait();
   if (c->done || (run_if && !*run_if)) return;
   const long n = TRANS ? D.nz : D.nv;
   double acc[1] = {0.0}, mx = 0.0;
@@ -339,6 +359,8 @@ SPK_SP_KERNEL spk_k_Lop_ctl(SpkDims D, SpkPtrs P, const double *__restrict__ x, 
 // ---- SH (one thread): should_terminate! (sp.jl:270-344 / cp.jl:54-123), per-pass log, counters
 //      xi_slot: where the pass left (xi1, xi2); bc_from_branch: SuperMann's backtrack_count (9 on fallback)
 SPK_KERNEL void spk_k_terminate(SpkCtl *c, const double *scal, int xi_slot, int is_sp, double *log) {
+  spk_pdl_trigger();
+  spk_pdl_wait();  // chained to the previous launch of the pass by programmatic dependent launch
   if (c->done) return;
   const double xi1 = scal[xi_slot], xi2 = scal[xi_slot + 1];
   bool stop;
