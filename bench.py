@@ -220,10 +220,18 @@ def cpu_arm(name, n_threads, steps, warmup, budget_s=240.0):
     if need_gb * 1.2 < avail_gb:
         probe, o = cpu_passes(name, N_full, n_threads, 1, max(1, min(warmup, 1)))  # first pass pages the factors in
         k = int(max(1, min(steps, (budget_s - probe["build_s"]) / max(probe["s_per_pass"], 1e-9))))
-        t0 = time.perf_counter()
-        o.step(k)
-        dt = time.perf_counter() - t0
+        # the k passes as (up to) 5 repeats; value from the total, the median of the repeats next to it
+        chunks = [k // 5 + (1 if r < k % 5 else 0) for r in range(5)] if k >= 5 else [k]
+        reps, dt = [], 0.0
+        for c in chunks:
+            t0 = time.perf_counter()
+            o.step(c)
+            e = time.perf_counter() - t0
+            dt += e
+            reps.append(e / c)
         det.update({"extrapolated": False, "sample_nodes": n_full, "passes_timed": k, "seconds": dt, "build_s": probe["build_s"],
+                    "repeats": len(chunks), "s_per_pass_median_of_repeats": float(np.median(reps)),
+                    "s_per_pass_min": min(reps), "s_per_pass_max": max(reps),
                     "sample": f"the workload itself: {k} CP passes over all {n_full} nodes after {1 + probe['warmup']} warm-up passes"})
         return dt / k, det, o
     pts = []
