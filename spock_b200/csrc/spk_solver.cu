@@ -54,7 +54,10 @@ static int fail(int code, const std::string &msg) {
   } while (0)
 static int rt_malloc(void **p, size_t bytes) {
   const cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
-  if (e != cudaSuccess) return fail(SPK_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear the (non-sticky) error: the next handle's launch checks must not see this failure
+    return fail(SPK_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
   return SPK_OK;
 }
 static void rt_free(void *p) { cudaFree(p); }
