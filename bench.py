@@ -663,6 +663,18 @@ def main():
             res, _ = h.solve(x0, tol=1e-3, max_iter=1500, z0=np.zeros(h.nz), v0=np.zeros(h.nv))
             line["time_to_tol"] = {"tol": 1e-3, "seconds": res["solve_ms"] / 1e3, "iterations": res["passes"],
                                    "converged": bool(res["converged"]), "xi1": res["xi1"], "xi2": res["xi2"]}
+            # the same solve with ||L||^2 estimated on the device (spk_estimate_L_norm) instead of the reference's hard-coded
+            # L_norm = 10 (cpock.jl:62-63, valid for its server_heat data): larger step sizes 0.99 / sqrt(L_norm)
+            try:
+                t0 = time.perf_counter()
+                l_est = h.estimate_L_norm(60, apply=True)
+                t_est = time.perf_counter() - t0
+                res2, _ = h.solve(x0, tol=1e-3, max_iter=1500, z0=np.zeros(h.nz), v0=np.zeros(h.nv))
+                line["time_to_tol_estimated_L_norm"] = {"L_norm": l_est, "estimate_seconds": t_est, "seconds": res2["solve_ms"] / 1e3,
+                                                        "iterations": res2["passes"], "converged": bool(res2["converged"]),
+                                                        "note": "not the reference's step sizes: reported next to time_to_tol, never instead of it"}
+            except Exception as e:
+                line["time_to_tol_estimated_L_norm"] = {"error": str(e)[:200]}
         h.close()
         del z_host, v_host
         if not args.no_extras and world == 1:
