@@ -199,3 +199,45 @@ def test_nonuniform_risk_measures_on_specialised_shapes(cuda_lib, nx, nu, d, N):
 def test_offline_phase_on_device_equals_host(cuda_lib, name, monkeypatch):
     from tests.helpers import check_offline_device_vs_host, flat_of
     check_offline_device_vs_host(cuda_lib, flat_of(name), monkeypatch)
+
+
+def test_full_size_feasibility_properties_config3(cuda_lib):
+    """BASELINE config 3 at FULL size (1 048 575 nodes, nx=50, nu=20, per-node factors: 69 GB on the device), where the
+    oracle does not go: the reference's own feasibility tests (test/model_dynamics/implicit_L.jl:59-78) on the iterate the
+    fused path produces -- after any pass z = prox_f(.) lies in S1 and S2 exactly: x_1 = x0, x_j = A_w(j) x_anc(j) +
+    B_w(j) u_anc(j) for every node, E'y_i = tau_children + s_children for every non-leaf node -- plus per-node == per-stage."""
+    import torch
+
+    if torch.cuda.mem_get_info()[1] < 150e9:
+        pytest.skip("needs a 180 GB device")
+    N, d, nx, nu = 20, 2, 50, 20
+    scen_tree, cost, dynamics, rms, constraints = get_random_system_specs(N, d, nx, nu)
+    flat = flatten_problem(scen_tree, cost, dynamics, rms, constraints)
+    x0 = 0.1 * np.ones(nx) + 0.01 * np.arange(nx)
+    zs = []
+    for fm in (0, 1):
+        h = Handle(flat, CP, factor_mode=fm, lib=cuda_lib)
+        h.set_x0(x0)
+        h.step(4)
+        z, _ = h.get_iterate()
+        zo = h.z_off
+        h.close()
+        zs.append(z)
+        n, nnl = flat.n, flat.n_non_leaf
+        x, u = z[: n * nx].reshape(n, nx), z[zo[1]: zo[1] + nnl * nu].reshape(nnl, nu)
+        assert np.array_equal(x[0], x0)
+        j = np.arange(2, n + 1)                       # 1-based node numbers; anc(j) = (j-2) div d + 1, mode w(j) = j % d (0-based)
+        anc, w = (j - 2) // d, j % d
+        worst = 0.0
+        for mode in range(d):
+            sel = w == mode
+            pred = x[anc[sel]] @ np.asarray(dynamics.A[mode]).T + u[anc[sel]] @ np.asarray(dynamics.B[mode]).T
+            worst = max(worst, float(np.max(np.abs(pred - x[j[sel] - 1]))))
+        assert worst < 1e-11 * max(1.0, float(np.max(np.abs(x)))), worst
+        s, tau = z[zo[2]: zo[2] + n], z[zo[3]: zo[3] + n - 1]
+        y = z[zo[4]:].reshape(nnl, flat.ny)
+        lhs = y @ flat.E2d                             # (E'y_i)_c
+        c0 = d * np.arange(nnl) + 1                    # 0-based first child of node i0
+        rhs = np.stack([tau[c0 + c - 1] + s[c0 + c] for c in range(d)], axis=1)
+        assert float(np.max(np.abs(lhs - rhs))) < 1e-11 * max(1.0, float(np.max(np.abs(rhs))))
+    assert relerr(zs[0], zs[1]) < 1e-11
