@@ -167,6 +167,7 @@ struct spk_handle {
   SpkComm comm;
   int rank = 0, world = 1, t_cut = 0;
   long m_sub = 1;
+  bool scratch_ready = false;  // z_old, delta, xi_1/xi_2, xi and the modular operators' workspaces exist (ensure_scratch)
   bool in_group = false;  // sub-handle of a device group
   // per-node factors under the partition: only this rank's families are stored, packed level by level (replicated top
   // first); fac_start[t] = first packed family slot of level t
@@ -255,6 +256,8 @@ struct spk_handle {
   double *z() { return zv; }
   double *v() { return zv + D.nz; }
 };
+
+static int ensure_scratch(spk_handle *h);
 
 static int dev_alloc(spk_handle *h, double **p, long count, bool zero = true) {
   void *q = nullptr;
@@ -1138,6 +1141,7 @@ static bool decide_termination(spk_handle *h, const LoopState &S, double *xi, do
 // one pass of run_cp! (cp.jl:205-228) up to and including the launches of should_terminate!
 static int cp_pass_launch(spk_handle *h, const LoopState &S) {
   const long nzv = h->D.nz + h->D.nv;
+  if (!(h->fused_ok && !S.verbose_log)) SPK_TRY(ensure_scratch(h));
   if (h->fused_ok && !S.verbose_log) {
     // z_old is the input buffer itself and should_terminate!'s xi1, xi2 come out of the forward sweep (d_scal[0..1])
     SPK_TRY(op_T_fused(h, h->zv, h->zvbar, S.gamma, S.sigma, -1));
@@ -1557,6 +1561,29 @@ int spk_destroy(spk_handle *h) {
   return SPK_OK;
 }
 
+static int fill_ones(spk_handle *h, double *dst, long count) {
+  std::vector<double> ones((size_t)std::min(count, 1L << 20), 1.0);
+  for (long off = 0; off < count; off += (long)ones.size()) {
+    const long cnt = std::min((long)ones.size(), count - off);
+    SPK_TRY(rt_h2d(dst + off, ones.data(), sizeof(double) * cnt, h->stream));
+  }
+  return SPK_OK;
+}
+// The iterate-sized vectors outside the fused Chambolle-Pock path, allocated on first use (see create_impl)
+static int ensure_scratch(spk_handle *h) {
+  if (h->scratch_ready) return SPK_OK;
+  const long nr = h->D.nz + h->D.nv;
+  SPK_TRY(dev_alloc(h, &h->zv_old, nr));
+  SPK_TRY(dev_alloc(h, &h->dzv, nr));
+  SPK_TRY(dev_alloc(h, &h->xi12, nr));
+  SPK_TRY(dev_alloc(h, &h->zw, h->D.nz));
+  SPK_TRY(dev_alloc(h, &h->xi, h->D.nz));
+  SPK_TRY(dev_alloc(h, &h->ws_L, nr));
+  SPK_TRY(fill_ones(h, h->zv_old, nr));  // z_old, v_old (cpock.jl:98-99)
+  h->scratch_ready = true;
+  return SPK_OK;
+}
+
 #ifndef SPK_HOST_EMU
 // Mailbox of the peer-memory exchanges (spk_peer.cuh).  Between processes the ranks swap cudaIpc handles of their
 // mailboxes through one NCCL all-gather and map each other's; inside a device group the front handle links the pointers
@@ -1797,16 +1824,13 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
 
   // ---- state (cpock.jl:83-103)
   const long nr = D.nz + D.nv;
+  // The fused Chambolle-Pock path touches only (z, v), (zbar, vbar) and the sweep scratch q, d.  The other iterate-sized
+  // vectors (z_old, delta, xi_1 / xi_2, xi, the workspaces of the modular operators: 4 (nz+nv) + 2 nz doubles, 8.6 GB at config 3)
+  // belong to the LOG mode, the host-driven loop, SuperMann and the operator interface: ensure_scratch allocates them on first use.
   SPK_TRY(dev_alloc(h, &h->zv, nr));
   SPK_TRY(dev_alloc(h, &h->zvbar, nr));
-  SPK_TRY(dev_alloc(h, &h->zv_old, nr));
-  SPK_TRY(dev_alloc(h, &h->dzv, nr));
-  SPK_TRY(dev_alloc(h, &h->xi12, nr));
-  SPK_TRY(dev_alloc(h, &h->zw, D.nz));
-  SPK_TRY(dev_alloc(h, &h->xi, D.nz));
   SPK_TRY(dev_alloc(h, &h->ric_q, n * nx));
   SPK_TRY(dev_alloc(h, &h->ric_d, std::max(nnl, 1L) * nu));
-  SPK_TRY(dev_alloc(h, &h->ws_L, nr));
   h->red_blocks = SPK_EMU ? 8 : h->num_sms * 8;
   SPK_TRY(dev_alloc(h, &h->d_partial, h->red_blocks));
   SPK_TRY(dev_alloc(h, &h->d_scal, 32));
@@ -1894,15 +1918,8 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
     for (int k = 0; k < AA_M * AA_M; ++k) h->aaR[k] = 0.0;
     for (int k = 0; k < AA_M; ++k) h->aaR[k + k * AA_M] = 1.0;
   }
-  // fill the "ones" initial values: z_old, v_old (cpock.jl:98-99), rz_old, rv_old (spock.jl:187-188)
-  {
-    std::vector<double> ones((size_t)std::min(nr, 1L << 20), 1.0);
-    for (long off = 0; off < nr; off += (long)ones.size()) {
-      const long cnt = std::min((long)ones.size(), nr - off);
-      SPK_TRY(rt_h2d(h->zv_old + off, ones.data(), sizeof(double) * cnt, h->stream));
-      if (h->alg == SPK_SP) SPK_TRY(rt_h2d(h->rzv_old + off, ones.data(), sizeof(double) * cnt, h->stream));
-    }
-  }
+  if (h->alg == SPK_SP || !h->fused_ok) SPK_TRY(ensure_scratch(h));
+  if (h->alg == SPK_SP) SPK_TRY(fill_ones(h, h->rzv_old, nr));  // rz_old, rv_old (spock.jl:187-188)
   for (int c = 0; c < PC_COUNT; ++c) { h->prof_ms[c] = 0.0; h->prof_launches[c] = 0; }
   return rt_sync(h->stream);
 }
@@ -2145,6 +2162,7 @@ int spk_get_iterate(spk_handle *h, double *z, double *v) {
 int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double scalar) {
   if (!h || !in || !out) return fail(SPK_ERR_INVALID, "NULL argument");
   if (h->group) return group_first(h, [=](spk_handle *s) { return spk_apply(s, op, in, out, scalar); });
+  SPK_TRY(ensure_scratch(h));
   const SpkDims &D = h->D;
   const long nz = D.nz, nv = D.nv;
   // scratch that carries nothing across passes or solves: zvbar (rewritten by every operator evaluation) and xi12
@@ -2185,6 +2203,7 @@ int spk_apply(spk_handle *h, int32_t op, const double *in, double *out, double s
 int spk_mul(spk_handle *h, int32_t trans, const double *B, double alpha, double beta, double *C) {
   if (!h || !B || !C) return fail(SPK_ERR_INVALID, "NULL argument");
   if (h->group) return group_first(h, [=](spk_handle *s) { return spk_mul(s, trans, B, alpha, beta, C); });
+  SPK_TRY(ensure_scratch(h));
   const long nz = h->D.nz, nv = h->D.nv;
   double *tz = h->zvbar, *tv = h->zvbar + nz, *cz = h->xi12, *cv = h->xi12 + nz;  // scratch (see spk_apply)
   if (trans) {  // C (nz) <- alpha L'B + beta C, B (nv)
@@ -2209,6 +2228,7 @@ int spk_dot(spk_handle *h, const double *a_z, const double *a_v, const double *b
     *out = loc[0];
     return SPK_OK;
   }
+  SPK_TRY(ensure_scratch(h));
   const long nz = h->D.nz, nv = h->D.nv;
   SPK_TRY(rt_h2d(h->zvbar, a_z, sizeof(double) * nz, h->stream));
   SPK_TRY(rt_h2d(h->zvbar + nz, a_v, sizeof(double) * nv, h->stream));
@@ -2352,6 +2372,7 @@ static void state_blocks(spk_handle *h, std::vector<double *> &blocks) {
 int spk_get_state(spk_handle *h, double *state) {
   if (!h || !state) return fail(SPK_ERR_INVALID, "NULL argument");
   if (h->world > 1) return fail(SPK_ERR_INVALID, "spk_get_state is single-GPU");
+  SPK_TRY(ensure_scratch(h));
   const long nr = h->D.nz + h->D.nv;
   std::vector<double *> blocks;
   state_blocks(h, blocks);
@@ -2363,6 +2384,7 @@ int spk_get_state(spk_handle *h, double *state) {
 int spk_set_state(spk_handle *h, const double *state) {
   if (!h || !state) return fail(SPK_ERR_INVALID, "NULL argument");
   if (h->world > 1) return fail(SPK_ERR_INVALID, "spk_set_state is single-GPU");
+  SPK_TRY(ensure_scratch(h));
   const long nr = h->D.nz + h->D.nv;
   std::vector<double *> blocks;
   state_blocks(h, blocks);
@@ -2376,6 +2398,7 @@ int spk_set_state(spk_handle *h, const double *state) {
 int spk_estimate_L_norm(spk_handle *h, int32_t iters, double *L_norm) {
   if (!h || !L_norm) return fail(SPK_ERR_INVALID, "NULL argument");
   if (h->world > 1) return fail(SPK_ERR_INVALID, "spk_estimate_L_norm is single-GPU");
+  SPK_TRY(ensure_scratch(h));
   const long nz = h->D.nz;
   if (iters <= 0) iters = 50;
   // scratch that carries nothing across passes or solves
