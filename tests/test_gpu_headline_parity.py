@@ -241,3 +241,15 @@ def test_full_size_feasibility_properties_config3(cuda_lib):
         rhs = np.stack([tau[c0 + c - 1] + s[c0 + c] for c in range(d)], axis=1)
         assert float(np.max(np.abs(lhs - rhs))) < 1e-11 * max(1.0, float(np.max(np.abs(rhs))))
     assert relerr(zs[0], zs[1]) < 1e-11
+
+
+@pytest.mark.parametrize("N,d,nx,nu", [(2, 2, 3, 2), (2, 3, 1, 1), (3, 8, 2, 2), (3, 2, 1, 1), (4, 5, 2, 3), (2, 2, 1, 1)])
+def test_edge_shapes(cuda_lib, N, d, nx, nu):
+    """Smallest and most lopsided trees: N = 2 (a root whose children are leaves), scalar states and inputs, the widest
+    supported branching -- every operator, K passes of CP and SuperMann, both factor modes, against the oracle."""
+    from tests.helpers import check_k_steps, check_operators
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    for fm in (0, 1):
+        check_operators(cuda_lib, flat, fm)
+        check_k_steps(cuda_lib, flat, CP, 30, factor_mode=fm)
+        check_k_steps(cuda_lib, flat, SP, 10, factor_mode=fm)

@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 
 from oracle.oracle import CP, SP, Oracle
+from spock_b200.examples import get_random_system_specs
 from spock_b200.handle import Handle
+from spock_b200.problem import flatten_problem
 from tests.helpers import (SMALL_PROBLEMS, check_k_steps, check_nan_never_converges, check_operators, check_soc_branches, check_sp_options,
                            check_soc_edge_vectors, check_warm_started_second_solve, flat_of, golden_cp, golden_sp, relerr)
 
@@ -223,3 +225,15 @@ def test_batched_independent_problems(emu_lib):
 def test_offline_phase_on_device_equals_host(emu_lib, name, monkeypatch):
     from tests.helpers import check_offline_device_vs_host, flat_of
     check_offline_device_vs_host(emu_lib, flat_of(name), monkeypatch)
+
+
+@pytest.mark.parametrize("N,d,nx,nu", [(2, 2, 3, 2), (2, 3, 1, 1), (3, 8, 2, 2), (3, 2, 1, 1), (4, 5, 2, 3), (2, 2, 1, 1)])
+def test_edge_shapes(emu_lib, N, d, nx, nu):
+    """Smallest and most lopsided trees: N = 2 (a root whose children are leaves), scalar states and inputs, the widest
+    supported branching -- every operator, K passes of CP and SuperMann, both factor modes, against the oracle."""
+    from tests.helpers import check_k_steps, check_operators
+    flat = flatten_problem(*get_random_system_specs(N, d, nx, nu))
+    for fm in (0, 1):
+        check_operators(emu_lib, flat, fm)
+        check_k_steps(emu_lib, flat, CP, 30, factor_mode=fm)
+        check_k_steps(emu_lib, flat, SP, 10, factor_mode=fm)
