@@ -99,6 +99,11 @@ typedef struct {
    * per non-leaf node, back to back (node i at offsets (i-1)*ny*d and (i-1)*ny).  ny and the sub-cone list stay uniform,
    * as in the reference (implicit_l.jl:14,19). */
   int32_t n_rms;
+  /* caller-supplied mode map: mode_of_node[j-1] = node_info[j].w of the reference (scenario_tree.jl:77), the 1-based dynamics
+   * mode that leads to node j (entry 0, the root, is ignored); NULL = the generator's map w(j) = (j % d) + 1.  With a map
+   * the Riccati factors differ from node to node inside a stage, so `ricatti_offline` (implicit_l.jl:46-97) runs per node --
+   * batched on the device, one CTA per node, level by level -- and factor_mode must be SPK_FACTORS_PER_NODE (single GPU). */
+  const int32_t *mode_of_node;
 } spk_problem;
 
 typedef struct {

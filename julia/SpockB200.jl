@@ -49,6 +49,7 @@ struct SpkProblem
   rank::Int32; world_size::Int32; comm_id::Ptr{UInt8}
   n_devices::Int32; devices::Ptr{Int32}
   n_rms::Int32
+  mode_of_node::Ptr{Int32}
 end
 
 struct SpkResult
@@ -135,11 +136,15 @@ function spk_build(scen_tree, cost, dynamics, rms, constraints, algorithm :: Int
   fQ, fR, fQN = spk_flat(sQ), spk_flat(sR), spk_flat(sQN)
   devs = haskey(ENV, "SPOCK_B200_DEVICES") ? Int32[parse(Int32, s) for s in split(ENV["SPOCK_B200_DEVICES"], ",")] : Int32[]
   fmode = get(ENV, "SPOCK_B200_FACTORS", "per_node") == "per_stage" ? 1 : 0
-  keep = Any[A, B, fQ, fR, fQN, E, F, b, ct, cd, devs]
+  # node_info[j].w as the caller left it (scenario_tree.jl:77); NULL when it is the generator's (j % d) + 1
+  wmap = Int32[j == 1 ? 0 : scen_tree.node_info[j].w for j in 1:scen_tree.n]
+  default_w = all(j -> wmap[j] == (j % d) + 1, 2:scen_tree.n)
+  keep = Any[A, B, fQ, fR, fQN, E, F, b, ct, cd, devs, wmap]
   p = SpkProblem(scen_tree.N, d, nx, nu, pointer(A), pointer(B), dense, length(sQ), pointer(fQ), pointer(fR),
                  length(sQN), pointer(fQN), length(rm.b), pointer(E), pointer(F), pointer(b), length(ct), pointer(ct),
                  pointer(cd), constraints.x_min, constraints.x_max, constraints.u_min, constraints.u_max,
-                 algorithm, 0.0, fmode, -1, 0, 1, C_NULL, length(devs), isempty(devs) ? C_NULL : pointer(devs), length(rl))
+                 algorithm, 0.0, fmode, -1, 0, 1, C_NULL, length(devs), isempty(devs) ? C_NULL : pointer(devs), length(rl),
+                 default_w ? Ptr{Int32}(C_NULL) : pointer(wmap))
   h = Ref{Ptr{Cvoid}}(C_NULL)
   GC.@preserve keep spk_check(ccall((:spk_create, SPK_LIB), Cint, (Ref{SpkProblem}, Ref{Ptr{Cvoid}}), p, h))
   sz = zeros(Int64, 5); spk_check(ccall((:spk_sizes, SPK_LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], sz))

@@ -32,7 +32,7 @@ class _Problem(C.Structure):
         ("n_cones", C.c_int), ("cone_type", C.POINTER(C.c_int)), ("cone_dim", C.POINTER(C.c_int)),
         ("ls_matrix", C.POINTER(C.c_double)),
         ("x_min", C.c_double), ("x_max", C.c_double), ("u_min", C.c_double), ("u_max", C.c_double),
-        ("algorithm", C.c_int), ("L_norm", C.c_double), ("n_rms", C.c_int),
+        ("algorithm", C.c_int), ("L_norm", C.c_double), ("w", C.POINTER(C.c_int)), ("n_rms", C.c_int),
     ]
 
 
@@ -125,8 +125,12 @@ class Oracle:
             flat.N, flat.d, flat.nx, flat.nu, flat.ny, _dp(flat.A), _dp(flat.B), flat.cost_dense, flat.n_sqrtQ,
             _dp(flat.sqrtQ), _dp(flat.sqrtR), flat.n_sqrtQN, _dp(flat.sqrtQN), _dp(flat.E), _dp(flat.F), _dp(flat.b),
             len(flat.cone_type), self._keep[1].ctypes.data_as(ip), self._keep[2].ctypes.data_as(ip), _dp(ls),
-            flat.x_min, flat.x_max, flat.u_min, flat.u_max, algorithm, float(L_norm), n_rms,
+            flat.x_min, flat.x_max, flat.u_min, flat.u_max, algorithm, float(L_norm), None, n_rms,
         )
+        if getattr(flat, "w", None) is not None:
+            wv = np.ascontiguousarray(flat.w, dtype=np.int32)
+            self._keep.append(wv)
+            p.w = wv.ctypes.data_as(ip)
         self.h = self.lib.spo_create(C.byref(p), int(n_threads))
         if not self.h:
             raise ValueError("spo_create failed")

@@ -21,6 +21,7 @@
 
 struct spo_model {
   int sp_options; /* SPO_SP_LINESEARCH | SPO_SP_K0; 0 = the reference as shipped */
+  int custom_w;   /* node modes supplied by the caller */
   long n_rms;     /* 1 = uniform risk measures; nnl = per-node b and ls_matrix (get_nonuniform_rms_avar_v2) */
   int N, d, nx, nu, ny, nt, alg;
   long n, nnl, nl, nz, nv;
@@ -150,7 +151,7 @@ static void cost_mul(const spo_model *m, const double *S, int dim, const double 
 /* ------------------------------------------------------------------------------------------ build */
 
 /* scenario_tree.jl:61-109 */
-static void build_tree(spo_model *m) {
+static void build_tree(spo_model *m, const int *w_override) {
   const long d = m->d;
   long dN = 1;
   for (int k = 0; k < m->N; ++k) dN *= d; /* d^N */
@@ -162,6 +163,10 @@ static void build_tree(spo_model *m) {
   m->w = (int *)calloc((size_t)m->n, sizeof(int));
   m->min_idx = (long *)calloc((size_t)m->N, sizeof(long));
   for (long i = 1; i <= m->n; ++i) m->w[i - 1] = (i > 1) ? (int)(i % d) + 1 : 0; /* :77 */
+  if (w_override) { /* the caller's node_info[j].w */
+    for (long i = 2; i <= m->n; ++i) m->w[i - 1] = w_override[i - 1];
+    m->custom_w = 1;
+  }
   long child_index = 2;                                                           /* :82-88 */
   for (long i = 1; i <= m->nnl; ++i) {
     m->child_first[i - 1] = child_index;
@@ -239,7 +244,7 @@ static void riccati_offline(spo_model *m) {
     for (int k = 0; k < nx; ++k) m->P[(i - 1) * (long)nx * nx + k + (long)k * nx] = 1.0;
   double *wk = dalloc((long)nu * nu + 2L * nu * nx + 4L * nx * nx + 8);
   const char *env = getenv("SPO_FAITHFUL_OFFLINE");
-  if (env && env[0] == '1') {
+  if ((env && env[0] == '1') || m->custom_w) { /* with a caller-supplied mode map the nodes of a stage differ: node by node */
     for (long i = m->nnl; i >= 1; --i) riccati_node(m, i, wk); /* :71 */
   } else {
     for (int t = m->N - 2; t >= 0; --t) {
@@ -270,7 +275,7 @@ spo_model *spo_create(const spo_problem *p, int n_threads) {
   m->N = p->N; m->d = p->d; m->nx = p->nx; m->nu = p->nu; m->ny = p->ny;
   m->nt = n_threads > 1 ? n_threads : 1;
   m->alg = p->algorithm;
-  build_tree(m);
+  build_tree(m, p->w);
   const long n = m->n, nnl = m->nnl, nl = m->nl;
   const int nx = m->nx, nu = m->nu, ny = m->ny, d = m->d;
   /* get_nz implicit_l.jl:5-15 and z_to_* :106-158 */

@@ -39,6 +39,8 @@ typedef struct {
   double x_min, x_max, u_min, u_max; /* constraints.jl:11-22 */
   int algorithm;             /* SPO_ALG_CP / SPO_ALG_SP */
   double L_norm;             /* <=0: reference constants 10.0 (cpock.jl:63) / 3.28 (spock.jl:64) */
+  const int *w;              /* node_info[j].w supplied by the caller (1-based mode, n entries, entry 0 ignored), or NULL: the
+                                generator's (j % d) + 1 (scenario_tree.jl:77) */
   int n_rms;                 /* 0/1: uniform risk measures; n_non_leaf: b (ny each) and ls_matrix ((ny+2d)^2 each) hold one entry
                                 per non-leaf node, back to back (rms[i].b implicit_l.jl:219,427; ls_matrix[i] cpock.jl:125-128) */
 } spo_problem;

@@ -46,6 +46,7 @@ class SpkProblem(C.Structure):
         ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.POINTER(C.c_uint8)),
         ("n_devices", C.c_int32), ("devices", _i32p),
         ("n_rms", C.c_int32),
+        ("mode_of_node", _i32p),
     ]
 
 
@@ -153,8 +154,12 @@ def make_problem(flat, algorithm: int, L_norm: float = 0.0, factor_mode: int = F
         flat.N, flat.d, flat.nx, flat.nu, dptr(A), dptr(B), flat.cost_dense, flat.n_sqrtQ, dptr(sQ), dptr(sR),
         flat.n_sqrtQN, dptr(sQN), flat.ny, dptr(E), dptr(F), dptr(b), len(ct), ct.ctypes.data_as(_i32p),
         cd.ctypes.data_as(_i32p), flat.x_min, flat.x_max, flat.u_min, flat.u_max, int(algorithm), float(L_norm),
-        int(factor_mode), int(device), int(rank), int(world_size), cid, 0, None, int(getattr(flat, "n_rms", 1)),
+        int(factor_mode), int(device), int(rank), int(world_size), cid, 0, None, int(getattr(flat, "n_rms", 1)), None,
     )
+    if getattr(flat, "w", None) is not None:
+        wv = np.ascontiguousarray(flat.w, dtype=np.int32)
+        keep.append(wv)
+        p.mode_of_node = wv.ctypes.data_as(_i32p)
     if devices is not None and len(devices) > 0:
         dv = np.ascontiguousarray(devices, dtype=np.int32)
         keep.append(dv)

@@ -266,6 +266,11 @@ SPK_D int spk_child_mode_dev(int d, int c) {  // mode of child ordinal c: (j0 + 
   while (m >= d) m -= d;
   return m;
 }
+// the same with a caller-supplied mode map (spk_problem.mode_of_node): child c of the family whose first child is cfirst
+SPK_D int spk_mode_c(const SpkPtrs &P, int d, long cfirst, int c) {
+  if (__builtin_expect(P.w != nullptr, 0)) return P.w[cfirst + c];
+  return spk_child_mode_dev(d, c);
+}
 
 SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
   const long SA = spk_slices(T, D.nx), SB = spk_slices(T, D.nu), nw = (T + 31) / 32;
@@ -420,7 +425,7 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
       const SpkItem it = (o == tid) ? itB : spk_make_item(o, nu, SB, nx, nu);
       double acc = 0.0;
       for (int c = 0; c < d; ++c)
-        acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_child_mode_dev(d, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
+        acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_mode_c(P, d, cfirst, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
       partB[o] = acc;
     }
     if constexpr (PAIR) {
@@ -681,7 +686,7 @@ SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
       if (active) {
         if (r < NU_) acc = spk_dot_fixed<PA>(mK + rr, NU_, xb, ss * PA, HC);
         else acc = spk_dot_fixed<PA>(mABK + (long)c * D.abk_stride + rr, NX_, xb, ss * PA, HC) +
-                   spk_dot_fixed<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, NX_, ds, ss * PER_U, NU_);
+                   spk_dot_fixed<PER_U>(P.B + (long)spk_mode_c(P, d, cfirst, c) * nx * nu + rr, NX_, ds, ss * PER_U, NU_);
       }
       SPK_SYNCTHREADS();  // the first half is consumed: refill it while the second half is processed
       if (more && tid == 0) fetch_half(i0 + gridDim.x, 0);
@@ -710,7 +715,7 @@ SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
           acc = spk_dot_any<PER_X>(mK + rr, nu, xb, it.m0, it.m1, nx);
         } else {
           acc = spk_dot_any<PER_X>(mABK + (long)c * D.abk_stride + rr, nx, xb, it.m0, it.m1, nx) +
-                spk_dot_any<PER_U>(P.B + (long)spk_child_mode_dev(d, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
+                spk_dot_any<PER_U>(P.B + (long)spk_mode_c(P, d, cfirst, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
         }
         part[o] = acc;
       }

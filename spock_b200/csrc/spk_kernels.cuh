@@ -173,7 +173,7 @@ SPK_KERNEL void spk_k_s1_bwd(SpkDims D, SpkPtrs P, int t, int children_are_leave
   for (int k = lane; k < nu; k += LANES) {
     double s = 0.0;
     for (int c = 0; c < d; ++c) {
-      const double *Bt = P.Bt + (long)((d * i0 + 1 + c + 1) % d) * nx * nu;
+      const double *Bt = P.Bt + (long)spk_mode(P, d, (long)d * i0 + 1 + c) * nx * nu;
       const double *qj = qc + c * nx;
       double acc = 0.0;
       for (int r = 0; r < nx; ++r) acc += Bt[k + (long)r * nu] * qj[r];
@@ -245,7 +245,7 @@ SPK_KERNEL void spk_k_s1_fwd(SpkDims D, SpkPtrs P, int t, double *__restrict__ a
     const long j0 = (long)d * i0 + 1 + c;
     const long aslot = D.per_node ? (j0 - 1) : ((long)t * d + c);
     const double *Am = P.ABK + aslot * D.abk_stride;
-    const double *Bw = P.B + (long)((j0 + 1) % d) * nx * nu;
+    const double *Bw = P.B + (long)spk_mode(P, d, j0) * nx * nu;
     for (int r = lane; r < nx; r += LANES) {
       double acc = 0.0;
       for (int m = 0; m < nx; ++m) acc += Am[r + (long)m * nx] * xs[m];

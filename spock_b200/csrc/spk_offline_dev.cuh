@@ -17,6 +17,7 @@ struct SpkRiccatiArgs {
   double *ws;                                   // scratch, spk_riccati_ws_doubles
   int *fail;                                    // set to 1 + stage when I + sum B'PB is not positive definite
 };
+#define SPK_RICCATI_MAX_D 32
 SPK_HD long spk_riccati_ws_doubles(int d, int nx, int nu) {
   // PB (d nx nu), PA / PABK (d nx nx), ABK (d nx nx), sum_r, Rt, L (nu nu each), sum_k (nu nx), Pt (nx nx)
   return (long)d * nx * nu + 2L * d * nx * nx + 3L * nu * nu + (long)nu * nx + (long)nx * nx;
@@ -36,116 +37,159 @@ SPK_D void spk_cta_matmul(double *C, const double *A, bool a_trans, const double
 }
 SPK_D int spk_child_mode_off(int d, int c) { return (c + 2) % d; }  // Julia w(j) = (j % d) + 1 with j = 2 + c (mod d)
 
-SPK_KERNEL void spk_k_riccati(SpkRiccatiArgs R) {
-  const int nx = R.nx, nu = R.nu, d = R.d, S = R.N - 1;
-  const int tid = threadIdx.x, T = blockDim.x;
-  double *PB = R.ws, *PA = PB + (long)d * nx * nu, *ABKs = PA + (long)d * nx * nx, *sum_r = ABKs + (long)d * nx * nx, *Rt = sum_r + nu * nu,
+// One step of the recursion for ONE family (a non-leaf node and its d children), by all threads of the CTA:
+// Pc[c] = P of child c (NULL: the child is a leaf, P = I, implicit_l.jl:67-69), mode[c] = its dynamics mode (0-based).
+// Writes P of the node (oP, may be NULL) and the factor slots oABK / oABKt (d slots of abk_stride), oK, oKt, oG, oRinv.
+SPK_D void spk_riccati_family(int nx, int nu, int d, long abk_stride, const double *A, const double *B, const double *const *Pc, const int *mode,
+                              double *ws, double *oP, double *oABK, double *oABKt, double *oK, double *oKt, double *oG, double *oRinv,
+                              int *fail, int fail_code, int tid, int T) {
+  double *PB = ws, *PA = PB + (long)d * nx * nu, *ABKs = PA + (long)d * nx * nx, *sum_r = ABKs + (long)d * nx * nx, *Rt = sum_r + nu * nu,
          *L = Rt + nu * nu, *sum_k = L + nu * nu, *Pt = sum_k + nu * nx;
-  // leaves: P = I (implicit_l.jl:67-69)
-  double *Pleaf = R.P + (long)(R.N - 1) * nx * nx;
+  for (int c = 0; c < d; ++c) {  // :76-79
+    const double *Bw = B + (long)mode[c] * nx * nu, *Aw = A + (long)mode[c] * nx * nx;
+    if (Pc[c]) {
+      spk_cta_matmul(PB + (long)c * nx * nu, Pc[c], false, Bw, nx, nx, nu, false, tid, T);
+      spk_cta_matmul(PA + (long)c * nx * nx, Pc[c], false, Aw, nx, nx, nx, false, tid, T);
+    } else {  // leaf child: P = I
+      for (int idx = tid; idx < nx * nu; idx += T) PB[(long)c * nx * nu + idx] = Bw[idx];
+      for (int idx = tid; idx < nx * nx; idx += T) PA[(long)c * nx * nx + idx] = Aw[idx];
+    }
+  }
+  SPK_SYNCTHREADS();
+  for (int c = 0; c < d; ++c) {
+    const double *Bw = B + (long)mode[c] * nx * nu;
+    spk_cta_matmul(sum_r, Bw, true, PB + (long)c * nx * nu, nu, nx, nu, c > 0, tid, T);
+    spk_cta_matmul(sum_k, Bw, true, PA + (long)c * nx * nx, nu, nx, nx, c > 0, tid, T);
+  }
+  SPK_SYNCTHREADS();
+  for (int idx = tid; idx < nu * nu; idx += T) {  // :82-84 symmetrise, add I
+    const int i = idx % nu, j = idx / nu;
+    Rt[idx] = (i == j ? 1.0 : 0.0) + 0.5 * (sum_r[i + j * nu] + sum_r[j + i * nu]);
+    L[idx] = 0.0;
+  }
+  SPK_SYNCTHREADS();
+  for (int j = 0; j < nu; ++j) {  // lower Cholesky factor, column by column
+    if (tid == 0) {
+      double djj = Rt[j + j * nu];
+      for (int k = 0; k < j; ++k) djj -= L[j + k * nu] * L[j + k * nu];
+      if (!(djj > 0.0)) {
+        *fail = fail_code;
+        djj = 1.0;
+      }
+      L[j + j * nu] = sqrt(djj);
+    }
+    SPK_SYNCTHREADS();
+    const double djj = L[j + j * nu];
+    for (int i = j + 1 + tid; i < nu; i += T) {
+      double s = Rt[i + j * nu];
+      for (int k = 0; k < j; ++k) s -= L[i + k * nu] * L[j + k * nu];
+      L[i + j * nu] = s / djj;
+    }
+    SPK_SYNCTHREADS();
+  }
+  // K = -(L L')^{-1} sum_k (:86) and Rinv = (L L')^{-1}: one column per thread
+  for (int col = tid; col < nx + nu; col += T) {
+    double *X = col < nx ? oK + (long)col * nu : oRinv + (long)(col - nx) * nu;
+    for (int i = 0; i < nu; ++i) X[i] = col < nx ? -sum_k[i + (long)col * nu] : (i == col - nx ? 1.0 : 0.0);
+    for (int i = 0; i < nu; ++i) {
+      double s = X[i];
+      for (int k = 0; k < i; ++k) s -= L[i + k * nu] * X[k];
+      X[i] = s / L[i + i * nu];
+    }
+    for (int i = nu - 1; i >= 0; --i) {
+      double s = X[i];
+      for (int k = i + 1; k < nu; ++k) s -= L[k + i * nu] * X[k];
+      X[i] = s / L[i + i * nu];
+    }
+  }
+  SPK_SYNCTHREADS();
+  for (int idx = tid; idx < nu * nu; idx += T) {  // exact symmetry of Rinv
+    const int i = idx % nu, j = idx / nu;
+    if (i > j) {
+      const double m = 0.5 * (oRinv[i + j * nu] + oRinv[j + i * nu]);
+      oRinv[i + j * nu] = m;
+      oRinv[j + i * nu] = m;
+    }
+  }
+  for (int idx = tid; idx < nu * nx; idx += T) {  // K' (nx x nu)
+    const int i = idx % nu, j = idx / nu;
+    oKt[j + (long)i * nx] = oK[idx];
+  }
+  // P = I + K'K + sum_c ABK_c' P_c ABK_c (:89-93); G = sum_c ABK_c' P_c B_w
+  spk_cta_matmul(Pt, oK, true, oK, nx, nu, nx, false, tid, T);
+  for (int c = 0; c < d; ++c)  // ABK_c = A_w + B_w K
+    spk_cta_matmul(ABKs + (long)c * nx * nx, B + (long)mode[c] * nx * nu, false, oK, nx, nu, nx, false, tid, T);
+  SPK_SYNCTHREADS();
+  for (int idx = tid; idx < nx * nx; idx += T) Pt[idx] += (idx % nx == idx / nx) ? 1.0 : 0.0;
+  for (int c = 0; c < d; ++c) {
+    double *ABKc = ABKs + (long)c * nx * nx;
+    const double *Aw = A + (long)mode[c] * nx * nx;
+    for (int idx = tid; idx < nx * nx; idx += T) ABKc[idx] += Aw[idx];
+  }
+  SPK_SYNCTHREADS();
+  for (int c = 0; c < d; ++c) {  // PA is free: reuse it for P_c ABK_c
+    if (Pc[c]) spk_cta_matmul(PA + (long)c * nx * nx, Pc[c], false, ABKs + (long)c * nx * nx, nx, nx, nx, false, tid, T);
+    else
+      for (int idx = tid; idx < nx * nx; idx += T) PA[(long)c * nx * nx + idx] = ABKs[(long)c * nx * nx + idx];
+  }
+  SPK_SYNCTHREADS();
+  for (int c = 0; c < d; ++c) {
+    const double *ABKc = ABKs + (long)c * nx * nx;
+    spk_cta_matmul(Pt, ABKc, true, PA + (long)c * nx * nx, nx, nx, nx, true, tid, T);
+    spk_cta_matmul(oG, ABKc, true, PB + (long)c * nx * nu, nx, nx, nu, c > 0, tid, T);
+    double *o = oABK + (long)c * abk_stride, *ot = oABKt + (long)c * abk_stride;
+    for (int idx = tid; idx < nx * nx; idx += T) {
+      const int i = idx % nx, j = idx / nx;
+      o[idx] = ABKc[idx];
+      ot[j + (long)i * nx] = ABKc[idx];
+    }
+  }
+  SPK_SYNCTHREADS();
+  if (oP)
+    for (int idx = tid; idx < nx * nx; idx += T) oP[idx] = Pt[idx];
+  SPK_SYNCTHREADS();
+}
+
+// per stage: one CTA walks the N-1 parent stages (all nodes of a stage share their factors with the generator's mode map)
+SPK_KERNEL void spk_k_riccati(SpkRiccatiArgs R) {
+  const int nx = R.nx, d = R.d, S = R.N - 1;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double *Pleaf = R.P + (long)(R.N - 1) * nx * nx;  // leaves: P = I (implicit_l.jl:67-69); kept in the table for spk_get_factors
   for (int idx = tid; idx < nx * nx; idx += T) Pleaf[idx] = (idx % nx == idx / nx) ? 1.0 : 0.0;
   SPK_SYNCTHREADS();
   for (int t = S - 1; t >= 0; --t) {
-    const double *Pn = R.P + (long)(t + 1) * nx * nx;
-    for (int c = 0; c < d; ++c) {  // :76-79
-      const int w = spk_child_mode_off(d, c);
-      spk_cta_matmul(PB + (long)c * nx * nu, Pn, false, R.B + (long)w * nx * nu, nx, nx, nu, false, tid, T);
-      spk_cta_matmul(PA + (long)c * nx * nx, Pn, false, R.A + (long)w * nx * nx, nx, nx, nx, false, tid, T);
-    }
-    SPK_SYNCTHREADS();
+    const double *Pc[SPK_RICCATI_MAX_D];
+    int mode[SPK_RICCATI_MAX_D];
     for (int c = 0; c < d; ++c) {
-      const int w = spk_child_mode_off(d, c);
-      spk_cta_matmul(sum_r, R.B + (long)w * nx * nu, true, PB + (long)c * nx * nu, nu, nx, nu, c > 0, tid, T);
-      spk_cta_matmul(sum_k, R.B + (long)w * nx * nu, true, PA + (long)c * nx * nx, nu, nx, nx, c > 0, tid, T);
+      Pc[c] = R.P + (long)(t + 1) * nx * nx;
+      mode[c] = spk_child_mode_off(d, c);
     }
-    SPK_SYNCTHREADS();
-    for (int idx = tid; idx < nu * nu; idx += T) {  // :82-84 symmetrise, add I
-      const int i = idx % nu, j = idx / nu;
-      Rt[idx] = (i == j ? 1.0 : 0.0) + 0.5 * (sum_r[i + j * nu] + sum_r[j + i * nu]);
-      L[idx] = 0.0;
-    }
-    SPK_SYNCTHREADS();
-    for (int j = 0; j < nu; ++j) {  // lower Cholesky factor, column by column
-      if (tid == 0) {
-        double djj = Rt[j + j * nu];
-        for (int k = 0; k < j; ++k) djj -= L[j + k * nu] * L[j + k * nu];
-        if (!(djj > 0.0)) {
-          *R.fail = 1 + t;
-          djj = 1.0;
-        }
-        L[j + j * nu] = sqrt(djj);
-      }
-      SPK_SYNCTHREADS();
-      const double djj = L[j + j * nu];
-      for (int i = j + 1 + tid; i < nu; i += T) {
-        double s = Rt[i + j * nu];
-        for (int k = 0; k < j; ++k) s -= L[i + k * nu] * L[j + k * nu];
-        L[i + j * nu] = s / djj;
-      }
-      SPK_SYNCTHREADS();
-    }
-    // K = -(L L')^{-1} sum_k (:86) and Rinv = (L L')^{-1}: one column per thread
-    double *Kt_ = R.K + (long)t * R.k_stride, *Ri = R.Rinv + (long)t * R.r_stride;
-    for (int col = tid; col < nx + nu; col += T) {
-      double *X = col < nx ? Kt_ + (long)col * nu : Ri + (long)(col - nx) * nu;
-      for (int i = 0; i < nu; ++i) X[i] = col < nx ? -sum_k[i + (long)col * nu] : (i == col - nx ? 1.0 : 0.0);
-      for (int i = 0; i < nu; ++i) {
-        double s = X[i];
-        for (int k = 0; k < i; ++k) s -= L[i + k * nu] * X[k];
-        X[i] = s / L[i + i * nu];
-      }
-      for (int i = nu - 1; i >= 0; --i) {
-        double s = X[i];
-        for (int k = i + 1; k < nu; ++k) s -= L[k + i * nu] * X[k];
-        X[i] = s / L[i + i * nu];
-      }
-    }
-    SPK_SYNCTHREADS();
-    for (int idx = tid; idx < nu * nu; idx += T) {  // exact symmetry of Rinv (upper triangle <- mean)
-      const int i = idx % nu, j = idx / nu;
-      if (i > j) {
-        const double m = 0.5 * (Ri[i + j * nu] + Ri[j + i * nu]);
-        Ri[i + j * nu] = m;
-        Ri[j + i * nu] = m;
-      }
-    }
-    for (int idx = tid; idx < nu * nx; idx += T) {  // K' (nx x nu)
-      const int i = idx % nu, j = idx / nu;
-      R.Kt[(long)t * R.k_stride + j + (long)i * nx] = Kt_[idx];
-    }
-    // P_t = I + K'K + sum_c ABK_c' P ABK_c (:89-93); G = sum_c ABK_c' P B_w
-    spk_cta_matmul(Pt, Kt_, true, Kt_, nx, nu, nx, false, tid, T);
-    for (int c = 0; c < d; ++c) {  // ABK_c = A_w + B_w K
-      const int w = spk_child_mode_off(d, c);
-      spk_cta_matmul(ABKs + (long)c * nx * nx, R.B + (long)w * nx * nu, false, Kt_, nx, nu, nx, false, tid, T);
-    }
-    SPK_SYNCTHREADS();
-    for (int idx = tid; idx < nx * nx; idx += T) Pt[idx] += (idx % nx == idx / nx) ? 1.0 : 0.0;
+    spk_riccati_family(nx, R.nu, d, R.abk_stride, R.A, R.B, Pc, mode, R.ws, R.P + (long)t * nx * nx, R.ABK + (long)t * d * R.abk_stride,
+                       R.ABKt + (long)t * d * R.abk_stride, R.K + (long)t * R.k_stride, R.Kt + (long)t * R.k_stride, R.G + (long)t * R.k_stride,
+                       R.Rinv + (long)t * R.r_stride, R.fail, 1 + t, tid, T);
+  }
+}
+
+// per node (a caller-supplied mode map makes the factors of the nodes of a stage differ: `ricatti_offline` as the reference
+// runs it, implicit_l.jl:71-95, one node at a time -- here one CTA per node of a level, level by level from the leaves up).
+// Pchild: P of the nodes of level t+1 in level order (NULL: they are leaves), Pout: P of the nodes of level t.
+// Factor slots: node i0 -> slot i0 (single GPU).  ws: gridDim.x scratch areas of ws_stride doubles.
+SPK_KERNEL void spk_k_riccati_level(SpkRiccatiArgs R, int t, long first0, long count, const double *Pchild, double *Pout, const int *w,
+                                    long ws_stride) {
+  const int nx = R.nx, d = R.d;
+  const int tid = threadIdx.x, T = blockDim.x;
+  double *ws = R.ws + (long)blockIdx.x * ws_stride;
+  for (long p = blockIdx.x; p < count; p += gridDim.x) {
+    const long i0 = first0 + p, c0 = (long)d * i0 + 1;
+    const double *Pc[SPK_RICCATI_MAX_D];
+    int mode[SPK_RICCATI_MAX_D];
     for (int c = 0; c < d; ++c) {
-      const int w = spk_child_mode_off(d, c);
-      double *ABKc = ABKs + (long)c * nx * nx;
-      for (int idx = tid; idx < nx * nx; idx += T) ABKc[idx] += R.A[(long)w * nx * nx + idx];
+      Pc[c] = Pchild ? Pchild + ((long)d * p + c) * nx * nx : nullptr;
+      mode[c] = w[c0 + c];
     }
-    SPK_SYNCTHREADS();
-    for (int c = 0; c < d; ++c)  // PA is free: reuse it for P ABK_c
-      spk_cta_matmul(PA + (long)c * nx * nx, Pn, false, ABKs + (long)c * nx * nx, nx, nx, nx, false, tid, T);
-    SPK_SYNCTHREADS();
-    double *Gt = R.G + (long)t * R.k_stride;
-    for (int c = 0; c < d; ++c) {
-      const double *ABKc = ABKs + (long)c * nx * nx;
-      spk_cta_matmul(Pt, ABKc, true, PA + (long)c * nx * nx, nx, nx, nx, true, tid, T);
-      spk_cta_matmul(Gt, ABKc, true, PB + (long)c * nx * nu, nx, nx, nu, c > 0, tid, T);
-      double *o = R.ABK + ((long)t * d + c) * R.abk_stride, *ot = R.ABKt + ((long)t * d + c) * R.abk_stride;
-      for (int idx = tid; idx < nx * nx; idx += T) {
-        const int i = idx % nx, j = idx / nx;
-        o[idx] = ABKc[idx];
-        ot[j + (long)i * nx] = ABKc[idx];
-      }
-    }
-    SPK_SYNCTHREADS();
-    double *Pout = R.P + (long)t * nx * nx;
-    for (int idx = tid; idx < nx * nx; idx += T) Pout[idx] = Pt[idx];
-    SPK_SYNCTHREADS();
+    spk_riccati_family(nx, R.nu, d, R.abk_stride, R.A, R.B, Pc, mode, ws, Pout + p * (long)nx * nx, R.ABK + (long)d * i0 * R.abk_stride,
+                       R.ABKt + (long)d * i0 * R.abk_stride, R.K + i0 * R.k_stride, R.Kt + i0 * R.k_stride, R.G + i0 * R.k_stride,
+                       R.Rinv + i0 * R.r_stride, R.fail, 1 + t, tid, T);
   }
 }
 

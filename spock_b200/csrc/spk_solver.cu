@@ -167,6 +167,7 @@ struct spk_handle {
   SpkComm comm;
   int rank = 0, world = 1, t_cut = 0;
   long m_sub = 1;
+  bool custom_modes = false;   // spk_problem.mode_of_node: per-node Riccati recursion, no per-stage table
   bool scratch_ready = false;  // z_old, delta, xi_1/xi_2, xi and the modular operators' workspaces exist (ensure_scratch)
   bool in_group = false;  // sub-handle of a device group
   // per-node factors under the partition: only this rank's families are stored, packed level by level (replicated top
@@ -1507,6 +1508,10 @@ static int check_problem(const spk_problem *p) {
     if (p->rank < 0 || p->rank >= p->world_size) return fail(SPK_ERR_INVALID, "rank out of range");
   }
   if (p->n_rms < 0) return fail(SPK_ERR_INVALID, "n_rms must not be negative");
+  if (p->mode_of_node) {
+    if (p->factor_mode != SPK_FACTORS_PER_NODE) return fail(SPK_ERR_INVALID, "a mode map needs factor_mode = SPK_FACTORS_PER_NODE");
+    if (p->world_size > 1 || p->n_devices > 1) return fail(SPK_ERR_INVALID, "a mode map is single-GPU");
+  }
   if (p->n_devices > 1) {
     if (!p->devices) return fail(SPK_ERR_INVALID, "n_devices > 1 needs the devices array");
     if (p->world_size > 1) return fail(SPK_ERR_INVALID, "n_devices > 1 (one process) and world_size > 1 (one process per GPU) are exclusive");
@@ -1666,7 +1671,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   // The offline phase (Riccati recursion, kernel projectors) runs on the device (spk_offline_dev.cuh); SPK_HOST_OFFLINE=1
   // selects the host versions (spk_offline.cpp), which the tests use as the cross-check.
   const char *ho = getenv("SPK_HOST_OFFLINE");
-  const bool host_offline = ho && ho[0] == '1';
+  const bool host_offline = ho && ho[0] == '1' && !p->mode_of_node;  // (a mode map: the per-node recursion exists on the device only)
   const long n_rms = p->n_rms > 1 ? p->n_rms : 1;
   if (n_rms != 1 && n_rms != nnl) return fail(SPK_ERR_INVALID, "n_rms must be 1 (uniform risk measures) or n_non_leaf");
   D.rms_per_node = n_rms > 1 ? 1 : 0;
@@ -1695,6 +1700,22 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   SPK_TRY(upload(h, &tmp, p->A, (long)d * nx * nx)); h->P.A = tmp;
   SPK_TRY(upload(h, &tmp, p->B, (long)d * nx * nu)); h->P.B = tmp;
   h->B_host.assign(p->B, p->B + (size_t)d * nx * nu);
+  h->P.w = nullptr;
+  if (p->mode_of_node) {  // node_info[j].w (1-based) -> 0-based modes on the device
+    std::vector<int> w0((size_t)n, 0);
+    for (long j = 1; j < n; ++j) {
+      const int w = p->mode_of_node[j];
+      if (w < 1 || w > d) return fail(SPK_ERR_INVALID, "mode_of_node entries must be in 1..d");
+      w0[(size_t)j] = w - 1;
+    }
+    void *q = nullptr;
+    SPK_TRY(rt_malloc(&q, sizeof(int) * (size_t)n));
+    h->allocs.push_back(q);
+    h->bytes += (int64_t)(sizeof(int) * (size_t)n);
+    SPK_TRY(rt_h2d(q, w0.data(), sizeof(int) * (size_t)n, h->stream));
+    h->P.w = (const int *)q;
+    h->custom_modes = true;
+  }
   std::vector<double> Bt((size_t)d * nx * nu);
   for (int w = 0; w < d; ++w)
     for (int r = 0; r < nx; ++r)
@@ -1749,6 +1770,58 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
   //      (all of them on a single GPU), packed level by level
   SpkFactorTable &T = h->table;
   double *tABK, *tABKt, *tK, *tKt, *tG, *tR;
+  if (h->custom_modes) {
+    // ---- ricatti_offline per node (implicit_l.jl:71-95), batched on the device: one CTA per node, level by level from the
+    //      leaves up; P is kept for two adjacent levels only.  The factor slots ARE the per-node arrays (slot = node).
+    if (T.ABK.empty()) spk_table_init(p->N, d, nx, nu, T);
+    D.abk_stride = T.abk_stride; D.k_stride = T.k_stride; D.r_stride = T.r_stride;
+    double *nABK, *nABKt, *nK, *nKt, *nG, *nR, *ws = nullptr, *flag = nullptr;
+    SPK_TRY(dev_alloc(h, &nABK, (n - 1) * D.abk_stride, false));
+    SPK_TRY(dev_alloc(h, &nABKt, (n - 1) * D.abk_stride, false));
+    SPK_TRY(dev_alloc(h, &nK, nnl * D.k_stride, false));
+    SPK_TRY(dev_alloc(h, &nKt, nnl * D.k_stride, false));
+    SPK_TRY(dev_alloc(h, &nG, nnl * D.k_stride, false));
+    SPK_TRY(dev_alloc(h, &nR, nnl * D.r_stride, false));
+    SPK_TRY(dev_alloc(h, &flag, 1));
+    const long ws_stride = (spk_riccati_ws_doubles(d, nx, nu) + 1) & ~1L;
+    const long widest = spk_level_count(d, D.N - 2);
+    const long ctas = SPK_EMU ? std::min(widest, 4L) : std::min(widest, (long)h->num_sms * 2);
+    void *wsv = nullptr, *pa = nullptr, *pb = nullptr;  // temporaries: freed after the recursion
+    const size_t pbytes = sizeof(double) * (size_t)std::max(1L, spk_level_count(d, std::max(D.N - 3, 0))) * nx * nx;
+    const size_t pbytes2 = sizeof(double) * (size_t)widest * nx * nx;
+    SPK_TRY(rt_malloc(&wsv, sizeof(double) * (size_t)(ws_stride * ctas)));
+    if (rt_malloc(&pa, pbytes2) != SPK_OK) { rt_free(wsv); return SPK_ERR_ALLOC; }
+    if (rt_malloc(&pb, pbytes) != SPK_OK) { rt_free(wsv); rt_free(pa); return SPK_ERR_ALLOC; }
+    ws = (double *)wsv;
+    SpkRiccatiArgs R;
+    R.N = p->N; R.d = d; R.nx = nx; R.nu = nu;
+    R.abk_stride = D.abk_stride; R.k_stride = D.k_stride; R.r_stride = D.r_stride;
+    R.A = h->P.A; R.B = h->P.B;
+    R.P = nullptr; R.ABK = nABK; R.ABKt = nABKt; R.K = nK; R.Kt = nKt; R.G = nG; R.Rinv = nR; R.ws = ws;
+    R.fail = reinterpret_cast<int *>(flag);
+    int rc = SPK_OK;
+    double *Pcur = (double *)pa, *Pnext = (double *)pb;  // Pcur: level t (written), Pnext: level t+1 (read); sizes alternate
+    const double *Pchild = nullptr;                       // leaves: P = I
+    for (int t = D.N - 2; t >= 0 && rc == SPK_OK; --t) {
+      const long cnt = spk_level_count(d, t);
+      // level N-2 (widest) goes to the large buffer, then the two buffers alternate (each level fits: counts shrink by d)
+      double *Pout = ((D.N - 2 - t) % 2 == 0) ? (double *)pa : (double *)pb;
+      SPK_LAUNCH(spk_k_riccati_level, (unsigned)std::max(1L, std::min(cnt, ctas)), SPK_EMU ? 1 : 256, 0, h->stream, R, t,
+                 spk_level_first0(d, t), cnt, Pchild, Pout, h->P.w, ws_stride);
+      h->launches++;
+      rc = rt_launch_check();
+      Pchild = Pout;
+    }
+    (void)Pcur; (void)Pnext;
+    int bad = 0;
+    if (rc == SPK_OK) rc = rt_d2h(&bad, flag, sizeof(int), h->stream);
+    rt_free(wsv); rt_free(pa); rt_free(pb);
+    SPK_TRY(rc);
+    if (bad) return fail(SPK_ERR_INVALID, "Riccati recursion: I + sum B'PB is not positive definite at stage " + std::to_string(bad - 1));
+    h->P.ABK = nABK; h->P.ABKt = nABKt; h->P.K = nK; h->P.Kt = nKt; h->P.G = nG; h->P.Rinv = nR;
+    h->D_tab = D; h->P_tab = h->P;  // the modular kernels read the per-node slots as well
+    for (int t = 0; t <= D.N - 2; ++t) h->fac_start[t] = spk_level_first0(d, t);
+  } else {
   if (host_offline) {
     SPK_TRY(upload(h, &tABK, T.ABK.data(), (long)T.ABK.size()));
     SPK_TRY(upload(h, &tABKt, T.ABKt.data(), (long)T.ABKt.size()));
@@ -1821,6 +1894,7 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
       h->P.ABK = nABK; h->P.ABKt = nABKt; h->P.K = nK; h->P.Kt = nKt; h->P.G = nG; h->P.Rinv = nR;
     }
   }
+  }  // (!custom_modes)
 
   // ---- state (cpock.jl:83-103)
   const long nr = D.nz + D.nv;
@@ -2250,6 +2324,14 @@ int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, dou
   while (t + 1 < D.N && i0 >= spk_level_first0(D.d, t + 1)) ++t;
   const SpkFactorTable &T = h->table;
   const size_t nx2 = (size_t)D.nx * D.nx;
+  if (h->custom_modes) {  // per-node recursion: the slots of node i live on the device; P is not kept
+    if (Pm) return fail(SPK_ERR_INVALID, "P is not kept with a mode map (only two levels of it exist during the recursion)");
+    if (ABK && i0 >= 1) SPK_TRY(rt_d2h(ABK, h->P.ABK + (i0 - 1) * D.abk_stride, sizeof(double) * nx2, h->stream));
+    if (i0 < D.nnl) {
+      if (K) SPK_TRY(rt_d2h(K, h->P.K + i0 * D.k_stride, sizeof(double) * D.nu * D.nx, h->stream));
+      if (Rinv) SPK_TRY(rt_d2h(Rinv, h->P.Rinv + i0 * D.r_stride, sizeof(double) * D.nu * D.nu, h->stream));
+    }
+  } else {
   if (Pm) std::copy(T.P.begin() + t * nx2, T.P.begin() + (t + 1) * nx2, Pm);
   if (ABK && i0 >= 1) {
     const int c = (int)((i0 - 1) % D.d);
@@ -2259,6 +2341,7 @@ int spk_get_factors(const spk_handle *h, int64_t i, double *Pm, double *ABK, dou
   if (i0 < D.nnl) {
     if (K) std::copy(T.K.begin() + t * T.k_stride, T.K.begin() + t * T.k_stride + (size_t)D.nu * D.nx, K);
     if (Rinv) std::copy(T.Rinv.begin() + t * T.r_stride, T.Rinv.begin() + t * T.r_stride + (size_t)D.nu * D.nu, Rinv);
+  }
   }
   if (ls) {
     const size_t nls2 = (size_t)D.nls * D.nls, off = (D.rms_per_node && i0 < D.nnl) ? nls2 * (size_t)i0 : 0;

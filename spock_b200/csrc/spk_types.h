@@ -31,6 +31,7 @@ struct SpkPtrs {
   const double *ABK, *ABKt;              // closed-loop matrices A_w + B_w K and their transposes
   const double *K, *Kt, *Rinv, *G;       // feedback gain (nu*nx), its transpose, Rtilde^{-1}, sum ABK' P B
   const double *x0;
+  const int *w;                          // 0-based dynamics mode of every node, or NULL: the generator's map (j % d) + 1 (scenario_tree.jl:77)
 };
 
 SPK_HD long spk_level_first0(int d, int t) {
@@ -79,6 +80,9 @@ SPK_HD long long spk_bits_nn(double a) {
 #endif
 }
 SPK_HD double spk_max_nn(double a, double b) { return spk_bits_nn(a) >= spk_bits_nn(b) ? a : b; }
+
+// dynamics mode (0-based) of node j0: node_info[j].w - 1 (scenario_tree.jl:77), or a caller-supplied map
+SPK_HD int spk_mode(const SpkPtrs &P, int d, long j0) { return P.w ? P.w[j0] : (int)((j0 + 1) % d); }
 
 // risk vector b_i and kernel projector ls_matrix[i] of non-leaf node i0 (uniform risk measures: one copy for all nodes)
 SPK_HD const double *spk_b(const SpkDims &D, const SpkPtrs &P, long i0) { return D.rms_per_node ? P.b + i0 * D.ny : P.b; }

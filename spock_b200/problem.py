@@ -227,6 +227,7 @@ class FlatProblem:
     # kept for host-side use (not passed to C)
     E2d: np.ndarray = field(repr=False, default=None)
     F2d: np.ndarray = field(repr=False, default=None)
+    w: np.ndarray = field(repr=False, default=None)     # caller-supplied node_info[j].w (1-based, length n), or None
     n_rms: int = 1                                      # 1 = uniform risk measures, n_non_leaf = one (E, F, b) per node
     rms_list: list = field(repr=False, default=None)    # the per-node RiskMeasure objects when n_rms > 1
 
@@ -337,6 +338,7 @@ def flatten_problem(scen_tree: ScenarioTree, cost: Cost, dynamics: Dynamics, rms
         E=_colmajor(E) if uniform else np.concatenate([_colmajor(np.asarray(r.E, float)) for r in rms]),
         F=_colmajor(F) if uniform else np.concatenate([_colmajor(np.asarray(r.F, float)) for r in rms]),
         b=np.asarray(rm.b, float).copy() if uniform else np.concatenate([np.asarray(r.b, float) for r in rms]),
+        w=None if getattr(scen_tree, "w_override", None) is None else scen_tree.w_array(),
         n_rms=1 if uniform else len(rms),
         rms_list=None if uniform else list(rms),
         cone_type=np.array([c.type_id for c in rm.K.subcones], dtype=np.int32),

@@ -84,7 +84,7 @@ class _NodeInfo:
         return ScenarioTreeNodeInfo(
             x=list(range((i - 1) * t.nx + 1, i * t.nx + 1)),
             u=list(range((i - 1) * t.nu + 1, i * t.nu + 1)) if i <= t.n_non_leaf_nodes else None,
-            w=(i % t.d) + 1 if i > 1 else None,
+            w=(int(t.w_override[i - 1]) if t.w_override is not None else (i % t.d) + 1) if i > 1 else None,
             s=i,
             tau=i if i > 1 else None,
         )
@@ -104,6 +104,9 @@ class ScenarioTree:
     leaf_node_min_index: int
     leaf_node_max_index: int
     min_index_per_timestep: List[int]
+    # node_info[j].w supplied by the caller instead of the generator's (j % d) + 1 (the reference's node_info vector is a
+    # plain mutable Vector, scenario_tree.jl:73-81): 1-based modes, length n, entry 0 (the root) ignored
+    w_override: Optional[np.ndarray] = None
 
     @property
     def child_mapping(self) -> _ChildMapping:
@@ -129,8 +132,11 @@ class ScenarioTree:
         return a
 
     def w_array(self) -> np.ndarray:
-        j = np.arange(1, self.n + 1, dtype=np.int64)
-        w = (j % self.d) + 1
+        if self.w_override is not None:
+            w = np.array(self.w_override, dtype=np.int64)
+        else:
+            j = np.arange(1, self.n + 1, dtype=np.int64)
+            w = (j % self.d) + 1
         w[0] = 0
         return w.astype(np.int32)
 

@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 
 from oracle.oracle import CP, SP, Oracle
 from spock_b200.examples import get_random_system_specs, get_server_heat_specs, get_test_fixture_specs
@@ -398,3 +399,36 @@ def check_offline_device_vs_host(lib, flat, monkeypatch):
     for fh, fd in zip(*out):
         for a, b in zip(fh, fd):
             assert relerr(b, a) < 1e-12 or np.max(np.abs(a)) == 0.0
+
+
+def custom_mode_flat(N, d, nx, nu, seed=3):
+    """A tree whose node modes node_info[j].w are NOT the generator's (j % d) + 1 but a random map (the reference keeps
+    node_info in a plain mutable Vector, scenario_tree.jl:73-81, and ricatti_offline / projection_S1! read w node by node,
+    implicit_l.jl:71-95,610-680): the Riccati factors then differ from node to node inside a stage."""
+    spec = list(get_random_system_specs(N, d, nx, nu))
+    w = np.random.default_rng(seed).integers(1, d + 1, size=spec[0].n).astype(np.int32)
+    w[0] = 0
+    spec[0].w_override = w
+    return flatten_problem(*spec)
+
+
+def check_custom_modes(lib, flat):
+    from spock_b200._lib import check, dptr
+
+    nx, nu = flat.nx, flat.nu
+    check_operators(lib, flat, 0)
+    check_k_steps(lib, flat, CP, 40, factor_mode=0)
+    check_k_steps(lib, flat, SP, 10, factor_mode=0)
+    h, o = Handle(flat, CP, lib=lib), Oracle(flat, CP)
+    for i in sorted({1, 2, 3, flat.n_non_leaf, flat.n_non_leaf + 1, flat.n}):  # per-node factors against ricatti_offline node by node
+        ABK, K, Ri = np.zeros(nx * nx), np.zeros(nu * nx), np.zeros(nu * nu)
+        check(lib, lib.spk_get_factors(h._h, i, None, dptr(ABK), dptr(K), dptr(Ri), None))
+        _, ABKo, Ko, Rc = o.factors(i)
+        if i > 1:
+            assert relerr(ABK.reshape(nx, nx).T, ABKo) < 1e-12
+        if i <= flat.n_non_leaf:
+            assert relerr(K.reshape(nx, nu).T, Ko) < 1e-12
+            assert relerr(Ri.reshape(nu, nu).T, np.linalg.inv(Rc @ Rc.T)) < 1e-11
+    h.close()
+    with pytest.raises(Exception, match="SPK_FACTORS_PER_NODE"):  # per-stage tables cannot represent a mode map
+        Handle(flat, CP, factor_mode=1, lib=lib)

@@ -237,3 +237,11 @@ def test_edge_shapes(emu_lib, N, d, nx, nu):
         check_operators(emu_lib, flat, fm)
         check_k_steps(emu_lib, flat, CP, 30, factor_mode=fm)
         check_k_steps(emu_lib, flat, SP, 10, factor_mode=fm)
+
+
+@pytest.mark.parametrize("N,d,nx,nu", [(5, 2, 4, 3), (4, 3, 3, 2), (3, 4, 5, 5)])
+def test_caller_supplied_mode_map(emu_lib, N, d, nx, nu):
+    """spk_problem.mode_of_node: node modes that are not the generator's (j % d) + 1 -- per-node Riccati recursion on the
+    device (one CTA per node, level by level), the sweeps with per-node mode lookups, against the oracle."""
+    from tests.helpers import check_custom_modes, custom_mode_flat
+    check_custom_modes(emu_lib, custom_mode_flat(N, d, nx, nu))
