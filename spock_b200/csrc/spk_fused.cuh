@@ -266,10 +266,15 @@ SPK_D int spk_child_mode_dev(int d, int c) {  // mode of child ordinal c: (j0 + 
   while (m >= d) m -= d;
   return m;
 }
-// the same with a caller-supplied mode map (spk_problem.mode_of_node): child c of the family whose first child is cfirst
+// W: a caller-supplied mode map (spk_problem.mode_of_node) replaces the generator's; child c of the family whose first
+// child is cfirst.  A template parameter and not a run-time test of P.w: the instantiations for the generator's map stay
+// exactly the kernels that were tuned and verified, and the map costs them nothing (with a run-time branch here the
+// specialised spk_k_bwd<10,10,4,64> faulted on the GENERATOR's map -- invalid address space, every d = 4 case -- while the
+// runtime-size instantiation and the mode-map cases ran).  Only the runtime-size kernels are instantiated with W.
+template <bool W>
 SPK_D int spk_mode_c(const SpkPtrs &P, int d, long cfirst, int c) {
-  if (__builtin_expect(P.w != nullptr, 0)) return P.w[cfirst + c];
-  return spk_child_mode_dev(d, c);
+  if constexpr (W) return P.w[cfirst + c];
+  else return spk_child_mode_dev(d, c);
 }
 
 SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
@@ -283,7 +288,7 @@ SPK_HD long spk_bwd_smem_doubles(const SpkDims &D, int T) {
 // NX_, NU_, D_, T_ > 0: sizes fixed at compile time (every loop unrolls, index arithmetic folds); 0: runtime sizes
 // TOP: one level step inside a top-of-tree kernel -- the dependency on the previous step is a grid barrier instead of the
 // kernel boundary, and what other CTAs wrote in the previous step is read past the (incoherent) L1
-template <int NX_, int NU_, int D_, int T_, bool TOP>
+template <int NX_, int NU_, int D_, int T_, bool TOP, bool W>
 SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &A, double *smem, unsigned *gbar, unsigned &gtarget,
                         bool first_step) {
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
@@ -425,7 +430,7 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
       const SpkItem it = (o == tid) ? itB : spk_make_item(o, nu, SB, nx, nu);
       double acc = 0.0;
       for (int c = 0; c < d; ++c)
-        acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_mode_c(P, d, cfirst, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
+        acc += spk_dot_any<PER_BX>(P.Bt + (long)spk_mode_c<W>(P, d, cfirst, c) * nx * nu + it.r, nu, qc + c * nx, it.m0, it.m1, nx);
       partB[o] = acc;
     }
     if constexpr (PAIR) {
@@ -561,17 +566,17 @@ SPK_D void spk_bwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
   }
 }
 
-template <int NX_, int NU_, int D_, int T_>
+template <int NX_, int NU_, int D_, int T_, bool W = false>
 SPK_KERNEL void spk_k_bwd(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
   if (A.gate && *A.gate) return;
   spk_pdl_trigger();
   unsigned dummy = 0;
-  spk_bwd_body<NX_, NU_, D_, T_, false>(D, P, A, smem, nullptr, dummy, true);
+  spk_bwd_body<NX_, NU_, D_, T_, false, W>(D, P, A, smem, nullptr, dummy, true);
 }
 
 // all narrow levels of the backward sweep (plan.t descending) in one launch
-template <int NX_, int NU_, int D_, int T_>
+template <int NX_, int NU_, int D_, int T_, bool W = false>
 SPK_KERNEL void spk_k_bwd_top(SpkDims D, SpkPtrs P, SpkFusedArgs A, SpkTopPlan plan) {
   SPK_SMEM_DECL(double, smem);
   if (A.gate && *A.gate) return;
@@ -581,7 +586,7 @@ SPK_KERNEL void spk_k_bwd_top(SpkDims D, SpkPtrs P, SpkFusedArgs A, SpkTopPlan p
     SpkFusedArgs B = A;
     B.t = plan.t[s]; B.children_are_leaves = plan.leaves[s]; B.p_lo = plan.p_lo[s]; B.p_cnt = plan.p_cnt[s]; B.kshift = plan.kshift[s];
     B.reset_xi = (s == 0) ? A.reset_xi : 0;
-    spk_bwd_body<NX_, NU_, D_, T_, true>(D, P, B, smem, plan.bar, target, s == 0);
+    spk_bwd_body<NX_, NU_, D_, T_, true, W>(D, P, B, smem, plan.bar, target, s == 0);
   }
 }
 
@@ -592,7 +597,7 @@ SPK_HD long spk_fwd_smem_doubles(const SpkDims &D, int T) {
   return 2 + (long)D.d * D.abk_stride + D.k_stride + 2L * (D.nx + D.nu) + R * S + 4;
 }
 
-template <int NX_, int NU_, int D_, int T_, bool TOP>
+template <int NX_, int NU_, int D_, int T_, bool TOP, bool W>
 SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &A, double *smem, unsigned *gbar, unsigned &gtarget,
                         bool first_step) {
   const int nx = NX_ > 0 ? NX_ : D.nx, nu = NX_ > 0 ? NU_ : D.nu, d = NX_ > 0 ? D_ : D.d, T = NX_ > 0 ? T_ : (int)blockDim.x;
@@ -686,7 +691,7 @@ SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
       if (active) {
         if (r < NU_) acc = spk_dot_fixed<PA>(mK + rr, NU_, xb, ss * PA, HC);
         else acc = spk_dot_fixed<PA>(mABK + (long)c * D.abk_stride + rr, NX_, xb, ss * PA, HC) +
-                   spk_dot_fixed<PER_U>(P.B + (long)spk_mode_c(P, d, cfirst, c) * nx * nu + rr, NX_, ds, ss * PER_U, NU_);
+                   spk_dot_fixed<PER_U>(P.B + (long)spk_mode_c<W>(P, d, cfirst, c) * nx * nu + rr, NX_, ds, ss * PER_U, NU_);
       }
       SPK_SYNCTHREADS();  // the first half is consumed: refill it while the second half is processed
       if (more && tid == 0) fetch_half(i0 + gridDim.x, 0);
@@ -715,7 +720,7 @@ SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
           acc = spk_dot_any<PER_X>(mK + rr, nu, xb, it.m0, it.m1, nx);
         } else {
           acc = spk_dot_any<PER_X>(mABK + (long)c * D.abk_stride + rr, nx, xb, it.m0, it.m1, nx) +
-                spk_dot_any<PER_U>(P.B + (long)spk_mode_c(P, d, cfirst, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
+                spk_dot_any<PER_U>(P.B + (long)spk_mode_c<W>(P, d, cfirst, c) * nx * nu + rr, nx, ds, it.k0, it.k1, nu);
         }
         part[o] = acc;
       }
@@ -745,17 +750,17 @@ SPK_D void spk_fwd_body(const SpkDims &D, const SpkPtrs &P, const SpkFusedArgs &
   }
 }
 
-template <int NX_, int NU_, int D_, int T_>
+template <int NX_, int NU_, int D_, int T_, bool W = false>
 SPK_KERNEL void spk_k_fwd_s1(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   SPK_SMEM_DECL(double, smem);
   if (A.gate && *A.gate) return;
   spk_pdl_trigger();
   unsigned dummy = 0;
-  spk_fwd_body<NX_, NU_, D_, T_, false>(D, P, A, smem, nullptr, dummy, true);
+  spk_fwd_body<NX_, NU_, D_, T_, false, W>(D, P, A, smem, nullptr, dummy, true);
 }
 
 // all narrow levels of the forward sweep (plan.t ascending) in one launch
-template <int NX_, int NU_, int D_, int T_>
+template <int NX_, int NU_, int D_, int T_, bool W = false>
 SPK_KERNEL void spk_k_fwd_top(SpkDims D, SpkPtrs P, SpkFusedArgs A, SpkTopPlan plan) {
   SPK_SMEM_DECL(double, smem);
   if (A.gate && *A.gate) return;
@@ -764,7 +769,7 @@ SPK_KERNEL void spk_k_fwd_top(SpkDims D, SpkPtrs P, SpkFusedArgs A, SpkTopPlan p
   for (int s = 0; s < plan.n; ++s) {
     SpkFusedArgs B = A;
     B.t = plan.t[s]; B.children_are_leaves = plan.leaves[s]; B.p_lo = plan.p_lo[s]; B.p_cnt = plan.p_cnt[s]; B.kshift = plan.kshift[s];
-    spk_fwd_body<NX_, NU_, D_, T_, true>(D, P, B, smem, plan.bar, target, s == 0);
+    spk_fwd_body<NX_, NU_, D_, T_, true, W>(D, P, B, smem, plan.bar, target, s == 0);
   }
 }
 

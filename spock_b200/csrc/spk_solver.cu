@@ -592,14 +592,23 @@ static int fused_setup(spk_handle *h) {
   h->k_dual2 = spk_k_dual2<0, 0, 0>;
   h->k_bwd_top = spk_k_bwd_top<0, 0, 0, 0>;
   h->k_fwd_top = spk_k_fwd_top<0, 0, 0, 0>;
+  if (h->custom_modes) {
+    h->k_bwd = spk_k_bwd<0, 0, 0, 0, true>;
+    h->k_fwd = spk_k_fwd_s1<0, 0, 0, 0, true>;
+    h->k_bwd_top = spk_k_bwd_top<0, 0, 0, 0, true>;
+    h->k_fwd_top = spk_k_fwd_top<0, 0, 0, 0, true>;
+  }
   const char *gen = getenv("SPK_GENERIC_KERNELS");
 #ifndef SPK_HOST_EMU
   if (!(gen && gen[0] == '1'))
     for (const spk_shape_getter_t getter : g_shapes) {
       const SpkShapeEntry &e = *getter();
       if (e.nx == D.nx && e.nu == D.nu && e.d == D.d) {
-        Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd; h->k_dual = e.dual; h->k_dual2 = e.dual2;
-        h->k_bwd_top = e.bwd_top; h->k_fwd_top = e.fwd_top;
+        h->k_dual = e.dual; h->k_dual2 = e.dual2;
+        if (!h->custom_modes) {  // (a mode map runs the runtime-size sweeps: see spk_mode_c)
+          Tb = e.Tb; Tf = e.Tf; h->k_bwd = e.bwd; h->k_fwd = e.fwd;
+          h->k_bwd_top = e.bwd_top; h->k_fwd_top = e.fwd_top;
+        }
         h->shape_specialised = true;
         // register-resident dual kernel: Diagonal sqrt-costs, risk cone and branching within one warp
         const char *e3 = getenv("SPK_NO_DUAL3");
