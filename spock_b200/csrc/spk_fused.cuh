@@ -1403,6 +1403,9 @@ SPK_KERNEL void spk_k_dual2(SpkDims D, SpkPtrs P, SpkFusedArgs A, int F, long fa
 SPK_CONSTEXPR_HD int spk_dual3_group(int nx, int nu, int d) {
   int m = nx > nu ? nx : nu;
   if (m > 32) return 32;
+  // nx, nu in 9..10: THREE families per warp on lanes 0 .. 3m-1 (the other lanes retire at once) instead of two in
+  // groups of 16 with 6 idle lanes each -- the kernel is bound by instruction issue at these sizes
+  if (m > 8 && m <= 10 && d <= m) return m;
   int g = 8;
   while (g < m || g < d) g <<= 1;
   return g;
@@ -1415,10 +1418,10 @@ SPK_D void spk_atomic_max_lazy(double *addr, double val) {
 
 // exact maximum of non-negative doubles over the warp with two integer REDUX operations (high words, then the low
 // words of the lanes that hold the maximal high word)
-SPK_D double spk_warp_max_nonneg(double v) {
+SPK_D double spk_warp_max_nonneg(double v, unsigned mask = 0xffffffffu) {
   const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  const unsigned mh = __reduce_max_sync(mask, hi);
+  const unsigned ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
   return __hiloint2double((int)mh, (int)ml);
 }
 
@@ -1434,10 +1437,27 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
   // redundant atomic at the end, never a missed one)
   const double seen_xi1 = __ldcg(A.xi + 0), seen_xi2 = __ldcg(A.xi + 1);
   constexpr int G = spk_dual3_group(NX, NU, DD), FPW = 32 / G;  // lanes per family, families per warp
+  constexpr bool POW2 = (G & (G - 1)) == 0;                     // (else: groups of G consecutive lanes, 32 - FPW G lanes unused)
+  constexpr unsigned MASK = POW2 ? 0xffffffffu : ((1u << (FPW * G)) - 1u);
+  constexpr int GP2 = G > 16 ? 16 : (G > 8 ? 8 : (G > 4 ? 4 : 2));  // largest power of two below a non-power-of-two G
   constexpr int RX = (NX + G - 1) / G, RU = (NU + G - 1) / G, CD = UC ? 1 : DD, LD = LEAVES ? DD : 1;
   __shared__ double s_red[3 * 4];
   const int wlane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int lane = wlane & (G - 1);  // lane within the family's group
+  if (!POW2 && wlane >= FPW * G) return;  // (exited lanes count as arrived at the barrier of the <r,Pr> fold)
+  const int lane = POW2 ? (wlane & (G - 1)) : (wlane % G);  // lane within the family's group
+  const int gbase = wlane - lane;
+  // sum over the group on every lane of it: butterflies, or (G not a power of two) a fold towards lane 0 and a broadcast
+#define SPK_GSUM_STEP(x_, o_)                                                \
+  {                                                                          \
+    if constexpr (POW2) (x_) += __shfl_xor_sync(0xffffffffu, (x_), (o_));    \
+    else {                                                                   \
+      const double t_ = __shfl_down_sync(MASK, (x_), (o_));                  \
+      if (lane + (o_) < G) (x_) += t_;                                       \
+    }                                                                        \
+  }
+#define SPK_GSUM_DONE(x_) \
+  { if constexpr (!POW2) (x_) = __shfl_sync(MASK, (x_), gbase); }
+#define SPK_GBCAST(x_, src_) (POW2 ? __shfl_sync(0xffffffffu, (x_), (src_), G) : __shfl_sync(MASK, (x_), gbase + (src_)))
   const int ny = D.ny;
   const double gamma = A.gamma, sigma = A.sigma, inv_sigma = A.inv_sigma, inv_gamma = A.inv_gamma;
   const double *__restrict__ z = A.z, *__restrict__ zb = A.zbar, *__restrict__ v = A.v;
@@ -1597,12 +1617,17 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     }
   }
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) {
+  for (int o = POW2 ? G / 2 : GP2; o > 0; o >>= 1) {
 #pragma unroll
     for (int c = 0; c < DD; ++c) {
-      part[c] += __shfl_xor_sync(0xffffffffu, part[c], o);
-      if (LEAVES) partl[c] += __shfl_xor_sync(0xffffffffu, partl[c], o);
+      SPK_GSUM_STEP(part[c], o);
+      if (LEAVES) SPK_GSUM_STEP(partl[c], o);
     }
+  }
+#pragma unroll
+  for (int c = 0; c < DD; ++c) {
+    SPK_GSUM_DONE(part[c]);
+    if (LEAVES) SPK_GSUM_DONE(partl[c]);
   }
   // lane c turns (t_c, ||.||_c) into the SOC projection coefficients of child c (risk_measures.jl:57-70):
   // Proj(t, x) = (pt, a x) with a = 1 | 0 | t'/||x||, pt = t | 0 | t'
@@ -1647,9 +1672,10 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
         for (int c2 = 0; c2 < c; ++c2) off += D.cone_dim[c2];
         double sq = (lane > off && lane < off + D.cone_dim[c]) ? W1 * W1 : 0.0;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        for (int o = POW2 ? G / 2 : GP2; o > 0; o >>= 1) SPK_GSUM_STEP(sq, o);
+        SPK_GSUM_DONE(sq);
         const double snrm = sqrt(sq);
-        const double st = __shfl_sync(0xffffffffu, W1, off, G);
+        const double st = SPK_GBCAST(W1, off);
         int mode;
         double tp;
         spk_soc_coeffs(st, snrm, mode, tp);
@@ -1660,10 +1686,12 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     if (lane < ny) SPK_FIN3(vb + i0 * ny + lane, W1, v1o, dy, pr, dv1);
     double bwy = b_k * wy, bdy = b_k * dy;
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-      bwy += __shfl_xor_sync(0xffffffffu, bwy, o);
-      bdy += __shfl_xor_sync(0xffffffffu, bdy, o);
+    for (int o = POW2 ? G / 2 : GP2; o > 0; o >>= 1) {
+      SPK_GSUM_STEP(bwy, o);
+      SPK_GSUM_STEP(bdy, o);
     }
+    SPK_GSUM_DONE(bwy);
+    SPK_GSUM_DONE(bdy);
     const double w2 = v2o * inv_sigma + (ws_i - bwy);  // L! :214-222
     const double v2new = sigma * (w2 - (w2 >= 0 ? w2 : 0.0));
     dv2 = v2new - v2o;
@@ -1699,7 +1727,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
 #pragma unroll
   for (int c = 0; c < DD; ++c) {
     const long jm = cfirst - 1 + c;
-    const double a = __shfl_sync(0xffffffffu, my_a, c, G);
+    const double a = SPK_GBCAST(my_a, c);
     double *vb3 = vb + D.vo[2] + jm * NX, *vb4 = vb + D.vo[3] + jm * NU;
 #pragma unroll
     for (int r = 0; r < RX; ++r) {
@@ -1721,7 +1749,7 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
     }
     if (LEAVES) {  // leaf children: SOC(nx+2) on (v13; v11, v12) (:768-800), v14 box (:804-809)
       const long l = lfirst + c;
-      const double al = __shfl_sync(0xffffffffu, my_al, c, G);
+      const double al = SPK_GBCAST(my_al, c);
       double *vb11 = vb + D.vo[7] + l * NX, *vb14 = vb + D.vo[10] + l * NX;
 #pragma unroll
       for (int r = 0; r < RX; ++r) {
@@ -1765,15 +1793,28 @@ __global__ void spk_k_dual3(SpkDims D, SpkPtrs P, SpkFusedArgs A, long fam_lo, l
 #undef SPK_Z3
 #undef SPK_XON
 #undef SPK_UON
+#undef SPK_GSUM_STEP
+#undef SPK_GSUM_DONE
+#undef SPK_GBCAST
   // ---- folds: maxima by (lazy) atomicMax; <r, P r> as one deterministic partial per CTA
   if (!valid) my_pn = 0.0;
-  const double m1 = spk_warp_max_nonneg(my_xi1), m2 = spk_warp_max_nonneg(my_xi2);
+  const double m1 = spk_warp_max_nonneg(my_xi1, MASK), m2 = spk_warp_max_nonneg(my_xi2, MASK);
   if (wlane == 0) {
     if (spk_bits_nn(m1) > spk_bits_nn(seen_xi1)) spk_atomic_max_nonneg(A.xi + 0, m1);
     if (spk_bits_nn(m2) > spk_bits_nn(seen_xi2)) spk_atomic_max_nonneg(A.xi + 1, m2);
   }
   if (PN) {
-    const double ps = spk_warp_sum(my_pn);
+    double ps;
+    if constexpr (POW2) {
+      ps = spk_warp_sum(my_pn);
+    } else {  // fold towards lane 0 over the FPW G live lanes
+      ps = my_pn;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_down_sync(MASK, ps, o);
+        if (wlane + o < FPW * G) ps += t;
+      }
+    }
     if (wlane == 0) s_red[warp] = ps;
     __syncthreads();
     if (threadIdx.x == 0) {
