@@ -43,8 +43,14 @@ def _nvcc() -> str:
 def shapes():
     """(nx, nu, d, threads_bwd, threads_fwd) per line of csrc/spk_shapes.def"""
     txt = open(os.path.join(CSRC, "spk_shapes.def")).read()
-    return [tuple(int(x) for x in m) for m in
-            re.findall(r"^SPK_SHAPE_X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt, flags=re.M)]
+    out = [tuple(int(x) for x in m) for m in
+           re.findall(r"^SPK_SHAPE_X\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt, flags=re.M)]
+    # SPK_SHAPE_THREADS="20,20,2:64,64;10,10,4:32,32": thread counts of development variants (tools/ab_variants.sh)
+    for item in filter(None, os.environ.get("SPK_SHAPE_THREADS", "").split(";")):
+        key, val = item.split(":")
+        key, val = tuple(int(x) for x in key.split(",")), tuple(int(x) for x in val.split(","))
+        out = [s[:3] + val if s[:3] == key else s for s in out]
+    return out
 
 
 def _units():
@@ -81,8 +87,11 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", extra_f
     """variant/extra_flags: development builds with extra nvcc flags into csrc/_variants/<variant>.so (tuning sweeps)."""
     global OBJ, LIB, NVCC_FLAGS
     if variant:
+        default_obj = OBJ
         OBJ = os.path.join(CSRC, "_variants", variant + "_obj")
         LIB = os.path.join(CSRC, "_variants", variant + ".so")
+        if not os.path.exists(OBJ) and os.path.exists(default_obj):
+            shutil.copytree(default_obj, OBJ)  # units whose flags and sources are unchanged are not recompiled
         NVCC_FLAGS = NVCC_FLAGS + list(extra_flags)
     if not force and not needs_build():
         return LIB
