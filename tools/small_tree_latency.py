@@ -1,6 +1,6 @@
 """Latency-bound configurations: microseconds per CP / SuperMann pass and kernel launches per
 pass on small trees, device-resident loop (default) vs host-driven loop (SPK_HOST_LOOP=1).
-usage: python tools/small_tree_latency.py > latency.jsonl"""
+usage: [SPK_LAT_FACTOR_MODE=0|1] python tools/small_tree_latency.py > latency.jsonl   (0: per-node factors, 1: per-stage tables)"""
 import json
 import os
 import subprocess
@@ -19,9 +19,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
 
     for N, nx, d in CASES:
         flat = flatten_problem(*get_server_heat_specs(N, nx, d))
-        row = {"N": N, "nx": nx, "d": d, "nodes": flat.n, "host_loop": os.environ.get("SPK_HOST_LOOP", "0")}
+        row = {"N": N, "nx": nx, "d": d, "nodes": flat.n, "host_loop": os.environ.get("SPK_HOST_LOOP", "0"),
+               "factor_mode": int(os.environ.get("SPK_LAT_FACTOR_MODE", "1"))}
         for alg, name in ((1, "cp"), (2, "sp")):
-            h = Handle(flat, alg, factor_mode=1)
+            h = Handle(flat, alg, factor_mode=int(os.environ.get("SPK_LAT_FACTOR_MODE", "1")))
             x0 = 0.1 * np.ones(nx)
             h.solve(x0, tol=1e-3)  # warm-up: graph capture, instruction caches
             l0 = h.launch_count()
@@ -31,6 +32,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
             h.close()
         print(json.dumps(row), flush=True)
 else:
-    for hl in ("0", "1"):
+    for hl in os.environ.get("SPK_LAT_LOOPS", "0,1").split(","):
         env = dict(os.environ, SPK_HOST_LOOP=hl)
         subprocess.run([sys.executable, __file__, "--child"], env=env, check=True)
