@@ -814,6 +814,80 @@ SPK_KERNEL void spk_k_s2t(SpkDims D, SpkPtrs P, SpkFusedArgs A) {
   if (i0 == 0) A.zbar[D.zo[2]] = A.z[D.zo[2]] - gamma * v2i - gamma;
 }
 
+// 3b. The same for ONE contiguous node range and one risk measure for all nodes (every single-GPU reference workload),
+// staged through shared memory.  With a thread per node the direct version's gathers and scatters are strided (ny or d
+// doubles per thread: a warp-level access touches 8-20 cache lines) and the projector is read entry by entry from L1:
+// ncu counts ~1200 L1 wavefronts per warp, which is what bounds it (0.82 ms per pass at config 5, 22 % of the HBM rate
+// for its bytes).  Here the CTA's 128 nodes are loaded and stored with coalesced accesses (their entries are contiguous
+// in every segment), the combination z - gamma L'v happens on the way into shared memory (rows padded to an odd length:
+// conflict-free row reads), and the projector arrives as a kernel parameter, so its entries are constant-bank operands
+// of the FMAs instead of loads.  Arithmetic and its order are those of spk_k_s2t.
+template <int NY_, int DD_>
+struct SpkLsMat {
+  double m[(NY_ + 2 * DD_) * (NY_ + 2 * DD_)];  // column-major like P.ls
+};
+#if !SPK_EMU
+template <int NY_, int DD_>
+__launch_bounds__(128)
+__global__ void spk_k_s2t_st(SpkDims D, SpkPtrs P, SpkFusedArgs A, const __grid_constant__ SpkLsMat<NY_, DD_> M) {
+  if (A.gate && *A.gate) return;
+  constexpr int T = 128, NLS = NY_ + 2 * DD_, NYP = NY_ | 1, DP = DD_ | 1;
+  __shared__ double sy[T * NYP], ss[T * DP], st[T * DP];
+  const int tid = threadIdx.x;
+  const long total = A.r_prefix[1], off = (long)blockIdx.x * T;
+  if (off == 0 && tid == 0 && A.topbar) {  // arrival counters of this evaluation's top-of-tree kernels
+    A.topbar[0] = 0u; A.topbar[1] = 0u; A.topbar[2] = 0u;
+  }
+  if (off >= total) return;
+  const long b0 = A.r_start[0] + off, c0 = (long)DD_ * b0 + 1;  // the CTA's first node and that node's first child
+  const int cnt = (int)(total - off < T ? total - off : T);
+  const double gamma = A.gamma;
+  const double *__restrict__ z = A.z, *__restrict__ v = A.v;
+  for (int j = tid; j < cnt * NY_; j += T) {  // (z - gamma L'v) on y_i (L_transpose! :423-431)
+    const int n = j / NY_, k = j - n * NY_;
+    sy[n * NYP + k] = z[D.zo[4] + b0 * NY_ + j] - gamma * (v[b0 * NY_ + j] - P.b[k] * v[D.vo[1] + b0 + n]);
+  }
+  for (int j = tid; j < cnt * DD_; j += T) {  // ... on s_c and tau_c of the children (:433-448)
+    const int n = j / DD_, c = j - n * DD_;
+    const long j0 = c0 + j;
+    const double lt = (j0 < D.nnl) ? v[D.vo[1] + j0] : 0.5 * v[D.vo[8] + (j0 - D.nnl)] + 0.5 * v[D.vo[9] + (j0 - D.nnl)];
+    ss[n * DP + c] = z[D.zo[2] + j0] - gamma * lt;
+    st[n * DP + c] = z[D.zo[3] + j0 - 1] - gamma * (0.5 * v[D.vo[4] + j0 - 1] + 0.5 * v[D.vo[5] + j0 - 1]);
+  }
+  __syncthreads();
+  if (tid < cnt) {  // projection_S2! :688-727 for the thread's node, results back into its own rows
+    double in[NLS];
+#pragma unroll
+    for (int k = 0; k < NY_; ++k) in[k] = sy[tid * NYP + k];
+#pragma unroll
+    for (int c = 0; c < DD_; ++c) {
+      in[NY_ + c] = ss[tid * DP + c];
+      in[NY_ + DD_ + c] = st[tid * DP + c];
+    }
+#pragma unroll
+    for (int k = 0; k < NLS; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int m = 0; m < NLS; ++m) acc += M.m[k + m * NLS] * in[m];
+      if (k < NY_) sy[tid * NYP + k] = acc;
+      else if (k < NY_ + DD_) ss[tid * DP + (k - NY_)] = acc;
+      else st[tid * DP + (k - NY_ - DD_)] = acc;
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < cnt * NY_; j += T) {
+    const int n = j / NY_, k = j - n * NY_;
+    A.zbar[D.zo[4] + b0 * NY_ + j] = sy[n * NYP + k];
+  }
+  for (int j = tid; j < cnt * DD_; j += T) {
+    const int n = j / DD_, c = j - n * DD_;
+    A.zbar[D.zo[2] + c0 + j] = ss[n * DP + c];
+    A.zbar[D.zo[3] + c0 + j - 1] = st[n * DP + c];
+  }
+  if (b0 == 0 && tid == 0) A.zbar[D.zo[2]] = z[D.zo[2]] - gamma * v[D.vo[1]] - gamma;  // prox_f!'s s_1 -= gamma (:741)
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------ 4. dual blocks
 
 SPK_D void spk_soc_coeffs(double t, double nrm, int &mode, double &tp) {  // risk_measures.jl:57-70

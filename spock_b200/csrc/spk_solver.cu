@@ -219,6 +219,7 @@ struct spk_handle {
   bool peer_ok = false;
   long lenA = 0, lenB = 0;
   bool graph_nccl = false;  // SPK_GRAPH_NCCL=1: capture the cut-level exchanges inside the evaluation's CUDA graph (one graph per evaluation)
+  bool use_s2_staged = true;  // SPK_NO_S2_STAGED=1: the direct thread-per-node S2 kernel everywhere (cross-check)
   bool use_pdl = true;  // SPK_NO_PDL=1: plain stream order between the level launches of the S1 sweeps
 #ifndef SPK_HOST_EMU
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; };
@@ -713,6 +714,8 @@ static int fused_setup(spk_handle *h) {
 #endif
   h->fused_ok = true;
   {
+    const char *ns2 = getenv("SPK_NO_S2_STAGED");
+    h->use_s2_staged = !(ns2 && ns2[0] == '1');
     const char *np = getenv("SPK_NO_PDL");
     h->use_pdl = !(np && np[0] == '1');
   }
@@ -782,6 +785,16 @@ static int launch_exchange(spk_handle *h, int kind, double *vec, long vlen) {
 // `parts`: 1 = kernels up to the cut-level exchange, 2 = that exchange (all-gather of the subtree roots' q), 4 = the remaining
 // kernels, 8 = the exchange of the subtree roots' vbar2.  All (15) for a plain launch; the multi-GPU graph replay captures the
 // kernel segments 1 and 4 separately and issues the two NCCL exchanges between them on the stream.
+#ifndef SPK_HOST_EMU
+// S2 staged through shared memory (spk_k_s2t_st): the projector of the one risk measure travels as a kernel parameter
+template <int NY_, int DD_>
+static void launch_s2t_staged(spk_handle *h, const SpkDims &D, const SpkFusedArgs &A, long owned) {
+  SpkLsMat<NY_, DD_> M;
+  std::copy(h->ls_host.begin(), h->ls_host.begin() + (size_t)(NY_ + 2 * DD_) * (NY_ + 2 * DD_), M.m);
+  spk_k_s2t_st<NY_, DD_><<<grid_for(owned, 128), 128, 0, h->stream>>>(D, h->P, A, M);
+}
+#endif
+
 static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out, double gamma, double sigma, int pnorm_slot,
                              int parts = 15) {
   const SpkDims &D = h->D;
@@ -809,7 +822,24 @@ static int op_T_fused_launch(spk_handle *h, const double *zv_in, double *zv_out,
       else if (D.ny == 8 && D.d == 3) ks2 = spk_k_s2t<8, 3>;
       else if (D.ny == 10 && D.d == 4) ks2 = spk_k_s2t<10, 4>;
     }
-    SPK_LAUNCH(ks2, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
+    bool staged = false;
+#ifndef SPK_HOST_EMU
+    // one contiguous node range and one risk measure for all nodes: the shared-memory-staged version (spk_k_s2t_st)
+    // (not on small trees: its 2.6 KB of extra kernel parameters cost a launch ~1 us, more than the kernel saves there;
+    // SPK_MAX_CTAS, the test switch that makes small trees exercise the steady-state paths, keeps it on)
+    if (h->use_s2_staged && A.n_ranges == 1 && !D.rms_per_node && (long)h->ls_host.size() == (long)D.nls * D.nls &&
+        (owned >= 4096 || h->max_ctas > 0)) {
+      staged = true;
+      if (D.ny == 5 && D.d == 2) launch_s2t_staged<5, 2>(h, D, A, owned);
+      else if (D.ny == 7 && D.d == 3) launch_s2t_staged<7, 3>(h, D, A, owned);
+      else if (D.ny == 9 && D.d == 4) launch_s2t_staged<9, 4>(h, D, A, owned);
+      else if (D.ny == 6 && D.d == 2) launch_s2t_staged<6, 2>(h, D, A, owned);
+      else if (D.ny == 8 && D.d == 3) launch_s2t_staged<8, 3>(h, D, A, owned);
+      else if (D.ny == 10 && D.d == 4) launch_s2t_staged<10, 4>(h, D, A, owned);
+      else staged = false;
+    }
+#endif
+    if (!staged) SPK_LAUNCH(ks2, grid_for(owned, b), b, 0, h->stream, D, h->P, A);
     COUNT_LAUNCH(h, PC_S2);
   }
   // levels 0 .. t_top of both sweeps run in one single-CTA launch (single GPU, tensor-pipe kernels)
@@ -1761,6 +1791,10 @@ static int create_impl(const spk_problem *p, spk_handle *h) {
     SPK_TRY(rc);
     if (bad) return fail(SPK_ERR_INVALID, "kernel projector: the risk measure has E = F = 0");
     h->P.ls = dls;
+    if (n_rms == 1) {  // host copy of the one projector: spk_k_s2t_st takes it as a kernel parameter
+      h->ls_host.resize(nls2);
+      SPK_TRY(rt_d2h(h->ls_host.data(), dls, sizeof(double) * nls2, h->stream));
+    }
   }
   SPK_TRY(dev_alloc(h, &h->x0, nx)); h->P.x0 = h->x0;
 

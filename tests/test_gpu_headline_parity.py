@@ -94,6 +94,26 @@ def test_persistent_loop_body_with_capped_grid(cuda_lib, nx, nu, d, N, monkeypat
         assert np.array_equal(zc, zf) and np.array_equal(vc, vf) and xc == xf
 
 
+@pytest.mark.parametrize("d,N,risk", [(2, 7, "avar"), (3, 5, "avar"), (4, 5, "avar"), (2, 7, "l2ball"), (3, 5, "l2ball"), (4, 5, "l2ball")])
+def test_staged_s2_kernel_matches_direct_and_oracle(cuda_lib, d, N, risk, monkeypatch):
+    """spk_k_s2t_st (coalesced shared-memory staging, projector as a kernel parameter; one node range, one risk measure,
+    >= 4096 non-leaf nodes or SPK_MAX_CTAS) against the direct thread-per-node kernel: same arithmetic in the same order,
+    so bitwise equal iterates -- for every (ny, d) it is instantiated for -- and both against the oracle (projection_S2!,
+    implicit_l.jl:688-727).  The last CTA is partial (the non-leaf count is not a multiple of 128)."""
+    kw = {"risk": "l2ball"} if risk == "l2ball" else {}
+    flat = flatten_problem(*get_server_heat_specs(N, 10, d, **kw))
+    rng = np.random.default_rng(17 * d + N)
+    o = Oracle(flat, CP)
+    z0, v0 = 0.3 * rng.standard_normal(o.nz), 0.3 * rng.standard_normal(o.nv)
+    monkeypatch.setenv("SPK_MAX_CTAS", "3")
+    monkeypatch.setenv("SPK_NO_S2_STAGED", "0")
+    _, staged = _run_pair(cuda_lib, flat, CP, 5, z0=z0, v0=v0)
+    monkeypatch.setenv("SPK_NO_S2_STAGED", "1")
+    _, direct = _run_pair(cuda_lib, flat, CP, 5, z0=z0, v0=v0)
+    for (zs, vs, xs), (zd, vd, xd) in zip(staged, direct):
+        assert np.array_equal(zs, zd) and np.array_equal(vs, vd) and xs == xd
+
+
 # ------------------------------------------------------------------------------------------------ SOC branches
 
 def _set_dual_variant(monkeypatch, variant):
