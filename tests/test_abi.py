@@ -79,3 +79,17 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
                 assert "hostemu" not in src or f in ("_lib.py", "spk_runtime.h"), f
+
+
+def test_shape_table_and_thread_variants(monkeypatch):
+    """spk_shapes.def: threads per family are whole warps; SPK_SHAPE_THREADS (development variants for same-box A/B
+    timing, tools/ab_variants.sh) overrides exactly the named shape."""
+    from spock_b200 import build
+    monkeypatch.delenv("SPK_SHAPE_THREADS", raising=False)
+    base = build.shapes()
+    assert (50, 20, 2) in [s[:3] for s in base] and all(s[3] % 32 == 0 and s[4] % 32 == 0 for s in base)
+    monkeypatch.setenv("SPK_SHAPE_THREADS", "20,20,2:64,96;10,10,4:32,32")
+    var = build.shapes()
+    assert [s for s in var if s[:3] == (20, 20, 2)] == [(20, 20, 2, 64, 96)]
+    assert [s for s in var if s[:3] == (10, 10, 4)] == [(10, 10, 4, 32, 32)]
+    assert [s for s in var if s[:3] not in ((20, 20, 2), (10, 10, 4))] == [s for s in base if s[:3] not in ((20, 20, 2), (10, 10, 4))]
